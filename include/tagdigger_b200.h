@@ -1,0 +1,188 @@
+/*
+ * tagdigger_b200 -- C ABI of the B200-native TagDigger read-counting path.
+ *
+ * The reference (lvclark/tagdigger, pure Python) has no FFI layer.  The seam this
+ * library plugs into is the plain call
+ *     tagdigger_fun.find_tags_fastq(fqfile, barcodes, tags, cutsite, maxreads)
+ * (tagdigger_fun.py:192-277) made once per FASTQ file from
+ * tagdigger_script.py:123-126 and tagdigger_interactive.py:110-112, whose
+ * results are merged by combineReadCounts (tagdigger_fun.py:1061-1098).
+ * Each entry point below names the reference lines it replaces.  Signatures use
+ * plain pointers and sizes only; the Python binding is ctypes.
+ *
+ * Conventions
+ *   - every function returns TDG_OK (0) or a negative TDG_ERR_* code and never
+ *     throws or aborts; tdg_last_error() returns the message for the last failure;
+ *   - the caller owns every host buffer it passes and every output buffer;
+ *     the context owns all device and pinned memory it allocates;
+ *   - a context is bound to one CUDA device and is not thread-safe: one
+ *     submitting host thread per context (= per GPU);
+ *   - sequences are ASCII A/C/G/T (upper case), concatenated, with an offsets
+ *     array of n+1 entries (CSR style);
+ *   - there is no CPU implementation behind this ABI: without a CUDA device
+ *     tdg_create fails.
+ */
+#ifndef TAGDIGGER_B200_H
+#define TAGDIGGER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDG_ABI_VERSION 1
+
+#define TDG_OK            0
+#define TDG_ERR_CUDA     -1   /* a CUDA runtime call failed (message has the CUDA error string) */
+#define TDG_ERR_ARG      -2   /* invalid argument */
+#define TDG_ERR_IO       -3   /* file could not be opened / read */
+#define TDG_ERR_STATE    -4   /* call made out of order (e.g. submit before begin_file) */
+#define TDG_ERR_NOMEM    -5
+#define TDG_ERR_GZIP     -6   /* not a gzip stream / corrupt stream */
+
+/* flags for tdg_set_tags / tdg_begin_file */
+#define TDG_ANY_BASE      1u  /* the pattern set is the single empty pattern: matches
+                                 iff the next character is A/C/G/T, consuming nothing
+                                 (tagdigger_fun.py:109-110) */
+
+/* what preceded byte 0 of a chunk (tdg_count_device) */
+#define TDG_PREV_NONE     0   /* start of file: byte 0 starts a line */
+#define TDG_PREV_LF       1   /* the previous byte ended a line: byte 0 starts a line */
+#define TDG_PREV_CR       2   /* the previous byte was '\r': it ended a line unless byte 0 is '\n' */
+#define TDG_PREV_OTHER    3   /* byte 0 continues a line that started earlier */
+
+#define TDG_LINE_CHAINED  UINT64_MAX  /* take line_base/prev_kind from the previous chunk on this context */
+
+/* geometry the device-resident entry point needs from its caller */
+#define TDG_TILE_BYTES    16384u
+#define TDG_HALO_BYTES    512u
+
+typedef struct tdg_ctx tdg_ctx;
+
+int         tdg_abi_version(void);
+
+/* Create a context on CUDA device `device`.  `chunk_bytes` is the largest piece
+ * tdg_submit / tdg_count_file move at once (0 = default 64 MiB); no single text
+ * line may be longer than that. */
+int         tdg_create(tdg_ctx **out, int device, size_t chunk_bytes);
+void        tdg_destroy(tdg_ctx *ctx);
+/* Message for the most recent failure on `ctx` (or of tdg_create if ctx is NULL). */
+const char *tdg_last_error(const tdg_ctx *ctx);
+
+/* The effective tag set: what build_sequence_tree(tags, len(tags))
+ * (tagdigger_fun.py:98-113, :233) leaves reachable after its conflict rules,
+ * i.e. a prefix-free list.  col[i] is the column of the count matrix that tag i
+ * feeds (the index the reference's trie would return).  The host computes the
+ * effective set (tagdigger_b200/matchset.py); this call packs it 2 bits per
+ * base and builds the device hash table.  A set that is not prefix-free is
+ * refused (TDG_ERR_ARG). */
+int         tdg_set_tags(tdg_ctx *ctx, const char *bases, const uint64_t *off,
+                         const int32_t *col, uint32_t ntags, uint32_t flags);
+
+/* The int32 count matrix [rows x cols] (mycounts, tagdigger_fun.py:237; rows are
+ * GLOBAL sample rows so the per-file matrices of tagdigger_script.py:123-126
+ * never materialise).  tdg_set_matrix allocates and zeroes it; tdg_bind_matrix
+ * uses caller-owned device memory instead (e.g. a torch tensor that is later
+ * all-reduced with NCCL) and does not touch its contents. */
+int         tdg_set_matrix(tdg_ctx *ctx, uint32_t rows, uint32_t cols);
+int         tdg_bind_matrix(tdg_ctx *ctx, void *dev_int32, uint32_t rows, uint32_t cols);
+int         tdg_zero_matrix(tdg_ctx *ctx);
+
+/* Barcode+cutsite patterns of the file about to be streamed: the effective
+ * (reachable, prefix-free) part of barcut (tagdigger_fun.py:213-219), each with
+ * the matrix row it counts into and the offset at which tag comparison starts
+ * (barcutlen, :209 and :231).  Patterns are at most 32 bases.  Resets the line
+ * counter and the per-file totals. */
+int         tdg_begin_file(tdg_ctx *ctx, const char *bases, const uint32_t *off,
+                           const int32_t *row, const uint32_t *tag_off,
+                           uint32_t npat, uint32_t flags);
+
+/* Stream raw (uncompressed) FASTQ bytes from HOST memory: H2D copies and the
+ * counting kernel, pipelined over `chunk_bytes` pieces.  Successive calls for one
+ * file must pass the file's bytes in order; a trailing partial line is carried
+ * over to the next call inside the context.  Returns once `bytes` may be reused
+ * (kernels may still be running).  `reads_limit` is the number of reads of this
+ * file to process in total (the reference's maxreads, :272-273, converted by the
+ * host to max(1, ceil(maxreads))).  Replaces the loop at :250-274. */
+int         tdg_submit(tdg_ctx *ctx, const void *bytes, size_t n, uint64_t reads_limit);
+/* End of the current file: processes the carried partial last line. */
+int         tdg_end_file(tdg_ctx *ctx, uint64_t reads_limit);
+
+/* One chunk that is already resident in DEVICE memory (16-byte aligned).  The
+ * allocation behind `dev_bytes` must extend to at least
+ *   round_up(n, TDG_TILE_BYTES) + TDG_HALO_BYTES
+ * bytes (contents past n are ignored).  `line_base` is the index the next line
+ * START receives and `prev_kind` (TDG_PREV_*) says what preceded byte 0; pass
+ * TDG_LINE_CHAINED to continue from the previous chunk on this context.  A line
+ * that is cut by the end of the chunk is matched against the bytes present only,
+ * so callers cut chunks at line ends (tdg_submit does).  Asynchronous. */
+int         tdg_count_device(tdg_ctx *ctx, const void *dev_bytes, size_t n,
+                             uint64_t line_base, int prev_kind, uint64_t reads_limit);
+
+/* Count only the line ends of a device-resident chunk (no matching): fills
+ * state[0] = line_base for the chunk that follows, state[1] = its prev_kind.
+ * Used to shard one file across GPUs.  Synchronises. */
+int         tdg_count_lines_device(tdg_ctx *ctx, const void *dev_bytes, size_t n,
+                                   uint64_t line_base, int prev_kind, uint64_t state[2]);
+
+/* Whole file: open (zlib inflate on a host thread when `gz` is non-zero -- the
+ * reference decides gz by the last two characters of the name, :240; the
+ * binding passes that decision), stream through pinned buffers, count.
+ * totals: reads, reads with barcode+cutsite, reads with tag, text lines. */
+int         tdg_count_file(tdg_ctx *ctx, const char *path, int gz,
+                           uint64_t reads_limit, uint64_t totals[4]);
+
+/* Wait for all submitted work. */
+int         tdg_sync(tdg_ctx *ctx);
+/* Running totals since the last tdg_begin_file (synchronises): reads, reads with
+ * barcode+cutsite, reads with tag, text lines started. */
+int         tdg_file_totals(tdg_ctx *ctx, uint64_t totals[4]);
+/* Synchronise and copy the matrix to host (`out` may be NULL to skip). */
+int         tdg_read_matrix(tdg_ctx *ctx, int32_t *out);
+
+/* Device pointer of the matrix and the CUDA stream the kernels run on, so the
+ * caller can all-reduce the matrix in place (NCCL) right behind the last kernel:
+ * the multi-GPU replacement for the sum in combineReadCounts (:1081-1097). */
+void       *tdg_matrix_device_ptr(tdg_ctx *ctx);
+void       *tdg_stream(tdg_ctx *ctx);
+/* Make the context's stream wait for work already queued on `other_stream`, or
+ * `other_stream` wait for the context's stream (handles are cudaStream_t passed
+ * as void*; NULL is the legacy default stream), for in-stream collectives. */
+int         tdg_stream_wait(tdg_ctx *ctx, void *other_stream);
+int         tdg_other_stream_wait(tdg_ctx *ctx, void *other_stream);
+
+/* Pinned host memory for callers that want tdg_submit to DMA straight from
+ * their buffer. */
+void       *tdg_host_alloc(tdg_ctx *ctx, size_t n);
+void        tdg_host_free(tdg_ctx *ctx, void *p);
+/* Plain device memory (for tdg_count_device callers without another allocator). */
+void       *tdg_device_alloc(tdg_ctx *ctx, size_t n);
+void        tdg_device_free(tdg_ctx *ctx, void *p);
+int         tdg_memcpy_h2d(tdg_ctx *ctx, void *dev, const void *host, size_t n);
+int         tdg_memcpy_d2h(tdg_ctx *ctx, void *host, const void *dev, size_t n);
+
+/* Number of kernels this context has launched (bench.py's gpu_launches). */
+uint64_t    tdg_launch_count(const tdg_ctx *ctx);
+/* Device time in milliseconds of the counting kernels launched between
+ * tdg_timing_begin and tdg_timing_end (CUDA events on the context's stream,
+ * one pair per kernel launch; at most 4096 launches).  tdg_timing_end
+ * synchronises; *nlaunch receives the number of kernels timed. */
+int         tdg_timing_begin(tdg_ctx *ctx);
+int         tdg_timing_end(tdg_ctx *ctx, double *kernel_ms, uint32_t *nlaunch);
+
+/* Host-side self test of the packed tables: looks one read (a sequence line as
+ * found in the file, without its line end) up in the tables exactly as the
+ * kernel does (same inline code compiled for the host).  Returns the matrix
+ * cell (row*cols+col), -1 for barcode but no tag, -2 for no barcode.  For unit
+ * tests of the table builders without a GPU; never used for counting. */
+int64_t     tdg_selftest_match(tdg_ctx *ctx, const char *read, size_t len);
+/* A context without a device, only usable with tdg_set_tags / tdg_begin_file /
+ * tdg_set_matrix (host tables only) / tdg_selftest_match. */
+int         tdg_create_hostonly(tdg_ctx **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAGDIGGER_B200_H */

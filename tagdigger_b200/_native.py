@@ -1,0 +1,325 @@
+"""Build and ctypes binding of ``libtagdigger_b200.so`` (include/tagdigger_b200.h).
+
+The library is compiled in-tree with nvcc for sm_100a only.  There is no CPU
+counting path: every ``Engine`` method that counts reads ends in the CUDA kernel
+of ``csrc/tdg_kernel.cuh``, and constructing an ``Engine`` without a CUDA device
+(or without the built library) raises.
+"""
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+LIB_PATH = os.path.join(_HERE, "libtagdigger_b200.so")
+_SOURCES = ["tdg_api.cu", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h"]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-diag-suppress", "20014,20011", "-shared"]
+
+TDG_OK = 0
+TDG_ERR_CUDA, TDG_ERR_ARG, TDG_ERR_IO, TDG_ERR_STATE, TDG_ERR_NOMEM, TDG_ERR_GZIP = -1, -2, -3, -4, -5, -6
+TDG_ANY_BASE = 1
+TDG_PREV_NONE, TDG_PREV_LF, TDG_PREV_CR, TDG_PREV_OTHER = 0, 1, 2, 3
+TDG_LINE_CHAINED = (1 << 64) - 1
+TDG_TILE_BYTES = 16384
+TDG_HALO_BYTES = 512
+NO_LIMIT = (1 << 63)
+
+EXPORTS = """tdg_abi_version tdg_create tdg_destroy tdg_last_error tdg_set_tags tdg_set_matrix
+tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_submit tdg_end_file tdg_count_device
+tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix
+tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
+tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
+tdg_timing_begin tdg_timing_end tdg_selftest_match tdg_create_hostonly""".split()
+
+
+class TdgError(RuntimeError):
+    def __init__(self, code, message):
+        RuntimeError.__init__(self, "tagdigger_b200 error %d: %s" % (code, message))
+        self.code = code
+        self.message = message
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    srcs = [os.path.join(_CSRC, s) for s in _SOURCES] + [os.path.join(_INCLUDE, "tagdigger_b200.h")]
+    return any(os.path.exists(s) and os.path.getmtime(s) > t for s in srcs)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/ into libtagdigger_b200.so with nvcc (cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB_PATH, os.path.join(_CSRC, "tdg_api.cu"), "-lz"]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout)
+    if verbose:
+        print(proc.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Builds it when sources are newer and nvcc exists;
+    raises if it is neither built nor buildable (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if _stale():
+        try:
+            build()
+        except (OSError, RuntimeError):
+            if not os.path.exists(LIB_PATH):
+                raise
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u64, u32, i32, sz = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_size_t
+    sig = {
+        "tdg_abi_version": (i32, []),
+        "tdg_create": (i32, [ctypes.POINTER(vp), i32, sz]),
+        "tdg_create_hostonly": (i32, [ctypes.POINTER(vp)]),
+        "tdg_destroy": (None, [vp]),
+        "tdg_last_error": (ctypes.c_char_p, [vp]),
+        "tdg_set_tags": (i32, [vp, vp, vp, vp, u32, u32]),
+        "tdg_set_matrix": (i32, [vp, u32, u32]),
+        "tdg_bind_matrix": (i32, [vp, vp, u32, u32]),
+        "tdg_zero_matrix": (i32, [vp]),
+        "tdg_begin_file": (i32, [vp, vp, vp, vp, vp, u32, u32]),
+        "tdg_submit": (i32, [vp, vp, sz, u64]),
+        "tdg_end_file": (i32, [vp, u64]),
+        "tdg_count_device": (i32, [vp, vp, sz, u64, i32, u64]),
+        "tdg_count_lines_device": (i32, [vp, vp, sz, u64, i32, vp]),
+        "tdg_count_file": (i32, [vp, ctypes.c_char_p, i32, u64, vp]),
+        "tdg_sync": (i32, [vp]),
+        "tdg_file_totals": (i32, [vp, vp]),
+        "tdg_read_matrix": (i32, [vp, vp]),
+        "tdg_matrix_device_ptr": (vp, [vp]),
+        "tdg_stream": (vp, [vp]),
+        "tdg_stream_wait": (i32, [vp, vp]),
+        "tdg_other_stream_wait": (i32, [vp, vp]),
+        "tdg_host_alloc": (vp, [vp, sz]),
+        "tdg_host_free": (None, [vp, vp]),
+        "tdg_device_alloc": (vp, [vp, sz]),
+        "tdg_device_free": (None, [vp, vp]),
+        "tdg_memcpy_h2d": (i32, [vp, vp, vp, sz]),
+        "tdg_memcpy_d2h": (i32, [vp, vp, vp, sz]),
+        "tdg_launch_count": (u64, [vp]),
+        "tdg_timing_begin": (i32, [vp]),
+        "tdg_timing_end": (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u32)]),
+        "tdg_selftest_match": (ctypes.c_int64, [vp, ctypes.c_char_p, sz]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _csr(seqs, offset_dtype):
+    blob = "".join(seqs).encode("ascii")
+    off = np.zeros(len(seqs) + 1, dtype=offset_dtype)
+    if len(seqs):
+        np.cumsum([len(s) for s in seqs], out=off[1:])
+    return blob, off
+
+
+def limit_from_maxreads(maxreads):
+    """The reference checks ``readscount >= maxreads`` after each read
+    (tagdigger_fun.py:272-273): at least one read is processed, and a
+    fractional maxreads rounds up."""
+    if maxreads is None:
+        return NO_LIMIT
+    m = float(maxreads)
+    if m != m:                       # NaN never compares >=
+        return NO_LIMIT
+    if m >= float(NO_LIMIT):
+        return NO_LIMIT
+    lim = int(m)
+    if lim < m:
+        lim += 1
+    return max(1, lim)
+
+
+class Engine(object):
+    """One context = one CUDA device (include/tagdigger_b200.h)."""
+
+    def __init__(self, device=0, chunk_bytes=0, hostonly=False):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        self.hostonly = hostonly
+        if hostonly:
+            rc = self._L.tdg_create_hostonly(ctypes.byref(self._h))
+        else:
+            rc = self._L.tdg_create(ctypes.byref(self._h), device, chunk_bytes)
+        if rc != TDG_OK:
+            msg = self._L.tdg_last_error(None).decode()
+            self._h = ctypes.c_void_p()
+            raise TdgError(rc, msg)
+        self.device = device
+        self.rows = self.cols = 0
+
+    # -- plumbing ----------------------------------------------------------
+    def _ck(self, rc):
+        if rc != TDG_OK:
+            raise TdgError(rc, self._L.tdg_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.tdg_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # noqa: BLE001 - interpreter shutdown
+            pass
+
+    # -- tables ------------------------------------------------------------
+    def set_tags(self, seqs, cols=None, any_base=False):
+        """seqs: the effective (prefix-free) tag list; cols[i]: matrix column."""
+        if cols is None:
+            cols = range(len(seqs))
+        blob, off = _csr(seqs, np.uint64)
+        col = np.asarray(list(cols), dtype=np.int32)
+        self._keep_tags = (blob, off, col)
+        self._ck(self._L.tdg_set_tags(self._h, blob, off.ctypes.data, col.ctypes.data, len(seqs),
+                                      TDG_ANY_BASE if any_base else 0))
+
+    def set_matrix(self, rows, cols):
+        self._ck(self._L.tdg_set_matrix(self._h, rows, cols))
+        self.rows, self.cols = rows, cols
+
+    def bind_matrix(self, dev_ptr, rows, cols):
+        self._ck(self._L.tdg_bind_matrix(self._h, dev_ptr, rows, cols))
+        self.rows, self.cols = rows, cols
+
+    def zero_matrix(self):
+        self._ck(self._L.tdg_zero_matrix(self._h))
+
+    def begin_file(self, patterns, rows, tag_offs, any_base=False):
+        blob, off = _csr(patterns, np.uint32)
+        row = np.asarray(list(rows), dtype=np.int32)
+        toff = np.asarray(list(tag_offs), dtype=np.uint32)
+        self._ck(self._L.tdg_begin_file(self._h, blob, off.ctypes.data, row.ctypes.data, toff.ctypes.data,
+                                        len(patterns), TDG_ANY_BASE if any_base else 0))
+
+    # -- counting ----------------------------------------------------------
+    def submit(self, data, reads_limit=NO_LIMIT):
+        """data: bytes / bytearray / uint8 ndarray / (address, nbytes)."""
+        if isinstance(data, tuple):
+            addr, n = data
+        elif isinstance(data, np.ndarray):
+            addr, n = data.ctypes.data, data.nbytes
+            self._pin = data
+        else:
+            buf = np.frombuffer(data, dtype=np.uint8)
+            addr, n = buf.ctypes.data, buf.nbytes
+            self._pin = buf
+        self._ck(self._L.tdg_submit(self._h, addr, n, reads_limit))
+
+    def end_file(self, reads_limit=NO_LIMIT):
+        self._ck(self._L.tdg_end_file(self._h, reads_limit))
+
+    def count_device(self, dev_ptr, n, line_base=0, prev_kind=TDG_PREV_NONE, reads_limit=NO_LIMIT):
+        self._ck(self._L.tdg_count_device(self._h, dev_ptr, n, line_base, prev_kind, reads_limit))
+
+    def count_lines_device(self, dev_ptr, n, line_base=0, prev_kind=TDG_PREV_NONE):
+        st = np.zeros(2, dtype=np.uint64)
+        self._ck(self._L.tdg_count_lines_device(self._h, dev_ptr, n, line_base, prev_kind, st.ctypes.data))
+        return int(st[0]), int(st[1])
+
+    def count_file(self, path, gz, reads_limit=NO_LIMIT):
+        tot = np.zeros(4, dtype=np.uint64)
+        self._ck(self._L.tdg_count_file(self._h, os.fsencode(path), 1 if gz else 0, reads_limit, tot.ctypes.data))
+        return [int(x) for x in tot]
+
+    def sync(self):
+        self._ck(self._L.tdg_sync(self._h))
+
+    def file_totals(self):
+        tot = np.zeros(4, dtype=np.uint64)
+        self._ck(self._L.tdg_file_totals(self._h, tot.ctypes.data))
+        return [int(x) for x in tot]
+
+    def read_matrix(self, out=None):
+        if out is None:
+            out = np.empty((self.rows, self.cols), dtype=np.int32)
+        self._ck(self._L.tdg_read_matrix(self._h, out.ctypes.data))
+        return out
+
+    # -- memory / streams --------------------------------------------------
+    def matrix_ptr(self):
+        return self._L.tdg_matrix_device_ptr(self._h)
+
+    def stream(self):
+        return self._L.tdg_stream(self._h)
+
+    def stream_wait(self, other):
+        self._ck(self._L.tdg_stream_wait(self._h, other))
+
+    def other_stream_wait(self, other):
+        self._ck(self._L.tdg_other_stream_wait(self._h, other))
+
+    def host_alloc(self, n):
+        p = self._L.tdg_host_alloc(self._h, n)
+        if not p:
+            raise TdgError(TDG_ERR_NOMEM, "pinned allocation of %d bytes failed" % n)
+        return p
+
+    def host_free(self, p):
+        self._L.tdg_host_free(self._h, p)
+
+    def device_alloc(self, n):
+        p = self._L.tdg_device_alloc(self._h, n)
+        if not p:
+            raise TdgError(TDG_ERR_NOMEM, "device allocation of %d bytes failed" % n)
+        return p
+
+    def device_free(self, p):
+        self._L.tdg_device_free(self._h, p)
+
+    def memcpy_h2d(self, dev, host_addr, n):
+        self._ck(self._L.tdg_memcpy_h2d(self._h, dev, host_addr, n))
+
+    def memcpy_d2h(self, host_addr, dev, n):
+        self._ck(self._L.tdg_memcpy_d2h(self._h, host_addr, dev, n))
+
+    def upload(self, data):
+        """Copy a host FASTQ image to a fresh, suitably padded device buffer.
+        Returns (device pointer, nbytes); free with device_free."""
+        arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        n = arr.nbytes
+        cap = (n + TDG_TILE_BYTES - 1) // TDG_TILE_BYTES * TDG_TILE_BYTES + TDG_HALO_BYTES
+        p = self.device_alloc(cap)
+        if n:
+            self.memcpy_h2d(p, arr.ctypes.data, n)
+        return p, n
+
+    # -- accounting --------------------------------------------------------
+    def launch_count(self):
+        return int(self._L.tdg_launch_count(self._h))
+
+    def timing_begin(self):
+        self._ck(self._L.tdg_timing_begin(self._h))
+
+    def timing_end(self):
+        ms = ctypes.c_double(0)
+        n = ctypes.c_uint32(0)
+        self._ck(self._L.tdg_timing_end(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def selftest_match(self, read):
+        if isinstance(read, str):
+            read = read.encode("utf-8")
+        return int(self._L.tdg_selftest_match(self._h, read, len(read)))

@@ -1,0 +1,896 @@
+// C ABI of tagdigger_b200 (see include/tagdigger_b200.h): contexts, table
+// upload, chunk streaming with pinned buffers, zlib inflate on a host thread.
+// There is no CPU counting path in this file: every count comes from
+// count_kernel (tdg_kernel.cuh).
+#include <cuda_runtime.h>
+#include <zlib.h>
+
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/tagdigger_b200.h"
+#include "tdg_kernel.cuh"
+#include "tdg_tables.h"
+
+static_assert(TDG_TILE_BYTES == tdg::TILE, "header and kernel disagree on the tile size");
+static_assert(TDG_HALO_BYTES == tdg::HALO, "header and kernel disagree on the halo size");
+
+namespace {
+
+constexpr int NSLOT = 3;
+constexpr int MAX_TIMED = 4096;
+std::string g_create_error;
+
+struct Slot {
+    uint8_t *dev = nullptr;
+    uint8_t *carry = nullptr;      // pinned: partial last line of the previous piece
+    size_t carry_cap = 0;
+    cudaEvent_t copied = nullptr;  // H2D of this slot finished
+    cudaEvent_t done = nullptr;    // kernel on this slot finished
+};
+
+}  // namespace
+
+struct tdg_ctx {
+    bool hostonly = false;
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    size_t chunk_bytes = 0;
+
+    cudaStream_t stream = nullptr;       // kernels
+    cudaStream_t copy_stream = nullptr;  // H2D
+
+    // tables
+    tdg::HostTagTable tags;
+    bool have_tags = false;
+    tdg::TagEntry *d_entries = nullptr;
+    uint64_t *d_ext = nullptr;
+    size_t d_entries_cap = 0, d_ext_cap = 0;
+    std::vector<uint8_t> bar_blob;
+    bool have_bar = false;
+    uint8_t *d_bar = nullptr;
+    size_t d_bar_cap = 0;
+
+    // matrix
+    int32_t *d_matrix = nullptr;
+    bool own_matrix = false;
+    uint32_t rows = 0, cols = 0;
+
+    // per-launch scratch: [0] ticket, [8..] tile descriptors
+    unsigned long long *d_sync = nullptr;
+    size_t sync_cap = 0;
+    tdg::LineState *d_state = nullptr;   // [2]
+    int state_cur = 0;
+    unsigned long long *d_totals = nullptr;   // [4]
+
+    // streaming
+    Slot slot[NSLOT];
+    size_t slot_cap = 0;
+    int next_slot = 0;
+    size_t carry_len = 0;        // bytes waiting in slot[next_slot].carry
+    bool file_open = false;
+
+    // accounting
+    uint64_t launches = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;
+    int tev_used = 0;
+};
+
+namespace {
+
+int fail(tdg_ctx *ctx, int code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(ctx, TDG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+int ensure_sync(tdg_ctx *ctx, size_t tiles)
+{
+    size_t need = 8 + tiles;
+    if (need <= ctx->sync_cap) return TDG_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_sync) CK(cudaFree(ctx->d_sync));
+    ctx->d_sync = nullptr;
+    size_t cap = need + need / 2;
+    CK(cudaMalloc(&ctx->d_sync, cap * sizeof(unsigned long long)));
+    ctx->sync_cap = cap;
+    return TDG_OK;
+}
+
+template <bool MATCH>
+int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_base, int prev_kind,
+                 uint64_t reads_limit)
+{
+    using namespace tdg;
+    if (n == 0) return TDG_OK;
+    if (((uintptr_t)dev_bytes & 15u) != 0) return fail(ctx, TDG_ERR_ARG, "device chunk must be 16-byte aligned");
+    size_t tiles = (n + TILE - 1) / TILE;
+    if (tiles >= 0xFFFFFFFFull) return fail(ctx, TDG_ERR_ARG, "chunk too large (limit 2^32 - 2 tiles of 16 KiB)");
+    int rc = ensure_sync(ctx, tiles);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_sync, 0, (8 + tiles) * sizeof(unsigned long long), ctx->stream));
+
+    ChunkArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bytes = (const uint8_t *)dev_bytes;
+    a.n = n;
+    a.num_tiles = (uint32_t)tiles;
+    if (line_base == TDG_LINE_CHAINED) {
+        a.use_arg_state = 0;
+    } else {
+        a.use_arg_state = 1;
+        a.line_base = line_base;
+        a.prev_kind = (uint32_t)prev_kind;
+    }
+    a.match = MATCH ? 1 : 0;
+    a.state_in = ctx->d_state + ctx->state_cur;
+    a.state_out = ctx->d_state + (ctx->state_cur ^ 1);
+    ctx->state_cur ^= 1;
+    a.desc = ctx->d_sync + 8;
+    a.ticket = ctx->d_sync;
+    a.reads_limit = reads_limit;
+    size_t bar_smem = 0;
+    if (MATCH) {
+        a.bar = (const BarTable *)ctx->d_bar;
+        a.bar_bytes = (uint32_t)ctx->bar_blob.size();
+        a.cols = ctx->cols;
+        a.tags = ctx->tags.t;
+        a.tags.entries = ctx->d_entries;
+        a.tags.ext = ctx->d_ext;
+        a.matrix = ctx->d_matrix;
+        a.totals = ctx->d_totals;
+        if (a.bar_bytes <= BAR_SMEM_MAX) bar_smem = round_up(a.bar_bytes, 16);
+    }
+    size_t smem = (size_t)STAGES * STAGE_STRIDE + STARTS_CAP * sizeof(uint16_t) + bar_smem;
+    auto kern = count_kernel<MATCH>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+    if (per_sm < 1) return fail(ctx, TDG_ERR_CUDA, "counting kernel does not fit on an SM");
+    size_t grid = (size_t)per_sm * ctx->sm_count;
+    if (grid > tiles) grid = tiles;
+
+    bool timed = ctx->timing && ctx->tev_used + 2 <= MAX_TIMED * 2;
+    if (timed) CK(cudaEventRecord(ctx->tev[ctx->tev_used++], ctx->stream));
+    kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    if (timed) CK(cudaEventRecord(ctx->tev[ctx->tev_used++], ctx->stream));
+    ctx->launches += 1;
+    return TDG_OK;
+}
+
+int need_device(tdg_ctx *ctx)
+{
+    if (!ctx) return TDG_ERR_ARG;
+    if (ctx->hostonly) return fail(ctx, TDG_ERR_STATE, "host-only context: no CUDA device behind it");
+    return TDG_OK;
+}
+
+int need_ready(tdg_ctx *ctx)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!ctx->have_tags) return fail(ctx, TDG_ERR_STATE, "tdg_set_tags has not been called");
+    if (!ctx->d_matrix) return fail(ctx, TDG_ERR_STATE, "tdg_set_matrix / tdg_bind_matrix has not been called");
+    if (!ctx->have_bar) return fail(ctx, TDG_ERR_STATE, "tdg_begin_file has not been called");
+    return TDG_OK;
+}
+
+int ensure_slots(tdg_ctx *ctx)
+{
+    if (ctx->slot_cap) return TDG_OK;
+    // a piece is the carried partial line (<= chunk_bytes) plus up to chunk_bytes new bytes
+    size_t cap = round_up(2 * ctx->chunk_bytes, TDG_TILE_BYTES) + TDG_TILE_BYTES + TDG_HALO_BYTES;
+    for (int i = 0; i < NSLOT; i++) {
+        CK(cudaMalloc(&ctx->slot[i].dev, cap));
+        ctx->slot[i].carry_cap = 1 << 20;
+        CK(cudaHostAlloc(&ctx->slot[i].carry, ctx->slot[i].carry_cap, cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&ctx->slot[i].copied, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->slot[i].done, cudaEventDisableTiming));
+    }
+    ctx->slot_cap = cap;
+    return TDG_OK;
+}
+
+int grow_carry(tdg_ctx *ctx, Slot &s, size_t need, size_t keep)
+{
+    if (need <= s.carry_cap) return TDG_OK;
+    size_t cap = s.carry_cap;
+    while (cap < need) cap *= 2;
+    uint8_t *p = nullptr;
+    CK(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+    if (keep) memcpy(p, s.carry, keep);
+    CK(cudaFreeHost(s.carry));
+    s.carry = p;
+    s.carry_cap = cap;
+    return TDG_OK;
+}
+
+// Where to cut bytes[0..n) so that everything before the cut is whole lines:
+// just after the last '\n', or (files with lone '\r' line ends) after the last
+// '\r' that is followed by another byte which is not '\n'.  0 if no line ends.
+size_t line_cut(const uint8_t *b, size_t n)
+{
+    const void *lf = memrchr(b, '\n', n);
+    size_t cut = lf ? (size_t)((const uint8_t *)lf - b) + 1 : 0;
+    // a lone '\r' after that point ends a line too
+    if (cut < n) {
+        const uint8_t *tail = b + cut;
+        size_t m = n - cut;
+        for (size_t i = m; i-- > 0;) {
+            if (tail[i] == '\r' && i + 1 < m) {      // tail[i+1] cannot be '\n' (it lies after the last '\n')
+                cut += i + 1;
+                break;
+            }
+        }
+    }
+    return cut;
+}
+
+// One piece: [carry | bytes[0..cut)] -> device slot -> kernel; bytes[cut..n) becomes the new carry.
+int submit_piece(tdg_ctx *ctx, const uint8_t *bytes, size_t n, size_t cut, uint64_t reads_limit)
+{
+    int si = ctx->next_slot;
+    Slot &s = ctx->slot[si];
+    size_t total = ctx->carry_len + cut;
+    int nxt = (si + 1) % NSLOT;
+    Slot &sn = ctx->slot[nxt];
+    if (total > 0) {
+        // the slot's previous kernel must be finished before its buffer is overwritten
+        CK(cudaStreamWaitEvent(ctx->copy_stream, s.done, 0));
+        if (ctx->carry_len) CK(cudaMemcpyAsync(s.dev, s.carry, ctx->carry_len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (cut) CK(cudaMemcpyAsync(s.dev + ctx->carry_len, bytes, cut, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(s.copied, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, s.copied, 0));
+        int rc = launch_chunk<true>(ctx, s.dev, total, TDG_LINE_CHAINED, 0, reads_limit);
+        if (rc) return rc;
+        CK(cudaEventRecord(s.done, ctx->stream));
+        // new carry goes to the next slot's pinned buffer, once its last H2D has drained
+        CK(cudaEventSynchronize(sn.copied));
+        size_t rest = n - cut;
+        int rc2 = grow_carry(ctx, sn, rest, 0);
+        if (rc2) return rc2;
+        if (rest) memcpy(sn.carry, bytes + cut, rest);
+        ctx->carry_len = rest;
+        ctx->next_slot = nxt;
+    } else {
+        // nothing complete yet: append to the current carry
+        size_t rest = n;
+        if (ctx->carry_len + rest > ctx->chunk_bytes)
+            return fail(ctx, TDG_ERR_ARG, "a single text line is longer than chunk_bytes");
+        int rc2 = grow_carry(ctx, s, ctx->carry_len + rest, ctx->carry_len);
+        if (rc2) return rc2;
+        memcpy(s.carry + ctx->carry_len, bytes, rest);
+        ctx->carry_len += rest;
+    }
+    return TDG_OK;
+}
+
+int submit_impl(tdg_ctx *ctx, const uint8_t *bytes, size_t n, uint64_t reads_limit, bool wait_copied)
+{
+    int rc = ensure_slots(ctx);
+    if (rc) return rc;
+    size_t pos = 0;
+    int last = -1;
+    while (pos < n) {
+        size_t m = n - pos < ctx->chunk_bytes ? n - pos : ctx->chunk_bytes;
+        size_t cut = line_cut(bytes + pos, m);
+        if (ctx->carry_len + cut > 2 * ctx->chunk_bytes)
+            return fail(ctx, TDG_ERR_ARG, "a single text line is longer than chunk_bytes");
+        if (cut) last = ctx->next_slot;
+        rc = submit_piece(ctx, bytes + pos, m, cut, reads_limit);
+        if (rc) return rc;
+        pos += m;
+    }
+    if (wait_copied && last >= 0) CK(cudaEventSynchronize(ctx->slot[last].copied));
+    return TDG_OK;
+}
+
+int end_file_impl(tdg_ctx *ctx, uint64_t reads_limit)
+{
+    if (ctx->carry_len) {
+        // the carried bytes are the file's last line (no line end follows)
+        int si = ctx->next_slot;
+        Slot &s = ctx->slot[si];
+        CK(cudaStreamWaitEvent(ctx->copy_stream, s.done, 0));
+        CK(cudaMemcpyAsync(s.dev, s.carry, ctx->carry_len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(s.copied, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, s.copied, 0));
+        int rc = launch_chunk<true>(ctx, s.dev, ctx->carry_len, TDG_LINE_CHAINED, 0, reads_limit);
+        if (rc) return rc;
+        CK(cudaEventRecord(s.done, ctx->stream));
+        CK(cudaEventSynchronize(s.copied));
+        ctx->carry_len = 0;
+        ctx->next_slot = (si + 1) % NSLOT;
+    }
+    return TDG_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+
+extern "C" {
+
+int tdg_abi_version(void) { return TDG_ABI_VERSION; }
+
+const char *tdg_last_error(const tdg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tdg_create_hostonly(tdg_ctx **out)
+{
+    if (!out) return TDG_ERR_ARG;
+    tdg_ctx *ctx = new (std::nothrow) tdg_ctx();
+    if (!ctx) return fail(nullptr, TDG_ERR_NOMEM, "out of memory");
+    ctx->hostonly = true;
+    *out = ctx;
+    return TDG_OK;
+}
+
+int tdg_create(tdg_ctx **out, int device, size_t chunk_bytes)
+{
+    if (!out) return TDG_ERR_ARG;
+    *out = nullptr;
+    tdg_ctx *ctx = nullptr;   // CK reports into g_create_error while ctx is null
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TDG_ERR_CUDA,
+                    std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                        " (tagdigger_b200 has no CPU counting path)");
+    if (device < 0 || device >= ndev) return fail(nullptr, TDG_ERR_ARG, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(nullptr, TDG_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 class; this library is built for sm_100a only");
+    tdg_ctx *c = new (std::nothrow) tdg_ctx();
+    if (!c) return fail(nullptr, TDG_ERR_NOMEM, "out of memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->chunk_bytes = chunk_bytes ? chunk_bytes : ((size_t)64 << 20);
+    if (c->chunk_bytes < 4096) c->chunk_bytes = 4096;
+    cudaError_t e2 = cudaSuccess;
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_state, 2 * sizeof(tdg::LineState));
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&c->d_totals, 4 * sizeof(unsigned long long));
+    if (e2 == cudaSuccess) e2 = cudaMemset(c->d_state, 0, 2 * sizeof(tdg::LineState));
+    if (e2 == cudaSuccess) e2 = cudaMemset(c->d_totals, 0, 4 * sizeof(unsigned long long));
+    if (e2 != cudaSuccess) {
+        std::string msg = std::string("context set-up failed: ") + cudaGetErrorString(e2);
+        tdg_destroy(c);
+        return fail(nullptr, TDG_ERR_CUDA, msg);
+    }
+    *out = c;
+    return TDG_OK;
+}
+
+void tdg_destroy(tdg_ctx *ctx)
+{
+    if (!ctx) return;
+    if (!ctx->hostonly) {
+        cudaSetDevice(ctx->device);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        for (int i = 0; i < NSLOT; i++) {
+            if (ctx->slot[i].dev) cudaFree(ctx->slot[i].dev);
+            if (ctx->slot[i].carry) cudaFreeHost(ctx->slot[i].carry);
+            if (ctx->slot[i].copied) cudaEventDestroy(ctx->slot[i].copied);
+            if (ctx->slot[i].done) cudaEventDestroy(ctx->slot[i].done);
+        }
+        for (cudaEvent_t ev : ctx->tev) cudaEventDestroy(ev);
+        if (ctx->d_entries) cudaFree(ctx->d_entries);
+        if (ctx->d_ext) cudaFree(ctx->d_ext);
+        if (ctx->d_bar) cudaFree(ctx->d_bar);
+        if (ctx->own_matrix && ctx->d_matrix) cudaFree(ctx->d_matrix);
+        if (ctx->d_sync) cudaFree(ctx->d_sync);
+        if (ctx->d_state) cudaFree(ctx->d_state);
+        if (ctx->d_totals) cudaFree(ctx->d_totals);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    }
+    delete ctx;
+}
+
+int tdg_set_tags(tdg_ctx *ctx, const char *bases, const uint64_t *off, const int32_t *col, uint32_t ntags,
+                 uint32_t flags)
+{
+    if (!ctx || !off || !col || (!bases && off[ntags] != off[0])) return fail(ctx, TDG_ERR_ARG, "null argument");
+    ctx->have_tags = false;
+    std::string why = tdg::build_tag_table(bases, off, col, ntags, flags, ctx->tags);
+    if (!why.empty()) return fail(ctx, TDG_ERR_ARG, "tdg_set_tags: " + why);
+    if (ctx->cols) {
+        for (uint32_t i = 0; i < ntags; i++)
+            if (col[i] < 0 || (uint32_t)col[i] >= ctx->cols) return fail(ctx, TDG_ERR_ARG, "tdg_set_tags: column out of range");
+    }
+    if (!ctx->hostonly) {
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamSynchronize(ctx->stream));
+        size_t ne = ctx->tags.entries.size(), nx = ctx->tags.ext.size();
+        if (ne > ctx->d_entries_cap) {
+            if (ctx->d_entries) CK(cudaFree(ctx->d_entries));
+            ctx->d_entries = nullptr;
+            CK(cudaMalloc(&ctx->d_entries, std::max<size_t>(ne, 1) * sizeof(tdg::TagEntry)));
+            ctx->d_entries_cap = ne;
+        }
+        if (nx > ctx->d_ext_cap || !ctx->d_ext) {
+            if (ctx->d_ext) CK(cudaFree(ctx->d_ext));
+            ctx->d_ext = nullptr;
+            CK(cudaMalloc(&ctx->d_ext, std::max<size_t>(nx, 1) * sizeof(uint64_t)));
+            ctx->d_ext_cap = nx;
+        }
+        if (ne) CK(cudaMemcpy(ctx->d_entries, ctx->tags.entries.data(), ne * sizeof(tdg::TagEntry), cudaMemcpyHostToDevice));
+        if (nx) CK(cudaMemcpy(ctx->d_ext, ctx->tags.ext.data(), nx * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    }
+    ctx->have_tags = true;
+    return TDG_OK;
+}
+
+int tdg_set_matrix(tdg_ctx *ctx, uint32_t rows, uint32_t cols)
+{
+    if (!ctx || rows == 0 || cols == 0) return fail(ctx, TDG_ERR_ARG, "matrix must have at least one row and column");
+    if (ctx->hostonly) {
+        ctx->rows = rows;
+        ctx->cols = cols;
+        return TDG_OK;
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_matrix && ctx->d_matrix) CK(cudaFree(ctx->d_matrix));
+    ctx->d_matrix = nullptr;
+    CK(cudaMalloc(&ctx->d_matrix, (size_t)rows * cols * sizeof(int32_t)));
+    ctx->own_matrix = true;
+    ctx->rows = rows;
+    ctx->cols = cols;
+    return tdg_zero_matrix(ctx);
+}
+
+int tdg_bind_matrix(tdg_ctx *ctx, void *dev_int32, uint32_t rows, uint32_t cols)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!dev_int32 || rows == 0 || cols == 0) return fail(ctx, TDG_ERR_ARG, "bad matrix");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_matrix && ctx->d_matrix) CK(cudaFree(ctx->d_matrix));
+    ctx->d_matrix = (int32_t *)dev_int32;
+    ctx->own_matrix = false;
+    ctx->rows = rows;
+    ctx->cols = cols;
+    return TDG_OK;
+}
+
+int tdg_zero_matrix(tdg_ctx *ctx)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!ctx->d_matrix) return fail(ctx, TDG_ERR_STATE, "no matrix");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_matrix, 0, (size_t)ctx->rows * ctx->cols * sizeof(int32_t), ctx->stream));
+    return TDG_OK;
+}
+
+int tdg_begin_file(tdg_ctx *ctx, const char *bases, const uint32_t *off, const int32_t *row, const uint32_t *tag_off,
+                   uint32_t npat, uint32_t flags)
+{
+    if (!ctx || !off || !row || !tag_off) return fail(ctx, TDG_ERR_ARG, "null argument");
+    if (ctx->carry_len) return fail(ctx, TDG_ERR_STATE, "previous file was not ended (tdg_end_file)");
+    ctx->have_bar = false;
+    std::string why = tdg::build_bar_table(bases, off, row, tag_off, npat, flags, ctx->bar_blob);
+    if (!why.empty()) return fail(ctx, TDG_ERR_ARG, "tdg_begin_file: " + why);
+    if (ctx->rows) {
+        for (uint32_t i = 0; i < npat; i++)
+            if (row[i] < 0 || (uint32_t)row[i] >= ctx->rows) return fail(ctx, TDG_ERR_ARG, "tdg_begin_file: row out of range");
+    }
+    if (!ctx->hostonly) {
+        CK(cudaSetDevice(ctx->device));
+        // the previous file's kernels read the old table
+        CK(cudaStreamSynchronize(ctx->stream));
+        size_t nb = round_up(ctx->bar_blob.size(), 16);
+        if (nb > ctx->d_bar_cap) {
+            if (ctx->d_bar) CK(cudaFree(ctx->d_bar));
+            ctx->d_bar = nullptr;
+            CK(cudaMalloc(&ctx->d_bar, nb));
+            ctx->d_bar_cap = nb;
+        }
+        CK(cudaMemcpy(ctx->d_bar, ctx->bar_blob.data(), ctx->bar_blob.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemsetAsync(ctx->d_state, 0, 2 * sizeof(tdg::LineState), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_totals, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        ctx->state_cur = 0;
+    }
+    ctx->have_bar = true;
+    ctx->file_open = true;
+    return TDG_OK;
+}
+
+int tdg_submit(tdg_ctx *ctx, const void *bytes, size_t n, uint64_t reads_limit)
+{
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (n == 0) return TDG_OK;
+    if (!bytes) return fail(ctx, TDG_ERR_ARG, "null buffer");
+    CK(cudaSetDevice(ctx->device));
+    return submit_impl(ctx, (const uint8_t *)bytes, n, reads_limit, true);
+}
+
+int tdg_end_file(tdg_ctx *ctx, uint64_t reads_limit)
+{
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    rc = ensure_slots(ctx);
+    if (rc) return rc;
+    return end_file_impl(ctx, reads_limit);
+}
+
+int tdg_count_device(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_base, int prev_kind,
+                     uint64_t reads_limit)
+{
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (n && !dev_bytes) return fail(ctx, TDG_ERR_ARG, "null buffer");
+    if (line_base != TDG_LINE_CHAINED && (prev_kind < 0 || prev_kind > 3)) return fail(ctx, TDG_ERR_ARG, "bad prev_kind");
+    CK(cudaSetDevice(ctx->device));
+    return launch_chunk<true>(ctx, dev_bytes, n, line_base, prev_kind, reads_limit);
+}
+
+int tdg_count_lines_device(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_base, int prev_kind,
+                           uint64_t state[2])
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!state || (n && !dev_bytes)) return fail(ctx, TDG_ERR_ARG, "null argument");
+    if (prev_kind < 0 || prev_kind > 3) return fail(ctx, TDG_ERR_ARG, "bad prev_kind");
+    CK(cudaSetDevice(ctx->device));
+    if (n == 0) {
+        state[0] = line_base;
+        state[1] = (uint64_t)prev_kind;
+        return TDG_OK;
+    }
+    rc = launch_chunk<false>(ctx, dev_bytes, n, line_base, prev_kind, 0);
+    if (rc) return rc;
+    tdg::LineState st;
+    CK(cudaMemcpyAsync(&st, ctx->d_state + ctx->state_cur, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    state[0] = st.next_line;
+    state[1] = st.prev_kind;
+    return TDG_OK;
+}
+
+int tdg_sync(tdg_ctx *ctx)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDG_OK;
+}
+
+int tdg_file_totals(tdg_ctx *ctx, uint64_t totals[4])
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!totals) return fail(ctx, TDG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long t[4];
+    tdg::LineState st;
+    CK(cudaMemcpyAsync(t, ctx->d_totals, sizeof(t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&st, ctx->d_state + ctx->state_cur, sizeof(st), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    totals[0] = t[0];
+    totals[1] = t[1];
+    totals[2] = t[2];
+    totals[3] = st.next_line;
+    return TDG_OK;
+}
+
+int tdg_read_matrix(tdg_ctx *ctx, int32_t *out)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!ctx->d_matrix) return fail(ctx, TDG_ERR_STATE, "no matrix");
+    CK(cudaSetDevice(ctx->device));
+    if (out)
+        CK(cudaMemcpyAsync(out, ctx->d_matrix, (size_t)ctx->rows * ctx->cols * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDG_OK;
+}
+
+void *tdg_matrix_device_ptr(tdg_ctx *ctx) { return ctx ? ctx->d_matrix : nullptr; }
+void *tdg_stream(tdg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int tdg_stream_wait(tdg_ctx *ctx, void *other_stream)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, (cudaStream_t)other_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    CK(cudaEventDestroy(ev));
+    return TDG_OK;
+}
+
+int tdg_other_stream_wait(tdg_ctx *ctx, void *other_stream)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaEventRecord(ev, ctx->stream));
+    CK(cudaStreamWaitEvent((cudaStream_t)other_stream, ev, 0));
+    CK(cudaEventDestroy(ev));
+    return TDG_OK;
+}
+
+void *tdg_host_alloc(tdg_ctx *ctx, size_t n)
+{
+    if (!ctx || ctx->hostonly) return nullptr;
+    void *p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) {
+        ctx->err = "cudaHostAlloc failed";
+        return nullptr;
+    }
+    return p;
+}
+void tdg_host_free(tdg_ctx *ctx, void *p)
+{
+    (void)ctx;
+    if (p) cudaFreeHost(p);
+}
+void *tdg_device_alloc(tdg_ctx *ctx, size_t n)
+{
+    if (!ctx || ctx->hostonly) return nullptr;
+    void *p = nullptr;
+    cudaSetDevice(ctx->device);
+    if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) {
+        ctx->err = "cudaMalloc failed";
+        return nullptr;
+    }
+    return p;
+}
+void tdg_device_free(tdg_ctx *ctx, void *p)
+{
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(p);
+}
+int tdg_memcpy_h2d(tdg_ctx *ctx, void *dev, const void *host, size_t n)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dev, host, n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDG_OK;
+}
+int tdg_memcpy_d2h(tdg_ctx *ctx, void *host, const void *dev, size_t n)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host, dev, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDG_OK;
+}
+
+uint64_t tdg_launch_count(const tdg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int tdg_timing_begin(tdg_ctx *ctx)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->tev.empty()) {
+        ctx->tev.resize(2 * MAX_TIMED);
+        for (auto &ev : ctx->tev) CK(cudaEventCreate(&ev));
+    }
+    ctx->tev_used = 0;
+    ctx->timing = true;
+    return TDG_OK;
+}
+
+int tdg_timing_end(tdg_ctx *ctx, double *kernel_ms, uint32_t *nlaunch)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double ms = 0;
+    for (int i = 0; i + 1 < ctx->tev_used; i += 2) {
+        float t = 0;
+        CK(cudaEventElapsedTime(&t, ctx->tev[i], ctx->tev[i + 1]));
+        ms += t;
+    }
+    if (kernel_ms) *kernel_ms = ms;
+    if (nlaunch) *nlaunch = (uint32_t)(ctx->tev_used / 2);
+    ctx->timing = false;
+    return TDG_OK;
+}
+
+int64_t tdg_selftest_match(tdg_ctx *ctx, const char *read, size_t len)
+{
+    if (!ctx || !ctx->have_tags || !ctx->have_bar) return -3;
+    const uint8_t *p = (const uint8_t *)read;
+    size_t pos = 0;
+    while (pos < len) {
+        uint32_t c = p[pos];
+        if (tdg::is_space(c)) { pos++; continue; }
+        if (c >= 0xC2 && c <= 0xE3 && pos + 2 < len) {
+            uint32_t u = tdg::utf8_space(c, p[pos + 1], p[pos + 2]);
+            if (u) { pos += u; continue; }
+        }
+        break;
+    }
+    tdg::HostFetch f;
+    f.p = p + pos;
+    f.limit = (uint32_t)(len - pos);
+    tdg::TagTable tt = ctx->tags.t;
+    tt.entries = ctx->tags.entries.data();
+    tt.ext = ctx->tags.ext.data();
+    const tdg::BarTable *bar = (const tdg::BarTable *)ctx->bar_blob.data();
+    const tdg::BarEntry *bent = (const tdg::BarEntry *)(ctx->bar_blob.data() + sizeof(tdg::BarTable));
+    tdg::MatchResult r = tdg::match_line(f, bar, bent, tt);
+    if (r.row < 0) return -2;
+    if (r.col < 0) return -1;
+    return (int64_t)r.row * ctx->cols + r.col;
+}
+
+// ---------------------------------------------------------------------------
+// Whole-file streaming: a reader thread (read() or zlib inflate) fills pinned
+// buffers; the calling thread feeds them to the GPU.
+
+int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit, uint64_t totals[4])
+{
+    int rc = need_ready(ctx);
+    if (rc) return rc;
+    if (!path) return fail(ctx, TDG_ERR_ARG, "null path");
+    CK(cudaSetDevice(ctx->device));
+    rc = ensure_slots(ctx);
+    if (rc) return rc;
+
+    constexpr int NBUF = 3;
+    struct Buf {
+        uint8_t *p = nullptr;
+        size_t n = 0;
+        int state = 0;   // 0 free, 1 full
+    } bufs[NBUF];
+    for (int i = 0; i < NBUF; i++) {
+        cudaError_t e = cudaHostAlloc(&bufs[i].p, ctx->chunk_bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            for (int k = 0; k < i; k++) cudaFreeHost(bufs[k].p);
+            return fail(ctx, TDG_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+        }
+    }
+    std::mutex mu;
+    std::condition_variable cv;
+    bool eof = false, stop = false;
+    int io_err = 0;
+    std::string io_msg;
+    size_t chunk = ctx->chunk_bytes;
+
+    std::thread reader([&]() {
+        FILE *fp = nullptr;
+        gzFile zf = nullptr;
+        if (gz) {
+            zf = gzopen(path, "rb");
+            if (!zf) { io_err = TDG_ERR_IO; io_msg = std::string("cannot open ") + path; }
+            else gzbuffer(zf, 1 << 20);
+        } else {
+            fp = fopen(path, "rb");
+            if (!fp) { io_err = TDG_ERR_IO; io_msg = std::string("cannot open ") + path; }
+        }
+        int bi = 0;
+        bool first = true;
+        while (!io_err) {
+            Buf &b = bufs[bi];
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return b.state == 0 || stop; });
+                if (stop) break;
+            }
+            size_t got = 0;
+            if (gz) {
+                while (got < chunk) {
+                    unsigned want = (unsigned)std::min<size_t>(chunk - got, 1u << 30);
+                    int r = gzread(zf, b.p + got, want);
+                    if (r < 0) {
+                        int en = 0;
+                        const char *m = gzerror(zf, &en);
+                        io_err = TDG_ERR_GZIP;
+                        io_msg = std::string("gzip error in ") + path + ": " + (m ? m : "?");
+                        break;
+                    }
+                    if (r == 0) break;
+                    got += (size_t)r;
+                    if (first) {
+                        first = false;
+                        if (gzdirect(zf)) {   // the reference's gzip.open raises on a non-gzip file
+                            io_err = TDG_ERR_GZIP;
+                            io_msg = std::string("Not a gzipped file: ") + path;
+                            break;
+                        }
+                    }
+                }
+            } else {
+                got = fread(b.p, 1, chunk, fp);
+                if (got < chunk && ferror(fp)) { io_err = TDG_ERR_IO; io_msg = std::string("read error on ") + path; }
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                b.n = got;
+                b.state = 1;
+                if (got == 0 || io_err) eof = true;
+            }
+            cv.notify_all();
+            if (got == 0 || io_err) break;
+            bi = (bi + 1) % NBUF;
+        }
+        if (io_err) {
+            std::lock_guard<std::mutex> lk(mu);
+            eof = true;
+            cv.notify_all();
+        }
+        if (fp) fclose(fp);
+        if (zf) gzclose(zf);
+    });
+
+    int bi = 0;
+    int result = TDG_OK;
+    for (;;) {
+        Buf &b = bufs[bi];
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return b.state == 1 || (eof && b.state != 1); });
+            if (b.state != 1) break;      // reader ended (error before filling this buffer)
+        }
+        if (b.n == 0) break;
+        result = submit_impl(ctx, b.p, b.n, reads_limit, true);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            b.state = 0;
+        }
+        cv.notify_all();
+        if (result) break;
+        bi = (bi + 1) % NBUF;
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        stop = true;
+    }
+    cv.notify_all();
+    reader.join();
+    if (result == TDG_OK && io_err) result = fail(ctx, io_err, io_msg);
+    if (result == TDG_OK) result = end_file_impl(ctx, reads_limit);
+    if (result != TDG_OK) ctx->carry_len = 0;
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < NBUF; i++) cudaFreeHost(bufs[i].p);
+    if (result == TDG_OK && totals) result = tdg_file_totals(ctx, totals);
+    return result;
+}
+
+}  // extern "C"

@@ -1,0 +1,262 @@
+"""Parity of the CUDA path with the oracle (run with -m gpu on a B200).
+
+Everything goes through the C ABI (ctypes -> libtagdigger_b200.so): whole files
+via tdg_count_file, host images via tdg_submit, device-resident chunks via
+tdg_count_device.  The bar is bit-exact counts (integer work)."""
+
+import gzip
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import file_bytes, load_golden, materialize
+from helpers import fastq_of, line_soup, rand_seq, small_setup
+from oracle import c_oracle
+from oracle import tagdigger_oracle as orc
+from tagdigger_b200 import _native, counting, matchset, synth
+
+pytestmark = pytest.mark.gpu
+
+FIND = [c for c in load_golden("find_tags.json") if not c["kwargs"].get("tassel_tagcount")]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return counting.get_engine(0)
+
+
+@pytest.mark.parametrize("i", range(len(FIND)))
+def test_find_tags_fastq_golden(i, in_tmp):
+    """The cases recorded from the reference itself, through the drop-in."""
+    case = FIND[i]
+    materialize(case["files"], in_tmp)
+    try:
+        ret, exc = counting.find_tags_fastq(*case["args"], **case["kwargs"]), None
+    except matchset.DegenerateTree:
+        assert case["exc"] is not None and case["exc"][0] in ("IndexError", "TypeError")
+        return
+    except BaseException as e:  # noqa: BLE001
+        ret, exc = None, [type(e).__name__, str(e)]
+    if case["exc"] is not None:
+        assert exc is not None and exc[0] == case["exc"][0], (exc, case["exc"])
+        if exc[0] == "AssertionError":
+            assert exc[1] == case["exc"][1]
+    else:
+        assert exc is None, exc
+        assert ret == case["ret"]
+
+
+def _oracle(data, barcodes, tags, cutsite="TGCAG", maxreads=5e9):
+    cnt = c_oracle.Counter(barcodes, tags, cutsite)
+    m, tot = cnt.count(data, maxreads)
+    return m.tolist(), tot, c_oracle.count_lines(data)
+
+
+@pytest.mark.parametrize("cutsite,newline,lengths", [
+    ("TGCAG", b"\n", None),
+    ("TGCAG", b"\r\n", None),
+    ("TGCAG", b"\r", None),
+    ("CWGC", b"\n", (20, 64)),
+    ("TGCAG", b"\n", (20, 64)),
+    ("TGCAG", b"\n", (70, 150)),
+    ("", b"\n", (25, 40)),
+])
+def test_synthetic_against_c_oracle(cutsite, newline, lengths):
+    rng = np.random.default_rng(abs(hash((cutsite, newline, lengths))) % 2**32)
+    site = orc.expand_cut_site(cutsite)[0]
+    bcs = synth.make_barcodes(24, rng, cutsite=site)
+    L = None if lengths is None else rng.integers(lengths[0], lengths[1] + 1, size=300)
+    _, _, seqs = synth.make_marker_pairs(300, rng, cutsite=site, lengths=L)
+    tags = [s for p in seqs for s in p]
+    readlen = 100 if lengths is None or lengths[1] <= 64 else 180
+    fq, truth = synth.make_fastq(60000, bcs, tags, rng, cutsite=site, newline=newline, readlen=readlen)
+    want, wtot, wlines = _oracle(fq, bcs, tags, cutsite)
+    tot = []
+    got = counting.find_tags_bytes(fq, bcs, tags, cutsite, totals=tot)
+    assert got == want
+    assert tot[:3] == wtot and tot[3] == wlines
+    assert (np.asarray(got) >= truth["expected"]).all()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_line_soup(seed):
+    """Arbitrary text: mixed line ends, blank lines, whitespace, truncated
+    lines, no final newline -- the line index must track Python's."""
+    r = random.Random(seed)
+    cutsite = r.choice(["TGCAG", "CWGC", "TGCAG"])
+    site = orc.expand_cut_site(cutsite)[0]
+    barcodes, tags = small_setup(r, site)
+    kinds = [("\n",), ("\r\n",), ("\r",), ("\n", "\r\n", "\r"), ("\n", "\r")][seed % 5]
+    data = line_soup(r, barcodes, tags, site, r.randint(500, 4000), kinds,
+                     final_newline=r.random() < 0.5, max_pad=r.choice([4, 40, 700]))
+    want, wtot, wlines = _oracle(data, barcodes, tags, cutsite)
+    assert want == orc.find_tags_text(data, barcodes, tags, cutsite)      # C oracle == Python oracle here
+    tot = []
+    got = counting.find_tags_bytes(data, barcodes, tags, cutsite, totals=tot)
+    assert got == want
+    assert tot[:3] == wtot and tot[3] == wlines
+    # the same image in random pieces (carry-over of partial lines)
+    cuts = sorted(r.sample(range(1, len(data)), min(7, len(data) - 1)))
+    tot2 = []
+    assert counting.find_tags_bytes(data, barcodes, tags, cutsite, totals=tot2, pieces=cuts) == want
+    assert tot2 == tot
+
+
+def test_unicode_whitespace_and_non_ascii():
+    barcodes, tags = ["AACG"], ["TGCAGCCCC", "TGCAGAAAA"]
+    reads = ["\u00a0AACGTGCAGCCCC", " \u3000 AACGTGCAGAAAAT", "AACGTGCAG\u00e9CCCC", "\u00e9AACGTGCAGCCCC",
+             "AACGTGCAGCCCC\u2009", "aacgtgcagcccc", "\u2003\u2028AACGTGCAGCCCC",
+             "\u0085\u1680\u205f\u202fAACGTGCAGCCCC"]
+    data = fastq_of([s.encode("utf-8") for s in reads])
+    data = data.replace(b"@r3", "@rü3".encode("utf-8"))
+    want = orc.find_tags_text(data, barcodes, tags)
+    assert c_oracle.find_tags_bytes(data, barcodes, tags) == want
+    assert counting.find_tags_bytes(data, barcodes, tags) == want
+    assert want == [[5, 1]]
+
+
+@pytest.mark.parametrize("delta", [-3, -2, -1, 0, 1, 2, 3, 17])
+def test_device_chunk_sizes_around_tile_edges(eng, delta):
+    """tdg_count_device with n just below / at / above multiples of the tile
+    size, and line ends falling exactly on tile and chunk boundaries."""
+    r = random.Random(7 + delta)
+    barcodes, tags = small_setup(r)
+    for ntiles in (1, 2, 5):
+        n = ntiles * _native.TDG_TILE_BYTES + delta
+        data = line_soup(r, barcodes, tags, "TGCAG", 3000, ("\n", "\r\n", "\r") if delta % 2 else ("\n",))
+        data = (data * (n // len(data) + 1))[:n]
+        # force interesting bytes at the edges
+        for pos, ch in ((_native.TDG_TILE_BYTES - 1, b"\n"), (_native.TDG_TILE_BYTES, b"\r"), (n - 1, b"\r" if delta % 2 else b"\n")):
+            if 0 <= pos < n:
+                data = data[:pos] + ch + data[pos + 1:]
+        want, wtot, wlines = _oracle(data, barcodes, tags)
+        p = matchset.plan(barcodes, tags, "TGCAG")
+        counting.load_plan(eng, p, nrows=p.barnum)
+        dev, nb = eng.upload(data)
+        try:
+            eng.count_device(dev, nb)
+            tot = eng.file_totals()
+            got = eng.read_matrix().tolist()
+            lines_only = eng.count_lines_device(dev, nb)
+        finally:
+            eng.device_free(dev)
+        assert got == want
+        assert tot[:3] == wtot
+        last = data[-1:]
+        # next_line = number of lines that have started = lines Python iterates
+        assert tot[3] == wlines == lines_only[0]
+        assert lines_only[1] == (1 if last == b"\n" else 2 if last == b"\r" else 3)
+
+
+def test_chunk_chaining_matches_whole(eng):
+    """A file given as several device chunks cut at line ends, chained on the
+    device, with explicit line bases, equals the whole."""
+    r = random.Random(99)
+    barcodes, tags = small_setup(r, ntag=20)
+    reads = [r.choice(barcodes) + r.choice(tags) + rand_seq(r, 20) for _ in range(5000)]
+    data = fastq_of(reads)
+    want, wtot, _ = _oracle(data, barcodes, tags)
+    p = matchset.plan(barcodes, tags, "TGCAG")
+    cuts = [0]
+    for frac in (0.2, 0.5, 0.9):
+        cuts.append(data.index(b"\n", int(len(data) * frac)) + 1)      # arbitrary LINE (not record) ends
+    cuts.append(len(data))
+    for mode in ("chained", "explicit"):
+        counting.load_plan(eng, p, nrows=p.barnum)
+        line = 0
+        bufs = []
+        for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+            dev, nb = eng.upload(data[a:b])
+            bufs.append(dev)
+            if mode == "chained" and k > 0:
+                eng.count_device(dev, nb, _native.TDG_LINE_CHAINED, 0)
+            else:
+                eng.count_device(dev, nb, line, _native.TDG_PREV_NONE if k == 0 else _native.TDG_PREV_LF)
+            line += data[a:b].count(b"\n")
+        got = eng.read_matrix().tolist()
+        tot = eng.file_totals()
+        for d in bufs:
+            eng.device_free(d)
+        assert got == want, mode
+        if mode == "chained":
+            assert tot[:3] == wtot
+
+
+@pytest.mark.parametrize("maxreads", [0, 1, 2.5, 7, 1000, 4999, 5000, 1e12])
+def test_maxreads(maxreads):
+    r = random.Random(5)
+    barcodes, tags = small_setup(r)
+    reads = [r.choice(barcodes) + r.choice(tags) + "ACGT" for _ in range(5000)]
+    data = fastq_of(reads)
+    want, wtot, _ = _oracle(data, barcodes, tags, maxreads=maxreads)
+    tot = []
+    assert counting.find_tags_bytes(data, barcodes, tags, maxreads=maxreads, totals=tot) == want
+    assert tot[:3] == wtot
+
+
+def test_files_plain_and_gzip(tmp_path):
+    rng = np.random.default_rng(3)
+    bcs = synth.make_barcodes(12, rng)
+    _, _, seqs = synth.make_marker_pairs(80, rng)
+    tags = [s for p in seqs for s in p]
+    fq, _ = synth.make_fastq(30000, bcs, tags, rng)
+    want, wtot, _ = _oracle(fq, bcs, tags)
+    plain = str(tmp_path / "reads.fastq")
+    with open(plain, "wb") as fh:
+        fh.write(fq)
+    gz = str(tmp_path / "reads.fastq.gz")
+    with gzip.open(gz, "wb", compresslevel=1) as fh:
+        fh.write(fq)
+    multi = str(tmp_path / "multi.fq.GZ")          # two gzip members, upper-case suffix
+    cut = fq.index(b"\n", len(fq) // 2) + 1
+    with open(multi, "wb") as fh:
+        fh.write(gzip.compress(fq[:cut]) + gzip.compress(fq[cut:]))
+    for path in (plain, gz, multi):
+        tot = []
+        assert counting.find_tags_fastq(path, bcs, tags, totals=tot) == want, path
+        assert tot == wtot
+    notgz = str(tmp_path / "plain_named.gz")
+    with open(notgz, "wb") as fh:
+        fh.write(fq[:1000])
+    with pytest.raises(gzip.BadGzipFile):
+        counting.find_tags_fastq(notgz, bcs, tags)
+    with pytest.raises(FileNotFoundError):
+        counting.find_tags_fastq(str(tmp_path / "missing.fq"), bcs, tags)
+
+
+def test_small_chunks_force_many_pieces():
+    """A context with tiny chunk_bytes: every piece boundary lands mid-line."""
+    rng = np.random.default_rng(8)
+    bcs = synth.make_barcodes(8, rng)
+    _, _, seqs = synth.make_marker_pairs(40, rng)
+    tags = [s for p in seqs for s in p]
+    fq, _ = synth.make_fastq(20000, bcs, tags, rng)
+    want, wtot, wlines = _oracle(fq, bcs, tags)
+    eng = _native.Engine(0, chunk_bytes=50000)
+    p = matchset.plan(bcs, tags, "TGCAG")
+    counting.load_plan(eng, p, nrows=p.barnum)
+    eng.submit(fq)
+    eng.end_file()
+    assert eng.read_matrix().tolist() == want
+    assert eng.file_totals() == wtot + [wlines]
+    eng.close()
+
+
+def test_two_million_reads_config1_shape():
+    """BASELINE config 1 shape (96 barcodes, 1000 biallelic pairs, PstI) at
+    2 M reads against the C oracle, plus the by-construction lower bound."""
+    rng = np.random.default_rng(20161)
+    bcs = synth.make_barcodes(96, rng)
+    _, _, seqs = synth.make_marker_pairs(1000, rng)
+    tags = [s for p in seqs for s in p]
+    fq, truth = synth.make_fastq(2000000, bcs, tags, rng)
+    cnt = c_oracle.Counter(bcs, tags)
+    want, wtot = cnt.count(fq)
+    tot = []
+    got = np.asarray(counting.find_tags_bytes(fq, bcs, tags, totals=tot))
+    assert (got == want).all()
+    assert tot[:3] == wtot
+    assert (got >= truth["expected"]).all()
+    assert got.sum() == tot[2]
