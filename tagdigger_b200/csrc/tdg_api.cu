@@ -18,7 +18,7 @@
 #include "tdg_kernel.cuh"
 #include "tdg_tables.h"
 
-static_assert(TDG_TILE_BYTES == tdg::TILE, "header and kernel disagree on the tile size");
+static_assert(TDG_TILE_BYTES % tdg::TILE == 0, "the padding granule must be a multiple of the kernel tile");
 static_assert(TDG_HALO_BYTES == tdg::HALO, "header and kernel disagree on the halo size");
 
 namespace {
@@ -62,10 +62,14 @@ struct tdg_ctx {
     int32_t *d_matrix = nullptr;
     bool own_matrix = false;
     uint32_t rows = 0, cols = 0;
+    uint32_t max_row = 0, max_col = 0;   // largest indices the loaded tables refer to
 
-    // per-launch scratch: [0] ticket, [8..] tile descriptors
+    // per-launch scratch (ScratchHeader, SegInfo[], FixEntry[])
     unsigned long long *d_sync = nullptr;
-    size_t sync_cap = 0;
+    size_t sync_cap = 0;          // in 8-byte words
+    int occ_match = 0, occ_lines = 0;
+    size_t occ_match_smem = 0, occ_lines_smem = 0;
+    uint32_t force_seg_tiles = 0; // test hook (TDG_SEG_TILES)
     tdg::LineState *d_state = nullptr;   // [2]
     int state_cur = 0;
     unsigned long long *d_totals = nullptr;   // [4]
@@ -101,9 +105,17 @@ int fail(tdg_ctx *ctx, int code, const std::string &msg)
 
 size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
-int ensure_sync(tdg_ctx *ctx, size_t tiles)
+// per-launch scratch: header, then SegInfo[num_segs], then FixEntry[num_segs]
+struct ScratchHeader {
+    unsigned long long ticket_main, ticket_fix;
+    uint32_t n_fix, last_kind;
+    unsigned long long pad;
+};
+static_assert(sizeof(ScratchHeader) == 32, "scratch header layout");
+
+int ensure_sync(tdg_ctx *ctx, size_t segs)
 {
-    size_t need = 8 + tiles;
+    size_t need = (sizeof(ScratchHeader) + segs * (sizeof(tdg::SegInfo) + sizeof(tdg::FixEntry)) + 7) / 8;
     if (need <= ctx->sync_cap) return TDG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_sync) CK(cudaFree(ctx->d_sync));
@@ -115,6 +127,16 @@ int ensure_sync(tdg_ctx *ctx, size_t tiles)
 }
 
 template <bool MATCH>
+int kernel_geometry(tdg_ctx *ctx, size_t smem, int *per_sm)
+{
+    auto kern = tdg::count_kernel<MATCH>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, tdg::THREADS, smem));
+    if (*per_sm < 1) return fail(ctx, TDG_ERR_CUDA, "counting kernel does not fit on an SM");
+    return TDG_OK;
+}
+
+template <bool MATCH>
 int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_base, int prev_kind,
                  uint64_t reads_limit)
 {
@@ -122,31 +144,61 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
     if (n == 0) return TDG_OK;
     if (((uintptr_t)dev_bytes & 15u) != 0) return fail(ctx, TDG_ERR_ARG, "device chunk must be 16-byte aligned");
     size_t tiles = (n + TILE - 1) / TILE;
-    if (tiles >= 0xFFFFFFFFull) return fail(ctx, TDG_ERR_ARG, "chunk too large (limit 2^32 - 2 tiles of 16 KiB)");
-    int rc = ensure_sync(ctx, tiles);
+    if (tiles >= 0xFFFFFFFFull) return fail(ctx, TDG_ERR_ARG, "chunk too large (limit 2^32 - 2 tiles)");
+
+    size_t bar_smem = 0;
+    if (MATCH && ctx->bar_blob.size() <= BAR_SMEM_MAX) bar_smem = round_up(ctx->bar_blob.size(), 16);
+    size_t smem = (size_t)STAGES * STAGE_STRIDE + STARTS_CAP * sizeof(uint16_t) + bar_smem;
+    int &per_sm = MATCH ? ctx->occ_match : ctx->occ_lines;
+    size_t &occ_smem = MATCH ? ctx->occ_match_smem : ctx->occ_lines_smem;
+    if (per_sm == 0 || occ_smem != smem) {
+        int rc = kernel_geometry<MATCH>(ctx, smem, &per_sm);
+        if (rc) return rc;
+        occ_smem = smem;
+    }
+    size_t max_grid = (size_t)per_sm * ctx->sm_count;
+    // segments: runs of consecutive tiles handed to one CTA; about 8 per CTA for
+    // load balance, at most 64 tiles (the fix pass redoes whole segments)
+    size_t seg_tiles = tiles / (max_grid * 8);
+    if (seg_tiles < 1) seg_tiles = 1;
+    if (seg_tiles > 64) seg_tiles = 64;
+    if (ctx->force_seg_tiles) seg_tiles = ctx->force_seg_tiles;
+    size_t segs = (tiles + seg_tiles - 1) / seg_tiles;
+    size_t grid = segs < max_grid ? segs : max_grid;
+
+    int rc = ensure_sync(ctx, segs);
     if (rc) return rc;
-    CK(cudaMemsetAsync(ctx->d_sync, 0, (8 + tiles) * sizeof(unsigned long long), ctx->stream));
+    ScratchHeader *hdr = (ScratchHeader *)ctx->d_sync;
+    SegInfo *seginfo = (SegInfo *)(hdr + 1);
+    FixEntry *fix = (FixEntry *)(seginfo + segs);
+    CK(cudaMemsetAsync(hdr, 0, sizeof(ScratchHeader), ctx->stream));
 
     ChunkArgs a;
     memset(&a, 0, sizeof(a));
     a.bytes = (const uint8_t *)dev_bytes;
     a.n = n;
     a.num_tiles = (uint32_t)tiles;
+    a.seg_tiles = (uint32_t)seg_tiles;
+    a.num_segs = (uint32_t)segs;
+    a.mode = MODE_MAIN;
+    VerifyArgs v;
+    memset(&v, 0, sizeof(v));
     if (line_base == TDG_LINE_CHAINED) {
-        a.use_arg_state = 0;
+        a.use_arg_state = v.use_arg_state = 0;
     } else {
-        a.use_arg_state = 1;
-        a.line_base = line_base;
-        a.prev_kind = (uint32_t)prev_kind;
+        a.use_arg_state = v.use_arg_state = 1;
+        a.line_base = v.line_base = line_base;
+        a.prev_kind = v.prev_kind = (uint32_t)prev_kind;
     }
-    a.match = MATCH ? 1 : 0;
-    a.state_in = ctx->d_state + ctx->state_cur;
-    a.state_out = ctx->d_state + (ctx->state_cur ^ 1);
+    a.state_in = v.state_in = ctx->d_state + ctx->state_cur;
+    v.state_out = ctx->d_state + (ctx->state_cur ^ 1);
     ctx->state_cur ^= 1;
-    a.desc = ctx->d_sync + 8;
-    a.ticket = ctx->d_sync;
+    a.ticket = &hdr->ticket_main;
+    a.seginfo = seginfo;
+    a.last_kind = &hdr->last_kind;
+    a.fix = fix;
+    a.n_fix = &hdr->n_fix;
     a.reads_limit = reads_limit;
-    size_t bar_smem = 0;
     if (MATCH) {
         a.bar = (const BarTable *)ctx->d_bar;
         a.bar_bytes = (uint32_t)ctx->bar_blob.size();
@@ -156,23 +208,33 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
         a.tags.ext = ctx->d_ext;
         a.matrix = ctx->d_matrix;
         a.totals = ctx->d_totals;
-        if (a.bar_bytes <= BAR_SMEM_MAX) bar_smem = round_up(a.bar_bytes, 16);
     }
-    size_t smem = (size_t)STAGES * STAGE_STRIDE + STARTS_CAP * sizeof(uint16_t) + bar_smem;
-    auto kern = count_kernel<MATCH>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-    if (per_sm < 1) return fail(ctx, TDG_ERR_CUDA, "counting kernel does not fit on an SM");
-    size_t grid = (size_t)per_sm * ctx->sm_count;
-    if (grid > tiles) grid = tiles;
+    v.num_segs = (uint32_t)segs;
+    v.make_fixes = MATCH ? 1 : 0;
+    v.reads_limit = reads_limit;
+    v.seginfo = seginfo;
+    v.last_kind = &hdr->last_kind;
+    v.fix = fix;
+    v.n_fix = &hdr->n_fix;
 
+    auto kern = count_kernel<MATCH>;
     bool timed = ctx->timing && ctx->tev_used + 2 <= MAX_TIMED * 2;
     if (timed) CK(cudaEventRecord(ctx->tev[ctx->tev_used++], ctx->stream));
     kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
+    verify_kernel<<<1, VERIFY_THREADS, 0, ctx->stream>>>(v);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    if (MATCH) {
+        // redo mis-numbered segments (none for well-formed FASTQ: the CTAs exit at once)
+        a.mode = MODE_FIX;
+        a.ticket = &hdr->ticket_fix;
+        size_t fgrid = 2 * segs < max_grid ? 2 * segs : max_grid;
+        kern<<<(unsigned)fgrid, THREADS, smem, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        ctx->launches += 1;
+    }
     if (timed) CK(cudaEventRecord(ctx->tev[ctx->tev_used++], ctx->stream));
-    ctx->launches += 1;
     return TDG_OK;
 }
 
@@ -190,6 +252,8 @@ int need_ready(tdg_ctx *ctx)
     if (!ctx->have_tags) return fail(ctx, TDG_ERR_STATE, "tdg_set_tags has not been called");
     if (!ctx->d_matrix) return fail(ctx, TDG_ERR_STATE, "tdg_set_matrix / tdg_bind_matrix has not been called");
     if (!ctx->have_bar) return fail(ctx, TDG_ERR_STATE, "tdg_begin_file has not been called");
+    if (ctx->max_col >= ctx->cols) return fail(ctx, TDG_ERR_ARG, "a tag column lies outside the matrix");
+    if (ctx->max_row >= ctx->rows) return fail(ctx, TDG_ERR_ARG, "a barcode row lies outside the matrix");
     return TDG_OK;
 }
 
@@ -365,6 +429,7 @@ int tdg_create(tdg_ctx **out, int device, size_t chunk_bytes)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->chunk_bytes = chunk_bytes ? chunk_bytes : ((size_t)64 << 20);
+    if (const char *e = getenv("TDG_SEG_TILES")) c->force_seg_tiles = (uint32_t)atoi(e);
     if (c->chunk_bytes < 4096) c->chunk_bytes = 4096;
     cudaError_t e2 = cudaSuccess;
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -416,9 +481,10 @@ int tdg_set_tags(tdg_ctx *ctx, const char *bases, const uint64_t *off, const int
     ctx->have_tags = false;
     std::string why = tdg::build_tag_table(bases, off, col, ntags, flags, ctx->tags);
     if (!why.empty()) return fail(ctx, TDG_ERR_ARG, "tdg_set_tags: " + why);
-    if (ctx->cols) {
-        for (uint32_t i = 0; i < ntags; i++)
-            if (col[i] < 0 || (uint32_t)col[i] >= ctx->cols) return fail(ctx, TDG_ERR_ARG, "tdg_set_tags: column out of range");
+    ctx->max_col = 0;
+    for (uint32_t i = 0; i < ntags; i++) {
+        if (col[i] < 0) return fail(ctx, TDG_ERR_ARG, "tdg_set_tags: negative column");
+        if ((uint32_t)col[i] > ctx->max_col) ctx->max_col = (uint32_t)col[i];
     }
     if (!ctx->hostonly) {
         CK(cudaSetDevice(ctx->device));
@@ -495,9 +561,10 @@ int tdg_begin_file(tdg_ctx *ctx, const char *bases, const uint32_t *off, const i
     ctx->have_bar = false;
     std::string why = tdg::build_bar_table(bases, off, row, tag_off, npat, flags, ctx->bar_blob);
     if (!why.empty()) return fail(ctx, TDG_ERR_ARG, "tdg_begin_file: " + why);
-    if (ctx->rows) {
-        for (uint32_t i = 0; i < npat; i++)
-            if (row[i] < 0 || (uint32_t)row[i] >= ctx->rows) return fail(ctx, TDG_ERR_ARG, "tdg_begin_file: row out of range");
+    ctx->max_row = 0;
+    for (uint32_t i = 0; i < npat; i++) {
+        if (row[i] < 0) return fail(ctx, TDG_ERR_ARG, "tdg_begin_file: negative row");
+        if ((uint32_t)row[i] > ctx->max_row) ctx->max_row = (uint32_t)row[i];
     }
     if (!ctx->hostonly) {
         CK(cudaSetDevice(ctx->device));

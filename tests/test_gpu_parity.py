@@ -260,3 +260,41 @@ def test_two_million_reads_config1_shape():
     assert tot[:3] == wtot
     assert (got >= truth["expected"]).all()
     assert got.sum() == tot[2]
+
+
+@pytest.mark.parametrize("seg_tiles", [2, 5])
+def test_multi_tile_segments_and_fix_pass(seg_tiles, monkeypatch):
+    """Segments of several tiles (TDG_SEG_TILES test hook) on text whose FASTQ
+    structure guess is wrong most of the time: exercises verify + fix pass, and
+    a read limit that falls inside a segment."""
+    monkeypatch.setenv("TDG_SEG_TILES", str(seg_tiles))
+    eng = _native.Engine(0)
+    r = random.Random(40 + seg_tiles)
+    barcodes, tags = small_setup(r)
+    p = matchset.plan(barcodes, tags, "TGCAG")
+    for kinds, limit in ((("\n",), None), (("\n", "\r\n", "\r"), None), (("\n",), 777), (("\r",), 1500)):
+        data = line_soup(r, barcodes, tags, "TGCAG", 9000, kinds)
+        want, wtot, wlines = _oracle(data, barcodes, tags, maxreads=limit or 5e9)
+        counting.load_plan(eng, p, nrows=p.barnum)
+        dev, nb = eng.upload(data)
+        eng.count_device(dev, nb, reads_limit=_native.limit_from_maxreads(limit or 5e9))
+        got = eng.read_matrix().tolist()
+        tot = eng.file_totals()
+        eng.device_free(dev)
+        assert got == want
+        assert tot[:3] == wtot
+        if limit is None:
+            assert tot[3] == wlines
+    # well-formed FASTQ shifted by one and two extra leading lines: every guess is
+    # right except where the structure is ambiguous; result must still be exact
+    reads = [r.choice(barcodes) + r.choice(tags) + rand_seq(r, 30) for _ in range(4000)]
+    for lead in (b"", b"x\n", b"x\ny\n", b"x\ny\nz\n"):
+        data = lead + fastq_of(reads)
+        want, wtot, _ = _oracle(data, barcodes, tags)
+        counting.load_plan(eng, p, nrows=p.barnum)
+        dev, nb = eng.upload(data)
+        eng.count_device(dev, nb)
+        assert eng.read_matrix().tolist() == want
+        assert eng.file_totals()[:3] == wtot
+        eng.device_free(dev)
+    eng.close()
