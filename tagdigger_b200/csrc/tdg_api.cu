@@ -805,7 +805,7 @@ int64_t tdg_selftest_match(tdg_ctx *ctx, const char *read, size_t len)
     size_t pos = 0;
     while (pos < len) {
         uint32_t c = p[pos];
-        if (tdg::is_space(c)) { pos++; continue; }
+        if (tdg::is_lead_space(c)) { pos++; continue; }
         if (c >= 0xC2 && c <= 0xE3 && pos + 2 < len) {
             uint32_t u = tdg::utf8_space(c, p[pos + 1], p[pos + 2]);
             if (u) { pos += u; continue; }

@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const ChunkArgs a)
                         const uint32_t staged = avail < STAGE_BYTES ? (uint32_t)avail : STAGE_BYTES;
                         while (pos < staged) {
                             uint32_t c = buf[pos];
-                            if (is_space(c)) { pos++; continue; }
+                            if (is_lead_space(c)) { pos++; continue; }
                             if (c >= 0xC2 && c <= 0xE3 && pos + 2 < staged) {
                                 uint32_t u = utf8_space(c, buf[pos + 1], buf[pos + 2]);
                                 if (u) { pos += u; continue; }
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const ChunkArgs a)
                             unsigned long long gp = pos;
                             while (gp < avail) {
                                 uint32_t c = g[gp];
-                                if (is_space(c)) { gp++; continue; }
+                                if (is_lead_space(c)) { gp++; continue; }
                                 if (c >= 0xC2 && c <= 0xE3 && gp + 2 < avail) {
                                     uint32_t u = utf8_space(c, g[gp + 1], g[gp + 2]);
                                     if (u) { gp += u; continue; }

@@ -211,9 +211,13 @@ TDG_HD MatchResult match_line(const Fetch &f, const BarTable *bar, const BarEntr
     return r;
 }
 
-TDG_HD bool is_space(uint32_t c)     // str.strip() whitespace, ASCII part
+// str.strip() whitespace (ASCII part) that can PRECEDE the sequence inside a
+// line.  '\n' and '\r' are whitespace too, but they end the line (universal
+// newlines): the scan for the first character must stop at them, so that an
+// empty or blank line stays empty instead of running into the next line.
+TDG_HD bool is_lead_space(uint32_t c)
 {
-    return (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x20);
+    return c == 0x09 || c == 0x0b || c == 0x0c || (c >= 0x1c && c <= 0x20);
 }
 
 // Length in bytes of the UTF-8 encoded Unicode whitespace character that starts
