@@ -99,6 +99,10 @@ int         tdg_begin_file(tdg_ctx *ctx, const char *bases, const uint32_t *off,
                            const int32_t *row, const uint32_t *tag_off,
                            uint32_t npat, uint32_t flags);
 
+/* Start the same file (same barcode table) again: resets the line counter and the
+ * per-file totals only. */
+int         tdg_reset_file(tdg_ctx *ctx);
+
 /* Stream raw (uncompressed) FASTQ bytes from HOST memory: H2D copies and the
  * counting kernel, pipelined over `chunk_bytes` pieces.  Successive calls for one
  * file must pass the file's bytes in order; a trailing partial line is carried

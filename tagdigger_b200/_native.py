@@ -31,7 +31,7 @@ TDG_HALO_BYTES = 512
 NO_LIMIT = (1 << 63)
 
 EXPORTS = """tdg_abi_version tdg_create tdg_destroy tdg_last_error tdg_set_tags tdg_set_matrix
-tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_submit tdg_end_file tdg_count_device
+tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end_file tdg_count_device
 tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
@@ -95,6 +95,7 @@ def lib():
         "tdg_bind_matrix": (i32, [vp, vp, u32, u32]),
         "tdg_zero_matrix": (i32, [vp]),
         "tdg_begin_file": (i32, [vp, vp, vp, vp, vp, u32, u32]),
+        "tdg_reset_file": (i32, [vp]),
         "tdg_submit": (i32, [vp, vp, sz, u64]),
         "tdg_end_file": (i32, [vp, u64]),
         "tdg_count_device": (i32, [vp, vp, sz, u64, i32, u64]),
@@ -213,6 +214,9 @@ class Engine(object):
         toff = np.asarray(list(tag_offs), dtype=np.uint32)
         self._ck(self._L.tdg_begin_file(self._h, blob, off.ctypes.data, row.ctypes.data, toff.ctypes.data,
                                         len(patterns), TDG_ANY_BASE if any_base else 0))
+
+    def reset_file(self):
+        self._ck(self._L.tdg_reset_file(self._h))
 
     # -- counting ----------------------------------------------------------
     def submit(self, data, reads_limit=NO_LIMIT):

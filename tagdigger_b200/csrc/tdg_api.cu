@@ -587,6 +587,19 @@ int tdg_begin_file(tdg_ctx *ctx, const char *bases, const uint32_t *off, const i
     return TDG_OK;
 }
 
+int tdg_reset_file(tdg_ctx *ctx)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!ctx->have_bar) return fail(ctx, TDG_ERR_STATE, "tdg_begin_file has not been called");
+    if (ctx->carry_len) return fail(ctx, TDG_ERR_STATE, "previous file was not ended (tdg_end_file)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_state, 0, 2 * sizeof(tdg::LineState), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_totals, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    ctx->state_cur = 0;
+    return TDG_OK;
+}
+
 int tdg_submit(tdg_ctx *ctx, const void *bytes, size_t n, uint64_t reads_limit)
 {
     int rc = need_ready(ctx);
