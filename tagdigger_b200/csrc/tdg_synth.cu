@@ -119,7 +119,7 @@ __device__ inline uint8_t seq_char(const Params &P, const Tables &T, const Rec &
     return ch;
 }
 
-__global__ void lengths_kernel(Params P, Tables T, uint64_t first, uint64_t n, uint32_t *len, int32_t *expected)
+__global__ void lengths_kernel(Params P, Tables T, uint64_t first, uint64_t n, uint64_t *len, int32_t *expected)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -197,8 +197,8 @@ int tdgs_generate(int device, uint64_t seed, uint64_t first, uint64_t n, uint32_
     P.p_hit = probs[0]; P.p_unknown = probs[1]; P.p_nobar = probs[2];
     P.p_n = probs[3]; P.p_lower = probs[4]; P.p_short = probs[5]; P.p_qual_at = probs[6];
     uint8_t *dbar = nullptr, *dtag = nullptr;
-    uint32_t *dbl = nullptr, *dtl = nullptr, *dcdf = nullptr, *dlen = nullptr;
-    uint64_t *doff = nullptr;
+    uint32_t *dbl = nullptr, *dtl = nullptr, *dcdf = nullptr;
+    uint64_t *doff = nullptr, *dlen = nullptr;   // 64-bit lengths: the scan accumulates in its input type
     void *tmp = nullptr;
     CKS(cudaMalloc(&dbar, (size_t)nbar * bar_stride));
     CKS(cudaMalloc(&dtag, (size_t)ntags * tag_stride));
@@ -211,9 +211,9 @@ int tdgs_generate(int device, uint64_t seed, uint64_t first, uint64_t n, uint32_
     CKS(cudaMemcpy(dtl, tag_len, ntags * 4, cudaMemcpyHostToDevice));
     CKS(cudaMemcpy(dcdf, tag_cdf, ntags * 4, cudaMemcpyHostToDevice));
     T.bar = dbar; T.bar_len = dbl; T.tag = dtag; T.tag_len = dtl; T.tag_cdf = dcdf;
-    CKS(cudaMalloc(&dlen, (n + 1) * sizeof(uint32_t)));
+    CKS(cudaMalloc(&dlen, (n + 1) * sizeof(uint64_t)));
     CKS(cudaMalloc(&doff, (n + 1) * sizeof(uint64_t)));
-    CKS(cudaMemset(dlen + n, 0, sizeof(uint32_t)));
+    CKS(cudaMemset(dlen + n, 0, sizeof(uint64_t)));
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (n) lengths_kernel<<<blocks, 256>>>(P, T, first, n, dlen, d_expected);
     CKS(cudaGetLastError());
