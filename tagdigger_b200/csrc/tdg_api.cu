@@ -18,7 +18,6 @@
 #include "tdg_kernel.cuh"
 #include "tdg_tables.h"
 
-static_assert(TDG_TILE_BYTES % tdg::TILE == 0, "the padding granule must be a multiple of the kernel tile");
 static_assert(TDG_HALO_BYTES == tdg::HALO, "header and kernel disagree on the halo size");
 
 namespace {
@@ -70,6 +69,7 @@ struct tdg_ctx {
     int occ_match = 0, occ_lines = 0;
     size_t occ_match_smem = 0, occ_lines_smem = 0;
     uint32_t force_seg_tiles = 0; // test hook (TDG_SEG_TILES)
+    bool force_general = false;   // test hook (TDG_GENERAL=1): never use the fast matcher
     tdg::LineState *d_state = nullptr;   // [2]
     int state_cur = 0;
     unsigned long long *d_totals = nullptr;   // [4]
@@ -148,7 +148,7 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
 
     size_t bar_smem = 0;
     if (MATCH && ctx->bar_blob.size() <= BAR_SMEM_MAX) bar_smem = round_up(ctx->bar_blob.size(), 16);
-    size_t smem = (size_t)STAGES * STAGE_STRIDE + STARTS_CAP * sizeof(uint16_t) + bar_smem;
+    size_t smem = SMEM_FIXED + bar_smem;
     int &per_sm = MATCH ? ctx->occ_match : ctx->occ_lines;
     size_t &occ_smem = MATCH ? ctx->occ_match_smem : ctx->occ_lines_smem;
     if (per_sm == 0 || occ_smem != smem) {
@@ -157,14 +157,16 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
         occ_smem = smem;
     }
     size_t max_grid = (size_t)per_sm * ctx->sm_count;
-    // segments: runs of consecutive tiles handed to one CTA; about 8 per CTA for
+    size_t workers = max_grid * WARPS;      // every warp is an independent pipeline
+    // segments: runs of consecutive tiles handed to one warp; about 8 per warp for
     // load balance, at most 64 tiles (the fix pass redoes whole segments)
-    size_t seg_tiles = tiles / (max_grid * 8);
+    size_t seg_tiles = tiles / (workers * 8);
     if (seg_tiles < 1) seg_tiles = 1;
     if (seg_tiles > 64) seg_tiles = 64;
     if (ctx->force_seg_tiles) seg_tiles = ctx->force_seg_tiles;
     size_t segs = (tiles + seg_tiles - 1) / seg_tiles;
-    size_t grid = segs < max_grid ? segs : max_grid;
+    size_t grid = (segs + WARPS - 1) / WARPS;
+    if (grid > max_grid) grid = max_grid;
 
     int rc = ensure_sync(ctx, segs);
     if (rc) return rc;
@@ -199,7 +201,17 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
     a.fix = fix;
     a.n_fix = &hdr->n_fix;
     a.reads_limit = reads_limit;
+    a.halo_bytes = HALO;
     if (MATCH) {
+        const BarTable *hbar = (const BarTable *)ctx->bar_blob.data();
+        a.fast_words = ctx->force_general ? 0 : fast_words_for(hbar, ctx->tags.t);
+        if (a.fast_words) {
+            // the fast matcher reads whole 4-word groups from the aligned word of the line start
+            uint32_t need = hbar->max_tag_off + ctx->tags.t.max_len + 36u;
+            uint32_t touch = 4u * a.fast_words + 16u;
+            uint32_t h = (std::max(need, touch) + 15u) & ~15u;
+            a.halo_bytes = std::min<uint32_t>(std::max<uint32_t>(h, 128u), HALO);
+        }
         a.bar = (const BarTable *)ctx->d_bar;
         a.bar_bytes = (uint32_t)ctx->bar_blob.size();
         a.cols = ctx->cols;
@@ -430,6 +442,7 @@ int tdg_create(tdg_ctx **out, int device, size_t chunk_bytes)
     c->sm_count = prop.multiProcessorCount;
     c->chunk_bytes = chunk_bytes ? chunk_bytes : ((size_t)64 << 20);
     if (const char *e = getenv("TDG_SEG_TILES")) c->force_seg_tiles = (uint32_t)atoi(e);
+    if (const char *e = getenv("TDG_GENERAL")) c->force_general = atoi(e) != 0;
     if (c->chunk_bytes < 4096) c->chunk_bytes = 4096;
     cudaError_t e2 = cudaSuccess;
     if (e2 == cudaSuccess) e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);

@@ -3,31 +3,45 @@
 // over the raw bytes (sm_100a).
 //
 // Replaces the loop of find_tags_fastq, /root/reference/tagdigger_fun.py:250-274:
-//   for line in fqcon:                      -> line ends found 64 bytes per thread (SWAR)
+//   for line in fqcon:                      -> line ends found 16 bytes at a time (SWAR)
 //       if lineindex % 4 == 1:              -> see "line numbering" below
 //           line1 = line.strip().upper()    -> leading-whitespace skip + case fold
-//           sequence_index_lookup(x2)       -> tdg_match.h (packed exact-match probes)
+//           sequence_index_lookup(x2)       -> packed exact-match probes (prefix-free sets)
 //           mycounts[bar][tag] += 1         -> warp-aggregated red.global.add.s32
 //
-// Data movement: a persistent grid; each CTA draws SEGMENTS (runs of consecutive
-// tiles) from a global ticket counter and streams their tiles through a ring of
-// shared-memory buffers filled by the TMA unit (cp.async.bulk + mbarrier
-// complete_tx).  Every byte of the stream is read from HBM exactly once.
+// Execution model: every WARP is an independent pipeline.  A warp draws SEGMENTS
+// (runs of consecutive tiles) from a global ticket counter and streams their tiles
+// through its own ring of three shared-memory stages filled by the TMA unit
+// (cp.async.bulk + mbarrier complete_tx).  There is no CTA-wide barrier after the
+// prologue, and every byte of the stream is read from HBM exactly once.
+//
+// Per tile (7,680 bytes + halo) a warp
+//   1. scans: each lane tests its 240 contiguous bytes for control characters,
+//      15 x 128-bit shared loads (240 = 15 x 16: consecutive lanes start in
+//      consecutive 16-byte bank groups, so the loads are conflict free);
+//   2. ranks the line ends with one warp prefix sum, which gives every line start
+//      its index in the file, and pushes the starts of SEQUENCE lines onto a small
+//      per-warp queue (positions inside the ring);
+//   3. whenever 32 starts are queued, matches them one per lane: pack 2 bits per
+//      base, barcode bucket lookup in shared memory, 128-bit key, one hash probe
+//      of the L2-resident tag table, warp-aggregated count update.
+// The queue decouples "lines per tile" from "lanes per warp": matching always runs
+// with full warps whatever the record length.
 //
 // Line numbering.  Which lines are sequence lines is decided by the GLOBAL line
-// index (lineindex % 4 == 1 counted from the start of the file), which a CTA
-// that starts in the middle of the file cannot know without every byte before
-// it.  The kernel therefore runs speculatively and verifies:
-//   1. count pass (this kernel, mode MAIN): each segment numbers its lines from a
-//      GUESS of its first line's index mod 4, read off the FASTQ structure of its
-//      first lines ('@' line, '+' two lines later, equal sequence/quality length),
-//      and records how many lines it saw.  Segment 0 knows its true index.
+// index (lineindex % 4 == 1 counted from the start of the file), which a warp that
+// starts in the middle of the file cannot know without every byte before it.  The
+// kernel therefore runs speculatively and verifies:
+//   1. count pass (MODE_MAIN): each segment numbers its lines from a GUESS of its
+//      first line's index mod 4, read off the FASTQ structure of its first lines
+//      ('@' line, '+' two lines later, equal sequence/quality length), and records
+//      how many lines it saw.  Segment 0 knows its true index.
 //   2. verify_kernel: a prefix sum over the per-segment line counts gives every
 //      segment's true first line index; segments whose guess was wrong (or that
 //      reach past the read limit) go on a fix list.  For real FASTQ it is empty.
-//   3. fix pass (this kernel, mode FIX): listed segments are counted again with
-//      the guessed numbering and weight -1, then with the true numbering, the
-//      read limit and weight +1.
+//   3. fix pass (MODE_FIX): listed segments are counted again with the guessed
+//      numbering and weight -1, then with the true numbering, the read limit and
+//      weight +1.
 // The result is exact for ANY byte stream; only the speed depends on the guess.
 #pragma once
 #include <cuda_runtime.h>
@@ -36,24 +50,27 @@
 
 namespace tdg {
 
-#ifndef TDG_THREADS
-#define TDG_THREADS 128
-#endif
-#ifndef TDG_STAGES
-#define TDG_STAGES 3
+#ifndef TDG_WARPS
+#define TDG_WARPS 8
 #endif
 
-constexpr int      THREADS = TDG_THREADS;
-constexpr int      WARPS = THREADS / 32;
-constexpr uint32_t SPAN = 64;                      // bytes per thread in the line scan
-constexpr uint32_t TILE = THREADS * SPAN;          // bytes per tile
+constexpr int      WARPS = TDG_WARPS;              // independent pipelines per CTA
+constexpr int      THREADS = WARPS * 32;
+constexpr uint32_t CHUNKS = 15;                    // 16-byte pieces per lane per tile
+constexpr uint32_t SPAN = CHUNKS * 16;             // 240 bytes per lane
+constexpr uint32_t TILE = 32 * SPAN;               // 7,680 bytes per warp tile
 constexpr uint32_t HALO = 512;                     // == TDG_HALO_BYTES
-constexpr uint32_t STAGE_BYTES = TILE + HALO;
-constexpr uint32_t STAGE_STRIDE = STAGE_BYTES + 128;   // slack for unaligned word reads
-constexpr int      STAGES = TDG_STAGES;
-constexpr uint32_t STARTS_CAP = TILE / 8;          // line starts kept per emission window
+constexpr uint32_t STAGE = TILE + HALO;            // 8,192: one ring stage
+constexpr uint32_t STAGE_SHIFT = 13;
+constexpr int      STAGES = 3;
+constexpr uint32_t RING = STAGES * STAGE;          // bytes of shared memory per warp
+constexpr uint32_t QCAP = 128;                     // queue slots (power of two)
+constexpr uint32_t PUSH_CAP = QCAP - 32;           // starts pushed per emission round
 constexpr uint32_t BAR_SMEM_MAX = 16384;           // barcode tables up to this size are copied to smem
 constexpr uint32_t GUESS_LINES = 16;               // lines inspected for the FASTQ structure guess
+constexpr uint32_t FAST_WORDS_MAX = 24;            // 4-character words the fast matcher packs per read
+static_assert(STAGE == (1u << STAGE_SHIFT), "stage size must be a power of two");
+static_assert(TILE % 16 == 0, "tiles must keep the 16-byte alignment TMA needs");
 
 enum { PREV_NONE = 0, PREV_LF = 1, PREV_CR = 2, PREV_OTHER = 3 };
 enum { MODE_MAIN = 0, MODE_FIX = 1 };
@@ -76,7 +93,7 @@ struct FixEntry {
 };
 
 struct ChunkArgs {
-    const uint8_t *bytes;           // 16-byte aligned; allocation >= round_up(n, TILE) + HALO
+    const uint8_t *bytes;           // 16-byte aligned; allocation >= round_up(n, 16)
     unsigned long long n;
     uint32_t num_tiles;
     uint32_t seg_tiles;             // tiles per segment
@@ -95,6 +112,8 @@ struct ChunkArgs {
     const BarTable *bar;
     uint32_t bar_bytes;             // header + entries
     uint32_t cols;
+    uint32_t halo_bytes;            // bytes copied past each tile (multiple of 16, <= HALO)
+    uint32_t fast_words;            // > 0: tables fit the fast matcher, which packs this many words
     TagTable tags;
     int32_t *matrix;
     unsigned long long *totals;     // [3]: reads, barcode+cutsite hits, tag hits
@@ -115,7 +134,33 @@ struct VerifyArgs {
     uint32_t *n_fix;
 };
 
+// Can the fast matcher serve these tables?  Returns the number of 4-character
+// words it has to pack per read (0 = use the general matcher).  Host and device
+// agree on this through ChunkArgs::fast_words.
+inline uint32_t fast_words_for(const BarTable *bar, const TagTable &tt)
+{
+    if (bar->any_base || tt.any_base) return 0;
+    if (bar->max_len > 16 || bar->max_tag_off > 28) return 0;
+    if (tt.n_classes != 1 || tt.max_len > 64 || tt.min_len < 1) return 0;
+    uint32_t chars = 3 + bar->max_tag_off + tt.max_len;       // 3: worst misalignment of the line start
+    if (chars < 3 + 16) chars = 3 + 16;                       // the barcode key is always 16 bases
+    uint32_t nw = (chars + 3) / 4;
+    return nw <= FAST_WORDS_MAX ? nw : 0;
+}
+
 #if defined(__CUDACC__)
+
+struct WarpShared {           // per-warp control block in shared memory
+    uint16_t q[QCAP];         // queued sequence-line starts: stage * STAGE + offset in stage
+    uint32_t item[STAGES];    // work item of the tile in each stage (or NONE)
+    uint32_t tix[STAGES];     // tile index inside its segment
+    uint32_t tile[STAGES];    // tile index inside the chunk
+    uint16_t gs[GUESS_LINES + 8];   // first line starts of a segment
+    uint32_t pad[3];
+};
+static_assert(sizeof(WarpShared) % 16 == 0, "control blocks must keep the barcode table 16-byte aligned");
+
+constexpr size_t SMEM_FIXED = (size_t)WARPS * RING + (size_t)WARPS * sizeof(WarpShared);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -154,16 +199,23 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         : "memory");
 }
 
-// 16 bytes -> 16-bit mask of bytes < 0x20 (every byte must be < 0x80).
-// Per word: bit 7 of (w + 0x60) is clear iff the byte is < 0x20; the multiply
-// gathers the four flags into the top nibble (no partial products collide).
+// 4 bytes -> 0x80 in every byte that is an ASCII control character (< 0x20).
+// Exact for all byte values: the low seven bits are tested without carries
+// between bytes, and bytes >= 0x80 are excluded by their own top bit.
+__device__ __forceinline__ uint32_t ctl4(uint32_t w)
+{
+    uint32_t t = (w & 0x7F7F7F7Fu) + 0x60606060u;
+    return ~(t | w) & 0x80808080u;
+}
+// 16 bytes -> 16-bit mask of control characters.  The multiply gathers the
+// four flags of a word into its top nibble (no partial products collide).
 __device__ __forceinline__ uint32_t ctl_mask16(uint4 q)
 {
-    uint32_t acc = 0, f;
-    f = ~(q.w + 0x60606060u) & 0x80808080u; acc = __funnelshift_l(f * 0x00204081u, acc, 4);
-    f = ~(q.z + 0x60606060u) & 0x80808080u; acc = __funnelshift_l(f * 0x00204081u, acc, 4);
-    f = ~(q.y + 0x60606060u) & 0x80808080u; acc = __funnelshift_l(f * 0x00204081u, acc, 4);
-    f = ~(q.x + 0x60606060u) & 0x80808080u; acc = __funnelshift_l(f * 0x00204081u, acc, 4);
+    uint32_t acc = 0;
+    acc = __funnelshift_l(ctl4(q.w) * 0x00204081u, acc, 4);
+    acc = __funnelshift_l(ctl4(q.z) * 0x00204081u, acc, 4);
+    acc = __funnelshift_l(ctl4(q.y) * 0x00204081u, acc, 4);
+    acc = __funnelshift_l(ctl4(q.x) * 0x00204081u, acc, 4);
     return acc;
 }
 
@@ -206,25 +258,83 @@ struct GlobalFetch {
     }
 };
 
+// General matcher for one line (any table shape, leading whitespace, lines cut
+// by the end of the chunk, lines that leave the staged bytes).  Rare: kept out
+// of line so that the fast path stays small.
+//   buf/pos: the line start inside a stage; staged: bytes of the stage that are
+//   valid (tile + halo, clipped to the chunk); gtile: the same tile in global
+//   memory; avail: bytes from the tile start to the end of the chunk.
+__device__ __noinline__ MatchResult match_general(const uint8_t *buf, uint32_t pos, uint32_t staged,
+                                                  const uint8_t *gtile, unsigned long long avail, uint32_t need,
+                                                  const BarTable *bar, const BarEntry *bent, const TagTable *tt)
+{
+    // leading whitespace (str.strip)
+    while (pos < staged) {
+        uint32_t c = buf[pos];
+        if (is_lead_space(c)) { pos++; continue; }
+        if (c >= 0xC2 && c <= 0xE3 && pos + 2 < staged) {
+            uint32_t u = utf8_space(c, buf[pos + 1], buf[pos + 2]);
+            if (u) { pos += u; continue; }
+        }
+        break;
+    }
+    if (pos + need <= staged || staged == avail) {
+        SmemFetch f;
+        f.p = buf + pos;
+        unsigned long long room = avail - pos;
+        f.limit = room > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)room;
+        return match_line(f, bar, bent, *tt);
+    }
+    // continue from global memory
+    unsigned long long gp = pos;
+    while (gp < avail) {
+        uint32_t c = gtile[gp];
+        if (is_lead_space(c)) { gp++; continue; }
+        if (c >= 0xC2 && c <= 0xE3 && gp + 2 < avail) {
+            uint32_t u = utf8_space(c, gtile[gp + 1], gtile[gp + 2]);
+            if (u) { gp += u; continue; }
+        }
+        break;
+    }
+    GlobalFetch f;
+    f.p = gtile + gp;
+    unsigned long long room = avail - gp;
+    f.limit = room > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)room;
+    return match_line(f, bar, bent, *tt);
+}
+
+// One 4-character word of the fast matcher: 2-bit codes gathered in the top
+// byte of the result; `bad` non-zero iff a character is not one of ACGTacgt.
+__device__ __forceinline__ uint32_t pack_word(uint32_t w, uint32_t &bad)
+{
+    uint32_t cf = w & 0xDFDFDFDFu;                    // fold case (exact for ASCII letters)
+    uint32_t c2 = (w >> 1) & 0x03030303u;             // A0 C1 T2 G3
+    uint32_t m = (c2 >> 1) & ~c2 & 0x01010101u;       // 1 where code == 2 (T)
+    uint32_t e = 0x41414141u + 2u * c2 + 15u * m;     // the letter that code stands for
+    bad = e ^ cf;
+    return c2 * 0x01041040u;                          // byte 3 = c0 | c1<<2 | c2<<4 | c3<<6
+}
+
+__device__ __forceinline__ uint32_t lowmask32(uint32_t nbases)    // first nbases (<= 16) bases of a 32-bit word
+{
+    return nbases >= 16 ? 0xFFFFFFFFu : ((1u << (2 * nbases)) - 1u);
+}
+
 template <bool MATCH>
-__global__ void __launch_bounds__(THREADS) count_kernel(const ChunkArgs a)
+__global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant__ ChunkArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *stage_base = smem;
-    uint16_t *starts = (uint16_t *)(smem + STAGES * STAGE_STRIDE);
-    uint8_t *bar_smem = (uint8_t *)(starts + STARTS_CAP);
-
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ uint32_t s_item[STAGES];            // work item of the tile in each stage (or NONE)
-    __shared__ uint32_t s_tix[STAGES];             // tile index inside its segment
-    __shared__ uint32_t s_warp_cnt[WARPS];
-    __shared__ uint32_t s_guess;
-    __shared__ unsigned long long s_tot[2];
+    __shared__ __align__(8) uint64_t full_bar[WARPS][STAGES];
 
     constexpr uint32_t NONE = 0xFFFFFFFFu;
+    constexpr uint32_t FULL = 0xFFFFFFFFu;
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
+
+    uint8_t *const wbase = smem + (size_t)warp * RING;
+    WarpShared *const ws = (WarpShared *)(smem + (size_t)WARPS * RING) + warp;
+    uint8_t *const bar_smem = smem + SMEM_FIXED;
 
     // ---- chunk-level state -------------------------------------------------
     unsigned long long line_base;
@@ -244,18 +354,28 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const ChunkArgs a)
         if (a.bar_bytes <= BAR_SMEM_MAX) {
             const uint4 *src = (const uint4 *)a.bar;
             uint4 *dst = (uint4 *)bar_smem;
-            for (uint32_t i = tid; i < a.bar_bytes / 16; i += THREADS) dst[i] = src[i];
+            for (uint32_t i = tid; i < (a.bar_bytes + 15u) / 16u; i += THREADS) dst[i] = src[i];
             bar = (const BarTable *)bar_smem;
         }
     }
     const BarEntry *bent = (const BarEntry *)((const uint8_t *)bar + sizeof(BarTable));
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; s++) mbar_init(&full_bar[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();           // the only CTA-wide barrier: table copy + barrier init
 
-    // ---- producer state (thread 0): the next tile to request ------------------
+    const uint32_t copy_bytes = TILE + a.halo_bytes;
+
+    // ---- producer: the next tile to request (state uniform across the warp) --------
     uint32_t p_item = NONE, p_seg = 0, p_tix = 0, p_ntiles = 0;
-    auto produce = [&](int s) {
-        // called by thread 0 only: pick the next tile and start its copy into stage s
-        if (p_tix == p_ntiles) {
-            unsigned long long t = atomicAdd(a.ticket, 1ull);
+    bool p_done = false;
+    auto produce = [&](uint32_t s) {
+        if (p_tix == p_ntiles && !p_done) {
+            unsigned long long t = 0;
+            if (lane == 0) t = atomicAdd(a.ticket, 1ull);
+            t = __shfl_sync(FULL, t, 0);
             if (t < n_items) {
                 p_item = (uint32_t)t;
                 p_seg = a.mode == MODE_FIX ? a.fix[p_item >> 1].seg : p_item;
@@ -267,50 +387,192 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const ChunkArgs a)
                 p_item = NONE;
                 p_ntiles = 0;
                 p_tix = 0;
+                p_done = true;
             }
         }
-        s_item[s] = p_item;
-        s_tix[s] = p_tix;
-        if (p_item != NONE) {
-            size_t tile = (size_t)p_seg * a.seg_tiles + p_tix;
-            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-            bulk_g2s(stage_base + s * STAGE_STRIDE, a.bytes + tile * TILE, STAGE_BYTES, &full_bar[s]);
-            p_tix++;
+        if (lane == 0) {
+            ws->item[s] = p_item;
+            ws->tix[s] = p_tix;
+            if (p_item != NONE) {
+                uint32_t tile = p_seg * a.seg_tiles + p_tix;
+                ws->tile[s] = tile;
+                unsigned long long off = (unsigned long long)tile * TILE;
+                unsigned long long left = a.n - off;
+                uint32_t bytes = copy_bytes;
+                if (left < bytes) bytes = ((uint32_t)left + 15u) & ~15u;
+                mbar_expect_tx(&full_bar[warp][s], bytes);
+                bulk_g2s(wbase + s * STAGE, a.bytes + off, bytes, &full_bar[warp][s]);
+            }
         }
+        if (p_item != NONE) p_tix++;
     };
+    produce(0);
+    produce(1);
 
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; s++) mbar_init(&full_bar[s], 1);
-        s_tot[0] = s_tot[1] = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < STAGES; s++) produce(s);
-    }
-    __syncthreads();
-
-    // bytes a match may touch past the stripped line start (fast path bound)
-    uint32_t need = 0;
+    // ---- matcher set-up (uniform) -----------------------------------------------------
+    const uint32_t nw = MATCH ? a.fast_words : 0;       // 0: general matcher only
+    uint32_t need = 0;                                  // bytes a match may touch past the stripped line start
+    uint32_t tagK = 0, tag_base = 0, tag_mask = 0;
+    bool uniform_len = false;
     if (MATCH) {
         need = bar->max_tag_off + a.tags.max_len + 36u;
         if (bar->max_len + 36u > need) need = bar->max_len + 36u;
+        tagK = a.tags.cls[0].K;
+        tag_base = a.tags.cls[0].base;
+        tag_mask = a.tags.cls[0].mask;
+        uniform_len = a.tags.min_len == a.tags.max_len;
     }
-    long long my_reads = 0;               // thread 0 only
+    const uint4 *tag_entries = (const uint4 *)a.tags.entries;
+    long long my_reads = 0;
     int32_t my_bar = 0, my_tag = 0;
 
-    // ---- per-item state (uniform across the CTA) -------------------------------
+    // ---- queue of sequence-line starts (uniform bookkeeping, contents in ws->q) ------------
+    uint32_t q_head = 0, q_len = 0, q_old = 0;
+
+    // ---- per-segment state (uniform across the warp) -----------------------------------------
     uint32_t seg = 0, seg_ntiles = 0, seg_lines = 0, guess = 0;
     unsigned long long seg_first = 0;     // (assumed) index of the segment's first line start
     unsigned long long limit = ~0ull;
     int32_t weight = 1;
     bool need_guess = false;
+    bool classify_first = !MATCH;         // sticky: this input has control characters other than '\n'
+    uint32_t cur_tile = 0;
 
-    for (uint32_t it = 0;; it++) {
-        const uint32_t s = it % STAGES;
-        const uint32_t parity = (it / STAGES) & 1u;
-        const uint32_t item = s_item[s];
+    // Match up to 32 queued line starts, one per lane.
+    auto run_batch = [&](uint32_t nb) {
+        uint32_t off = 0;
+        const bool have = lane < nb;
+        if (have) off = ws->q[(q_head + lane) & (QCAP - 1)];
+        q_head += nb;
+        q_len -= nb;
+        q_old = q_old > nb ? q_old - nb : 0;
+        int32_t row = -1, col = -1;
+        if (have) {
+            const uint32_t se = off >> STAGE_SHIFT;
+            const uint32_t p = off & (STAGE - 1);
+            const uint8_t *eb = wbase + (off & ~(STAGE - 1));
+            const uint32_t c0 = eb[p];
+            // the last tiles of a chunk may hold lines cut by the end of the data
+            bool slow = nw == 0 || cur_tile + 2 >= a.num_tiles || c0 >= 0x80 || is_lead_space(c0);
+            if (!slow) {
+                // ---- fast matcher: pack the first 4*nw characters (from the aligned
+                // word that holds the line start) once, 2 bits per base
+                const uint32_t sh = p & 3u;
+                const uint32_t *wp = (const uint32_t *)(eb + (p & ~3u));
+                uint32_t P[FAST_WORDS_MAX / 4];
+                uint32_t bm = 0;          // bit i: word i holds a character outside ACGTacgt
+#pragma unroll
+                for (uint32_t g = 0; g < FAST_WORDS_MAX / 4; g++) {
+                    P[g] = 0;
+                    if (4 * g < nw) {
+                        uint32_t x[4];
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; k++) {
+                            uint32_t bad;
+                            x[k] = pack_word(wp[4 * g + k], bad);
+                            if (g == 0 && k == 0) bad &= 0xFFFFFFFFu << (8u * sh);   // bytes before the line start
+                            if (bad) bm |= 1u << (4 * g + k);
+                        }
+                        P[g] = __byte_perm(__byte_perm(x[0], x[1], 0x0073), __byte_perm(x[2], x[3], 0x0073), 0x5410);
+                    }
+                }
+                bm &= nw >= 32 ? 0xFFFFFFFFu : ((1u << nw) - 1u);
+                // ---- barcode + cut site: first 16 bases, bucket = first 4
+                const uint32_t key0 = __funnelshift_r(P[0], P[1], 2u * sh);
+                uint32_t tag_off = 0, blen = 0;
+                {
+                    uint32_t b = key0 & 0xFFu;
+                    uint32_t lo = bar->bucket[b], hi = bar->bucket[b + 1];
+                    for (uint32_t e = lo; e < hi; e++) {
+                        uint4 be = *(const uint4 *)(bent + e);       // key lo, key hi, row, len | tag_off << 16
+                        uint32_t len = be.w & 0xFFFFu;
+                        if (((key0 ^ be.x) & lowmask32(len)) == 0) {
+                            row = (int32_t)be.z;
+                            blen = len;
+                            tag_off = be.w >> 16;
+                            break;
+                        }
+                    }
+                }
+                uint32_t tlen = 0;
+                if (row >= 0) {
+                    // ---- 128-bit tag key at tag_off, one probe sequence
+                    const uint32_t toff = sh + tag_off;
+                    const uint32_t bit = (toff & 15u) * 2u;
+                    const bool up = (toff >> 4) != 0;          // toff <= 31
+                    const uint32_t Q0 = up ? P[1] : P[0], Q1 = up ? P[2] : P[1], Q2 = up ? P[3] : P[2],
+                                   Q3 = up ? P[4] : P[3], Q4 = up ? P[5] : P[4];
+                    const uint32_t T0 = __funnelshift_r(Q0, Q1, bit), T1 = __funnelshift_r(Q1, Q2, bit),
+                                   T2 = __funnelshift_r(Q2, Q3, bit), T3 = __funnelshift_r(Q3, Q4, bit);
+                    const uint64_t pre = (((uint64_t)T1 << 32) | T0) & lowmask(tagK);
+                    uint32_t h = tag_hash(pre) & tag_mask;
+                    for (;;) {
+                        // two neighbouring slots per round trip
+                        const uint32_t h1 = (h + 1) & tag_mask;
+                        const uint4 *e0 = tag_entries + 2 * (size_t)(tag_base + h);
+                        const uint4 *e1 = tag_entries + 2 * (size_t)(tag_base + h1);
+                        const uint4 k0 = __ldg(e0), m0 = __ldg(e0 + 1);
+                        const uint4 k1 = __ldg(e1), m1 = __ldg(e1 + 1);
+                        if (m0.x == TDG_EMPTY_LEN) break;
+                        {
+                            const uint32_t L = m0.x;
+                            uint32_t d = ((k0.x ^ T0) & lowmask32(L)) | ((k0.y ^ T1) & lowmask32(L > 16 ? L - 16 : 0));
+                            d |= ((k0.z ^ T2) & lowmask32(L > 32 ? L - 32 : 0)) | ((k0.w ^ T3) & lowmask32(L > 48 ? L - 48 : 0));
+                            if (d == 0) { col = (int32_t)m0.y; tlen = L; break; }
+                        }
+                        if (m1.x == TDG_EMPTY_LEN) break;
+                        {
+                            const uint32_t L = m1.x;
+                            uint32_t d = ((k1.x ^ T0) & lowmask32(L)) | ((k1.y ^ T1) & lowmask32(L > 16 ? L - 16 : 0));
+                            d |= ((k1.z ^ T2) & lowmask32(L > 32 ? L - 32 : 0)) | ((k1.w ^ T3) & lowmask32(L > 48 ? L - 48 : 0));
+                            if (d == 0) { col = (int32_t)m1.y; tlen = L; break; }
+                        }
+                        h = (h1 + 1) & tag_mask;
+                    }
+                    (void)uniform_len;
+                }
+                if (row >= 0 && bm != 0) {
+                    // some character is not a base: the matches stand only if they end before it
+                    const uint32_t fw = __ffs(bm) - 1u;
+                    uint32_t bad;
+                    (void)pack_word(wp[fw], bad);
+                    if (fw == 0) bad &= 0xFFFFFFFFu << (8u * sh);
+                    const uint32_t k = (bad & 0xFFu) ? 0u : (bad & 0xFF00u) ? 1u : (bad & 0xFF0000u) ? 2u : 3u;
+                    const uint32_t V = 4u * fw + k - sh;       // valid bases from the line start
+                    if (blen > V) { row = -1; col = -1; }
+                    else if (col >= 0 && tag_off + tlen > V) col = -1;
+                }
+            } else {
+                const uint32_t tile = ws->tile[se];
+                const unsigned long long tile_off = (unsigned long long)tile * TILE;
+                const unsigned long long avail = a.n - tile_off;
+                const uint32_t staged = avail < copy_bytes ? (uint32_t)avail : copy_bytes;
+                MatchResult mr = match_general(eb, p, staged, a.bytes + tile_off, avail, need, bar, bent, &a.tags);
+                row = mr.row;
+                col = mr.col;
+            }
+        }
+        __syncwarp();
+        if (row >= 0) my_bar += weight;
+        // warp-aggregated count update: one red per distinct cell
+        uint32_t cell = NONE;
+        if (col >= 0) {
+            my_tag += weight;
+            cell = (uint32_t)row * a.cols + (uint32_t)col;
+        }
+        const uint32_t peers = __match_any_sync(FULL, cell);
+        if (cell != NONE && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&a.matrix[cell], weight * (int32_t)__popc(peers));
+    };
+
+    uint32_t s = 0, parity = 0;
+    for (;;) {
+        __syncwarp();
+        const uint32_t item = ws->item[s];
         if (item == NONE) break;
-        const uint32_t tix = s_tix[s];
-        mbar_wait(&full_bar[s], parity);
+        const uint32_t tix = ws->tix[s];
+        const uint32_t t = ws->tile[s];               // tile index in the chunk
+        cur_tile = t;
+        mbar_wait(&full_bar[warp][s], parity);
 
         if (tix == 0) {                    // a new segment starts
             seg_lines = 0;
@@ -325,16 +587,17 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const ChunkArgs a)
             } else {
                 seg = item;
                 if (seg == 0) seg_first = line_base;       // known exactly
-                else { seg_first = 0; need_guess = true; }
+                else { seg_first = 0; need_guess = MATCH; }
             }
             guess = (uint32_t)(seg_first & 3ull);
             uint32_t first_tile = seg * a.seg_tiles;
             uint32_t left = a.num_tiles - first_tile;
             seg_ntiles = left < a.seg_tiles ? left : a.seg_tiles;
         }
-        const uint32_t t = seg * a.seg_tiles + tix;         // tile index in the chunk
+        const bool seg_end = tix == seg_ntiles - 1;
+        const bool last_tile = t == a.num_tiles - 1;
 
-        const uint8_t *buf = stage_base + s * STAGE_STRIDE;
+        const uint8_t *buf = wbase + s * STAGE;
         const unsigned long long tile_off = (unsigned long long)t * TILE;
         const unsigned long long avail = a.n - tile_off;            // bytes from tile start to chunk end
         const uint32_t valid = avail < TILE ? (uint32_t)avail : TILE;
@@ -346,253 +609,191 @@ __global__ void __launch_bounds__(THREADS) count_kernel(const ChunkArgs a)
             else if (prev_kind == PREV_CR && buf[0] != '\n') extra = 1;
         }
 
-        // ---- phase A: line-end mask of my 64 bytes --------------------------
-        uint32_t mlo = 0, mhi = 0;          // bit i: a line ends at byte tid*64 + i
-        uint32_t hi_or = 0;
+        // ---- scan: control-character mask of my 240 bytes ----------------------
+        uint32_t mk[8];
         {
-            const uint4 *src = (const uint4 *)(buf + tid * SPAN);
+            const uint4 *src = (const uint4 *)(buf + lane * SPAN);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint32_t q = (i + (lane >> 1)) & 3u;      // conflict-free piece order
-                uint4 v = src[q];
-                hi_or |= v.x | v.y | v.z | v.w;
-                uint32_t m16 = ctl_mask16(v) << ((q & 1u) * 16u);
-                if (q & 2u) mhi |= m16; else mlo |= m16;
+            for (uint32_t i = 0; i < CHUNKS; i++) {
+                uint32_t m16 = ctl_mask16(src[i]);
+                if (i & 1u) mk[i >> 1] |= m16 << 16; else mk[i >> 1] = m16;
             }
         }
-        // every candidate must really be '\n' and every byte ASCII, otherwise
-        // the whole tile is redone exactly below
-        uint32_t bad = hi_or & 0x80808080u;
-        {
-            uint32_t m = mlo;
-            while (m) { uint32_t b = __ffs(m) - 1; m &= m - 1; bad |= (buf[tid * SPAN + b] != '\n'); }
-            m = mhi;
-            while (m) { uint32_t b = __ffs(m) - 1; m &= m - 1; bad |= (buf[tid * SPAN + 32 + b] != '\n'); }
+        if (last_tile) {
+            // The line that would start right after the last byte of the chunk is
+            // numbered by the NEXT chunk (PREV_LF), and bytes at and after n do not
+            // exist: keep line ends at p < valid - 1 only.
+            const uint32_t lim = valid - 1;
+            const uint32_t first = lane * SPAN;
+            const uint32_t keep = lim > first ? lim - first : 0;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++) {
+                uint32_t nb = keep > 32 * j ? keep - 32 * j : 0;
+                if (nb < 32) mk[j] &= (1u << nb) - 1u;
+            }
+            if (lane == 0) {
+                uint32_t c = buf[valid - 1];
+                *a.last_kind = c == '\n' ? PREV_LF : (c == '\r' ? PREV_CR : PREV_OTHER);
+            }
         }
-        const bool last_tile = t == a.num_tiles - 1;
-        auto clip_last = [&]() {
-            // The line that would start right after the last byte of the chunk
-            // is numbered by the NEXT chunk (PREV_LF), and bytes at and after n
-            // do not exist: keep line ends at p < valid - 1 only.
-            uint32_t lim = valid - 1;
-            uint32_t first = tid * SPAN;
-            if (first + 64 > lim) {
-                uint32_t keep = lim > first ? lim - first : 0;          // 0..63
-                uint64_t km = (1ull << keep) - 1ull;
-                mlo &= (uint32_t)km;
-                mhi &= (uint32_t)(km >> 32);
+
+        // exact line ends: '\n' ends a line; '\r' ends one unless a '\n' follows
+        // (Python universal newlines); every other control character is content.
+        auto classify = [&]() {
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++) {
+                uint32_t m = mk[j];
+                while (m) {
+                    uint32_t b = __ffs(m) - 1u;
+                    m &= m - 1u;
+                    uint32_t p = lane * SPAN + 32 * j + b;
+                    uint32_t c = buf[p];
+                    bool end = c == '\n';
+                    // the byte after the last byte of the chunk is unknown: pending
+                    if (c == '\r') end = (p + 1 < avail) && buf[p + 1] != '\n';
+                    if (!end) mk[j] &= ~(1u << b);
+                }
             }
         };
-        if (last_tile) clip_last();
-        uint32_t cnt = __popc(mlo) + __popc(mhi);
-        uint32_t incl = cnt;
+        bool verified = false;
+        if (classify_first || need_guess) { classify(); verified = true; }
+
+        uint32_t cnt, incl, total;
+        for (;;) {
+            cnt = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        if (lane == 31) s_warp_cnt[warp] = incl;
-        if (__syncthreads_or(bad)) {
-            // exact path: '\n' ends a line; '\r' ends one unless a '\n' follows
-            // (Python universal newlines); anything else is content.
-            mlo = mhi = 0;
-            for (uint32_t i = 0; i < SPAN; i++) {
-                uint32_t p = tid * SPAN + i;
-                uint32_t c = buf[p];
-                bool end = c == '\n';
-                if (c == '\r') {
-                    // the byte after the last byte of the chunk is unknown: pending
-                    end = (p + 1 < avail) && buf[p + 1] != '\n';
-                }
-                if (end) { if (i < 32) mlo |= 1u << i; else mhi |= 1u << (i - 32); }
-            }
-            if (last_tile) clip_last();
-            cnt = __popc(mlo) + __popc(mhi);
+            for (uint32_t j = 0; j < 8; j++) cnt += __popc(mk[j]);
             incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= d) incl += o;
+                uint32_t o = __shfl_up_sync(FULL, incl, d);
+                if (lane >= (uint32_t)d) incl += o;
             }
-            __syncthreads();                 // everyone has read the fast-path counts
-            if (lane == 31) s_warp_cnt[warp] = incl;
-            __syncthreads();
-        }
-        uint32_t before = extra, total = extra;
-#pragma unroll
-        for (int w = 0; w < WARPS; w++) {
-            uint32_t c = s_warp_cnt[w];
-            if (w < (int)warp) before += c;
-            total += c;
-        }
-        const uint32_t my_rank0 = before + incl - cnt;      // rank of my first line end in the tile
+            total = extra + __shfl_sync(FULL, incl, 31);
+            if (!MATCH) break;
+            const uint32_t rho0 = extra + incl - cnt;       // rank of the line start after my first line end
 
-        if (last_tile && tid == 0) {
-            uint32_t c = buf[valid - 1];
-            *a.last_kind = c == '\n' ? PREV_LF : (c == '\r' ? PREV_CR : PREV_OTHER);
-        }
-
-        if (MATCH) {
-            // ---- emission + matching, STARTS_CAP line starts at a time --------
-            for (uint32_t wlo = 0; wlo < total; wlo += STARTS_CAP) {
+            if (need_guess) {
+                // First lines of a segment whose position in the file is not known yet:
+                // find a line that looks like a FASTQ header ('@', then '+' two lines on,
+                // sequence and quality lines of equal length).  Any answer is acceptable --
+                // a wrong one is found and repaired by verify_kernel + the fix pass.
                 {
-                    uint32_t rank = my_rank0;
-                    uint32_t m = mlo;
-                    while (m) {
-                        uint32_t b = __ffs(m) - 1; m &= m - 1;
-                        uint32_t k = rank - wlo;
-                        if (k < STARTS_CAP) starts[k] = (uint16_t)(tid * SPAN + b + 1);
-                        rank++;
-                    }
-                    m = mhi;
-                    while (m) {
-                        uint32_t b = __ffs(m) - 1; m &= m - 1;
-                        uint32_t k = rank - wlo;
-                        if (k < STARTS_CAP) starts[k] = (uint16_t)(tid * SPAN + 32 + b + 1);
-                        rank++;
-                    }
-                    if (tid == 0 && extra && wlo == 0) starts[0] = 0;
-                }
-                __syncthreads();             // starts[] is ready
-
-                if (need_guess) {
-                    // First lines of a segment whose position in the file is not
-                    // known yet: find a line that looks like a FASTQ header
-                    // ('@', then '+' two lines on, sequence and quality lines of
-                    // equal length).  Any answer is acceptable -- a wrong one is
-                    // found and repaired by verify_kernel + the fix pass.
-                    if (tid == 0) {
-                        uint32_t g = 0;
-                        uint32_t have = total < STARTS_CAP ? total : STARTS_CAP;
-                        for (uint32_t k = 0; k + 4 < have && k < GUESS_LINES; k++) {
-                            uint32_t p0 = starts[k], p1 = starts[k + 1], p2 = starts[k + 2], p3 = starts[k + 3],
-                                     p4 = starts[k + 4];
-                            if (buf[p0] == '@' && buf[p2] == '+' && p2 - p1 == p4 - p3) {
-                                g = (4u - (k & 3u)) & 3u;          // line k has index 0 mod 4
-                                break;
-                            }
-                        }
-                        s_guess = g;
-                    }
-                    __syncthreads();
-                    guess = s_guess;
-                    seg_first = guess;
-                    need_guess = false;
-                }
-
-                const unsigned long long first_line = seg_first + seg_lines;   // index of rank 0 of this tile
-                // sequence lines: index % 4 == 1
-                uint32_t r0 = (uint32_t)((1ull - first_line) & 3ull);
-                uint32_t whi = wlo + STARTS_CAP < total ? wlo + STARTS_CAP : total;
-                // first r >= wlo with r % 4 == r0 % 4
-                uint32_t rbeg = wlo + ((r0 - wlo) & 3u);
-                for (uint32_t r = rbeg + 4 * tid; r < whi; r += 4 * THREADS) {
-                    unsigned long long read_idx = (first_line + r) >> 2;
-                    bool live = read_idx < limit;
-                    uint32_t pos = starts[r - wlo];       // always < avail (see clip_last)
-                    int32_t row = -1, col = -1;
-                    if (live) {
-                        // leading whitespace (str.strip)
-                        const uint32_t staged = avail < STAGE_BYTES ? (uint32_t)avail : STAGE_BYTES;
-                        while (pos < staged) {
-                            uint32_t c = buf[pos];
-                            if (is_lead_space(c)) { pos++; continue; }
-                            if (c >= 0xC2 && c <= 0xE3 && pos + 2 < staged) {
-                                uint32_t u = utf8_space(c, buf[pos + 1], buf[pos + 2]);
-                                if (u) { pos += u; continue; }
-                            }
-                            break;
-                        }
-                        MatchResult mr;
-                        if (pos + need <= STAGE_BYTES) {
-                            SmemFetch f;
-                            f.p = buf + pos;
-                            unsigned long long room = avail - pos;
-                            f.limit = room > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)room;
-                            mr = match_line(f, bar, bent, a.tags);
-                        } else {
-                            // rare: continue from global memory
-                            const uint8_t *g = a.bytes + tile_off;
-                            unsigned long long gp = pos;
-                            while (gp < avail) {
-                                uint32_t c = g[gp];
-                                if (is_lead_space(c)) { gp++; continue; }
-                                if (c >= 0xC2 && c <= 0xE3 && gp + 2 < avail) {
-                                    uint32_t u = utf8_space(c, g[gp + 1], g[gp + 2]);
-                                    if (u) { gp += u; continue; }
-                                }
-                                break;
-                            }
-                            GlobalFetch f;
-                            f.p = g + gp;
-                            unsigned long long room = avail - gp;
-                            f.limit = room > 0x7FFFFFFFull ? 0x7FFFFFFFu : (uint32_t)room;
-                            mr = match_line(f, bar, bent, a.tags);
-                        }
-                        row = mr.row;
-                        col = mr.col;
-                    }
-                    if (row >= 0) my_bar += weight;
-                    if (col >= 0) {
-                        my_tag += weight;
-                        // warp-aggregated count update: one red per distinct cell
-                        unsigned long long cell = (unsigned long long)(uint32_t)row * a.cols + (uint32_t)col;
-                        uint32_t act = __activemask();
-                        uint32_t peers = __match_any_sync(act, cell);
-                        if (lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&a.matrix[cell], weight * __popc(peers));
-                    }
-                }
-                if (tid == 0) {
-                    // reads in this window with read index below the limit
-                    // (read indices grow with r, so they form a prefix)
-                    long long nreads = 0;
-                    if (rbeg < whi) {
-                        unsigned long long cntr = (whi - rbeg + 3) / 4;
-                        unsigned long long first_idx = (first_line + rbeg) >> 2;
-                        if (first_idx < limit) {
-                            unsigned long long room = limit - first_idx;
-                            nreads = (long long)(cntr < room ? cntr : room);
+                    uint32_t r = rho0;
+#pragma unroll
+                    for (uint32_t j = 0; j < 8; j++) {
+                        uint32_t m = mk[j];
+                        while (m && r < GUESS_LINES + 5) {
+                            uint32_t b = __ffs(m) - 1u;
+                            m &= m - 1u;
+                            ws->gs[r] = (uint16_t)(lane * SPAN + 32 * j + b + 1);
+                            r++;
                         }
                     }
-                    my_reads += weight * nreads;
                 }
-                __syncthreads();             // starts[] (and finally the stage) may be reused
+                __syncwarp();
+                const uint32_t have = total < GUESS_LINES + 5 ? total : GUESS_LINES + 5;
+                bool hit = false;
+                if (lane < GUESS_LINES && lane + 4 < have) {
+                    uint32_t p0 = ws->gs[lane], p1 = ws->gs[lane + 1], p2 = ws->gs[lane + 2], p3 = ws->gs[lane + 3],
+                             p4 = ws->gs[lane + 4];
+                    hit = buf[p0] == '@' && buf[p2] == '+' && p2 - p1 == p4 - p3;
+                }
+                const uint32_t hits = __ballot_sync(FULL, hit);
+                guess = hits ? ((4u - ((uint32_t)(__ffs(hits) - 1) & 3u)) & 3u) : 0u;   // that line has index 0 mod 4
+                seg_first = guess;
+                need_guess = false;
             }
-            if (total == 0) __syncthreads();
-        } else {
-            __syncthreads();
+
+            // ---- emission: queue the starts of sequence lines (index % 4 == 1) -----------
+            const unsigned long long F = seg_first + seg_lines;        // index of rank 0 of this tile
+            const uint32_t a4 = (1u - (uint32_t)F) & 3u;                 // first rank that is a sequence line
+            const uint32_t nq = total > a4 ? (total - a4 + 3u) >> 2 : 0u;
+            uint32_t nlive = 0;                                          // those below the read limit (a prefix)
+            {
+                const unsigned long long first_idx = (F + a4) >> 2;
+                if (nq && first_idx < limit) {
+                    unsigned long long room = limit - first_idx;
+                    nlive = nq < room ? nq : (uint32_t)room;
+                }
+            }
+            bool redo = false;
+            for (uint32_t w0 = 0;;) {
+                const uint32_t room = nlive - w0 < PUSH_CAP ? nlive - w0 : PUSH_CAP;
+                const uint32_t qbase = q_head + q_len;
+                bool bad = false;
+                uint32_t r = rho0;
+#pragma unroll
+                for (uint32_t j = 0; j < 8; j++) {
+                    uint32_t m = mk[j];
+                    while (m) {
+                        const uint32_t b = __ffs(m) - 1u;
+                        m &= m - 1u;
+                        const uint32_t p = lane * SPAN + 32 * j + b;
+                        if (!verified) bad |= buf[p] != '\n';
+                        const uint32_t d = r - a4;
+                        if ((d & 3u) == 0 && (d >> 2) - w0 < room)
+                            ws->q[(qbase + (d >> 2) - w0) & (QCAP - 1)] = (uint16_t)(s * STAGE + p + 1);
+                        r++;
+                    }
+                }
+                if (lane == 0 && extra && a4 == 0 && w0 == 0 && room > 0) ws->q[qbase & (QCAP - 1)] = (uint16_t)(s * STAGE);
+                if (!verified) {
+                    if (__any_sync(FULL, bad)) { redo = true; break; }
+                    verified = true;
+                }
+                __syncwarp();
+                q_len += room;
+                while (q_len >= 32) run_batch(32);
+                w0 += room;
+                if (w0 >= nlive) break;
+            }
+            if (redo) {
+                classify();
+                verified = true;
+                classify_first = true;
+                continue;
+            }
+            // reads numbered in this tile (those below the limit)
+            my_reads += weight * (long long)nlive;
+            break;
         }
         seg_lines += total;
 
-        if (tid == 0) {
-            if (a.mode == MODE_MAIN && tix == seg_ntiles - 1) {
-                SegInfo si;
-                si.lines = seg_lines;
-                si.guess = guess;
-                a.seginfo[seg] = si;
-            }
-            // ---- refill this stage --------------------------------------------
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            produce(s);
+        if (MATCH) {
+            // Entries that point into the previous tile's stage must go before that
+            // stage is refilled; a segment's entries must go before its state changes.
+            while (q_len > 0 && (seg_end || q_old > 0)) run_batch(q_len < 32 ? q_len : 32);
+            q_old = q_len;
         }
+        if (lane == 0 && a.mode == MODE_MAIN && seg_end) {
+            SegInfo si;
+            si.lines = seg_lines;
+            si.guess = guess;
+            a.seginfo[seg] = si;
+        }
+
+        // ---- refill the stage of the previous tile (nothing points into it any more) ---
+        __syncwarp();
+        if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        {
+            const uint32_t sp = s == 0 ? STAGES - 1 : s - 1;
+            produce(sp);
+        }
+        if (++s == STAGES) { s = 0; parity ^= 1u; }
     }
 
     if (MATCH) {
-        // totals: one set of atomics per CTA
+        // totals: one set of atomics per warp
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            my_bar += __shfl_xor_sync(0xFFFFFFFFu, my_bar, o);
-            my_tag += __shfl_xor_sync(0xFFFFFFFFu, my_tag, o);
+            my_bar += __shfl_xor_sync(FULL, my_bar, o);
+            my_tag += __shfl_xor_sync(FULL, my_tag, o);
         }
         if (lane == 0) {
-            atomicAdd(&s_tot[0], (unsigned long long)(long long)my_bar);
-            atomicAdd(&s_tot[1], (unsigned long long)(long long)my_tag);
-        }
-        __syncthreads();
-        if (tid == 0) {
             if (my_reads) atomicAdd(&a.totals[0], (unsigned long long)my_reads);
-            if (s_tot[0]) atomicAdd(&a.totals[1], s_tot[0]);
-            if (s_tot[1]) atomicAdd(&a.totals[2], s_tot[1]);
+            if (my_bar) atomicAdd(&a.totals[1], (unsigned long long)(long long)my_bar);
+            if (my_tag) atomicAdd(&a.totals[2], (unsigned long long)(long long)my_tag);
         }
     }
 }

@@ -108,7 +108,7 @@ inline std::string build_tag_table(const char *bases, const uint64_t *off, const
         uint32_t K = 32;
         for (uint32_t i : members[c]) K = std::min<uint32_t>(K, (uint32_t)(off[i + 1] - off[i]));
         uint32_t slots = 16;
-        while (slots < 2 * members[c].size()) slots <<= 1;
+        while (slots < 4 * members[c].size()) slots <<= 1;   // load <= 1/4: short probe sequences
         TagClass &tc = out.t.cls[out.t.n_classes++];
         tc.K = K;
         tc.base = base;

@@ -117,18 +117,22 @@ def test_unicode_whitespace_and_non_ascii():
     assert want == [[5, 1]]
 
 
+KERNEL_TILE = 7680      # csrc/tdg_kernel.cuh: bytes per warp tile
+
+
+@pytest.mark.parametrize("tile", [KERNEL_TILE, _native.TDG_TILE_BYTES])
 @pytest.mark.parametrize("delta", [-3, -2, -1, 0, 1, 2, 3, 17])
-def test_device_chunk_sizes_around_tile_edges(eng, delta):
+def test_device_chunk_sizes_around_tile_edges(eng, delta, tile):
     """tdg_count_device with n just below / at / above multiples of the tile
     size, and line ends falling exactly on tile and chunk boundaries."""
     r = random.Random(7 + delta)
     barcodes, tags = small_setup(r)
     for ntiles in (1, 2, 5):
-        n = ntiles * _native.TDG_TILE_BYTES + delta
+        n = ntiles * tile + delta
         data = line_soup(r, barcodes, tags, "TGCAG", 3000, ("\n", "\r\n", "\r") if delta % 2 else ("\n",))
         data = (data * (n // len(data) + 1))[:n]
         # force interesting bytes at the edges
-        for pos, ch in ((_native.TDG_TILE_BYTES - 1, b"\n"), (_native.TDG_TILE_BYTES, b"\r"), (n - 1, b"\r" if delta % 2 else b"\n")):
+        for pos, ch in ((tile - 1, b"\n"), (tile, b"\r"), (n - 1, b"\r" if delta % 2 else b"\n")):
             if 0 <= pos < n:
                 data = data[:pos] + ch + data[pos + 1:]
         want, wtot, wlines = _oracle(data, barcodes, tags)
@@ -297,4 +301,107 @@ def test_multi_tile_segments_and_fix_pass(seg_tiles, monkeypatch):
         assert eng.read_matrix().tolist() == want
         assert eng.file_totals()[:3] == wtot
         eng.device_free(dev)
+    eng.close()
+
+
+def _device_count(eng, data, barcodes, tags, cutsite="TGCAG", limit=None):
+    p = matchset.plan(barcodes, tags, cutsite)
+    counting.load_plan(eng, p, nrows=p.barnum)
+    dev, nb = eng.upload(data)
+    try:
+        eng.count_device(dev, nb, reads_limit=_native.limit_from_maxreads(limit or 5e9))
+        return eng.read_matrix().tolist(), eng.file_totals()
+    finally:
+        eng.device_free(dev)
+
+
+@pytest.mark.parametrize("general", ["0", "1"])
+def test_pathological_line_shapes(general, monkeypatch):
+    """Inputs far from FASTQ: thousands of empty lines per tile (several emission
+    rounds per tile), lines longer than a tile, a file without any line end, tabs
+    and other control characters inside lines -- with the fast matcher and with
+    the general matcher (TDG_GENERAL test hook)."""
+    monkeypatch.setenv("TDG_GENERAL", general)
+    eng = _native.Engine(0)
+    r = random.Random(123)
+    barcodes, tags = small_setup(r)
+    hit = barcodes[0] + tags[0]
+    cases = []
+    cases.append(b"\n" * 40000)                                             # every line empty
+    cases.append((hit.encode() + b"\n") * 3000)                             # every line a read-shaped line
+    cases.append(b"\n".join([b"A", hit.encode(), b"", b"#"] * 5000) + b"\n")  # 2-byte records
+    cases.append(b"@h\n" + hit.encode() + b"G" * 30000 + b"\n+\n" + b"I" * 30000 + b"\n" + fastq_of([hit] * 50))
+    cases.append(hit.encode() * 2000)                                        # no line end at all
+    cases.append(b"x\n" + hit.encode())                                     # last line without line end
+    cases.append(fastq_of([hit[:12] + "\t" + hit[12:], "\x0b" + hit, hit + "\x1f", hit[:3] + "\x00" + hit[3:], hit] * 200))
+    cases.append(fastq_of([hit] * 300, newline=b"\r\n") + fastq_of([hit] * 300, newline=b"\r") + fastq_of([hit] * 300))
+    for data in cases:
+        want, wtot, wlines = _oracle(data, barcodes, tags)
+        got, tot = _device_count(eng, data, barcodes, tags)
+        assert got == want
+        assert tot[:3] == wtot
+        assert tot[3] == wlines
+    eng.close()
+
+
+@pytest.mark.parametrize("general", ["0", "1"])
+def test_invalid_bases_and_short_reads_near_tags(general, monkeypatch):
+    """N and other non-bases at every position around the barcode / tag spans,
+    reads cut at every length, variable-length tags (a shorter tag may match
+    although a later base is invalid)."""
+    monkeypatch.setenv("TDG_GENERAL", general)
+    eng = _native.Engine(0)
+    r = random.Random(321)
+    barcodes, tags = small_setup(r, nbar=8, ntag=30, tag_len=(6, 59))
+    reads = []
+    for _ in range(300):
+        s = r.choice(barcodes) + r.choice(tags) + rand_seq(r, r.randint(0, 12))
+        k = r.random()
+        if k < 0.4:
+            j = r.randrange(len(s))
+            s = s[:j] + r.choice("Nn.-*xX@") + s[j + 1:]
+        elif k < 0.7:
+            s = s[:r.randint(0, len(s))]
+        elif k < 0.8:
+            s = s.lower()
+        reads.append(s)
+    data = fastq_of(reads)
+    want, wtot, _ = _oracle(data, barcodes, tags)
+    got, tot = _device_count(eng, data, barcodes, tags)
+    assert got == want
+    assert tot[:3] == wtot
+    eng.close()
+
+
+def test_general_matcher_table_shapes(monkeypatch):
+    """Table shapes outside the fast matcher: tags longer than 64 bases, several
+    length classes, long barcodes, blank barcode with empty cut site."""
+    eng = _native.Engine(0)
+    r = random.Random(77)
+    for shape in ("long_tags", "short_tags", "long_barcodes", "blank"):
+        if shape == "long_tags":
+            barcodes, tags = small_setup(r, tag_len=(60, 150))
+            cutsite = "TGCAG"
+        elif shape == "short_tags":
+            barcodes, tags = small_setup(r, ntag=10, tag_len=(1, 30))
+            cutsite = "TGCAG"
+        elif shape == "long_barcodes":
+            barcodes, tags = small_setup(r)
+            barcodes = [b + rand_seq(r, 14) for b in barcodes]
+            cutsite = "TGCAG"
+        else:
+            barcodes, tags = [""], ["AACGC", "TTG"]
+            cutsite = ""
+        reads = []
+        for _ in range(2000):
+            s = r.choice(barcodes) + (r.choice(tags) if r.random() < 0.7 else cutsite + rand_seq(r, 40)) + rand_seq(r, 20)
+            if r.random() < 0.1:
+                j = r.randrange(len(s))
+                s = s[:j] + "N" + s[j + 1:]
+            reads.append(s)
+        data = fastq_of(reads)
+        want, wtot, _ = _oracle(data, barcodes, tags, cutsite)
+        got, tot = _device_count(eng, data, barcodes, tags, cutsite)
+        assert got == want, shape
+        assert tot[:3] == wtot, shape
     eng.close()
