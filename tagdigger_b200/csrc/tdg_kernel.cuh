@@ -51,26 +51,33 @@
 namespace tdg {
 
 #ifndef TDG_WARPS
-#define TDG_WARPS 8
+#define TDG_WARPS 12
+#endif
+#ifndef TDG_CHUNKS
+#define TDG_CHUNKS 11
+#endif
+#ifndef TDG_HALO
+#define TDG_HALO 256
 #endif
 
-constexpr int      WARPS = TDG_WARPS;              // independent pipelines per CTA
+constexpr int      WARPS = TDG_WARPS;              // independent pipelines per CTA (one CTA per SM)
 constexpr int      THREADS = WARPS * 32;
-constexpr uint32_t CHUNKS = 15;                    // 16-byte pieces per lane per tile
-constexpr uint32_t SPAN = CHUNKS * 16;             // 240 bytes per lane
-constexpr uint32_t TILE = 32 * SPAN;               // 7,680 bytes per warp tile
-constexpr uint32_t HALO = 512;                     // == TDG_HALO_BYTES
-constexpr uint32_t STAGE = TILE + HALO;            // 8,192: one ring stage
-constexpr uint32_t STAGE_SHIFT = 13;
+constexpr uint32_t CHUNKS = TDG_CHUNKS;            // 16-byte pieces per lane per tile; odd: see scan
+constexpr uint32_t SPAN = CHUNKS * 16;             // 176 bytes per lane
+constexpr uint32_t MWORDS = (SPAN + 31) / 32;      // 32-bit mask words per lane
+constexpr uint32_t TILE = 32 * SPAN;               // 5,632 bytes per warp tile
+constexpr uint32_t HALO = TDG_HALO;                // bytes staged past a tile (<= TDG_HALO_BYTES)
+constexpr uint32_t STAGE = TILE + HALO;            // one ring stage
 constexpr int      STAGES = 3;
 constexpr uint32_t RING = STAGES * STAGE;          // bytes of shared memory per warp
 constexpr uint32_t QCAP = 128;                     // queue slots (power of two)
 constexpr uint32_t PUSH_CAP = QCAP - 32;           // starts pushed per emission round
-constexpr uint32_t BAR_SMEM_MAX = 16384;           // barcode tables up to this size are copied to smem
+constexpr uint32_t BAR_SMEM_MAX = 6144;            // barcode tables up to this size are copied to smem
 constexpr uint32_t GUESS_LINES = 16;               // lines inspected for the FASTQ structure guess
 constexpr uint32_t FAST_WORDS_MAX = 24;            // 4-character words the fast matcher packs per read
-static_assert(STAGE == (1u << STAGE_SHIFT), "stage size must be a power of two");
-static_assert(TILE % 16 == 0, "tiles must keep the 16-byte alignment TMA needs");
+static_assert(CHUNKS % 2 == 1, "an odd chunk count keeps the 128-bit scan loads free of bank conflicts");
+static_assert(TILE % 16 == 0 && STAGE % 16 == 0, "tiles must keep the 16-byte alignment TMA needs");
+static_assert(RING < 65536, "queue entries are 16-bit offsets into a warp's ring");
 
 enum { PREV_NONE = 0, PREV_LF = 1, PREV_CR = 2, PREV_OTHER = 3 };
 enum { MODE_MAIN = 0, MODE_FIX = 1 };
@@ -151,7 +158,8 @@ inline uint32_t fast_words_for(const BarTable *bar, const TagTable &tt)
 #if defined(__CUDACC__)
 
 struct WarpShared {           // per-warp control block in shared memory
-    uint16_t q[QCAP];         // queued sequence-line starts: stage * STAGE + offset in stage
+    uint32_t mk[MWORDS][32];  // line-end masks of the tile being numbered: word j of lane l at [j][l]
+    uint16_t q[QCAP];         // queued sequence-line starts: offsets into the warp's ring
     uint32_t item[STAGES];    // work item of the tile in each stage (or NONE)
     uint32_t tix[STAGES];     // tile index inside its segment
     uint32_t tile[STAGES];    // tile index inside the chunk
@@ -207,16 +215,14 @@ __device__ __forceinline__ uint32_t ctl4(uint32_t w)
     uint32_t t = (w & 0x7F7F7F7Fu) + 0x60606060u;
     return ~(t | w) & 0x80808080u;
 }
-// 16 bytes -> 16-bit mask of control characters.  The multiply gathers the
-// four flags of a word into its top nibble (no partial products collide).
+// 16 bytes -> 16-bit mask of control characters.  A byte-wise dot product with
+// the weights 1,2,4,..,128 gathers the 0x80 flags of two words into eight
+// adjacent bits (scaled by 128): one IDP.4A per word.
 __device__ __forceinline__ uint32_t ctl_mask16(uint4 q)
 {
-    uint32_t acc = 0;
-    acc = __funnelshift_l(ctl4(q.w) * 0x00204081u, acc, 4);
-    acc = __funnelshift_l(ctl4(q.z) * 0x00204081u, acc, 4);
-    acc = __funnelshift_l(ctl4(q.y) * 0x00204081u, acc, 4);
-    acc = __funnelshift_l(ctl4(q.x) * 0x00204081u, acc, 4);
-    return acc;
+    uint32_t lo = __dp4a(ctl4(q.y), 0x80402010u, __dp4a(ctl4(q.x), 0x08040201u, 0u));   // flags of bytes 0-7, << 7
+    uint32_t hi = __dp4a(ctl4(q.w), 0x80402010u, __dp4a(ctl4(q.z), 0x08040201u, 0u));   // flags of bytes 8-15, << 7
+    return (hi * 256u + lo) >> 7;
 }
 
 // Unaligned 32-character window out of a shared-memory stage buffer.
@@ -413,15 +419,23 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     const uint32_t nw = MATCH ? a.fast_words : 0;       // 0: general matcher only
     uint32_t need = 0;                                  // bytes a match may touch past the stripped line start
     uint32_t tagK = 0, tag_base = 0, tag_mask = 0;
-    bool uniform_len = false;
+    uint32_t ulen = 0;                                  // > 0: every tag has this length
+    uint32_t UM0 = 0, UM1 = 0, UM2 = 0, UM3 = 0;        // and these are its compare masks
     if (MATCH) {
         need = bar->max_tag_off + a.tags.max_len + 36u;
         if (bar->max_len + 36u > need) need = bar->max_len + 36u;
         tagK = a.tags.cls[0].K;
         tag_base = a.tags.cls[0].base;
         tag_mask = a.tags.cls[0].mask;
-        uniform_len = a.tags.min_len == a.tags.max_len;
+        if (a.tags.min_len == a.tags.max_len && a.tags.max_len <= 64) {
+            ulen = a.tags.max_len;
+            UM0 = lowmask32(ulen);
+            UM1 = lowmask32(ulen > 16 ? ulen - 16 : 0);
+            UM2 = lowmask32(ulen > 32 ? ulen - 32 : 0);
+            UM3 = lowmask32(ulen > 48 ? ulen - 48 : 0);
+        }
     }
+    const uint64_t tag_km = lowmask(tagK);
     const uint4 *tag_entries = (const uint4 *)a.tags.entries;
     long long my_reads = 0;
     int32_t my_bar = 0, my_tag = 0;
@@ -438,6 +452,13 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     bool classify_first = !MATCH;         // sticky: this input has control characters other than '\n'
     uint32_t cur_tile = 0;
 
+    // 128-bit compare of a table entry with the read's key over the entry's length
+    auto tag_differs = [&](const uint4 &k, uint32_t L, uint32_t T0, uint32_t T1, uint32_t T2, uint32_t T3) -> uint32_t {
+        if (ulen) return ((k.x ^ T0) & UM0) | ((k.y ^ T1) & UM1) | ((k.z ^ T2) & UM2) | ((k.w ^ T3) & UM3);
+        return ((k.x ^ T0) & lowmask32(L)) | ((k.y ^ T1) & lowmask32(L > 16 ? L - 16 : 0)) |
+               ((k.z ^ T2) & lowmask32(L > 32 ? L - 32 : 0)) | ((k.w ^ T3) & lowmask32(L > 48 ? L - 48 : 0));
+    };
+
     // Match up to 32 queued line starts, one per lane.
     auto run_batch = [&](uint32_t nb) {
         uint32_t off = 0;
@@ -448,35 +469,33 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         q_old = q_old > nb ? q_old - nb : 0;
         int32_t row = -1, col = -1;
         if (have) {
-            const uint32_t se = off >> STAGE_SHIFT;
-            const uint32_t p = off & (STAGE - 1);
-            const uint8_t *eb = wbase + (off & ~(STAGE - 1));
-            const uint32_t c0 = eb[p];
+            const uint8_t *lp = wbase + off;          // the line start inside the ring
+            const uint32_t c0 = lp[0];
             // the last tiles of a chunk may hold lines cut by the end of the data
             bool slow = nw == 0 || cur_tile + 2 >= a.num_tiles || c0 >= 0x80 || is_lead_space(c0);
             if (!slow) {
                 // ---- fast matcher: pack the first 4*nw characters (from the aligned
                 // word that holds the line start) once, 2 bits per base
-                const uint32_t sh = p & 3u;
-                const uint32_t *wp = (const uint32_t *)(eb + (p & ~3u));
+                const uint32_t sh = off & 3u;
+                const uint32_t *wp = (const uint32_t *)(wbase + (off & ~3u));
                 uint32_t P[FAST_WORDS_MAX / 4];
-                uint32_t bm = 0;          // bit i: word i holds a character outside ACGTacgt
+                uint32_t gbm = 0;         // bit g: words 4g..4g+3 hold a character outside ACGTacgt
 #pragma unroll
                 for (uint32_t g = 0; g < FAST_WORDS_MAX / 4; g++) {
                     P[g] = 0;
                     if (4 * g < nw) {
-                        uint32_t x[4];
+                        uint32_t x[4], gbad = 0;
 #pragma unroll
                         for (uint32_t k = 0; k < 4; k++) {
                             uint32_t bad;
                             x[k] = pack_word(wp[4 * g + k], bad);
                             if (g == 0 && k == 0) bad &= 0xFFFFFFFFu << (8u * sh);   // bytes before the line start
-                            if (bad) bm |= 1u << (4 * g + k);
+                            if (4 * g + k < nw) gbad |= bad;
                         }
+                        if (gbad) gbm |= 1u << g;
                         P[g] = __byte_perm(__byte_perm(x[0], x[1], 0x0073), __byte_perm(x[2], x[3], 0x0073), 0x5410);
                     }
                 }
-                bm &= nw >= 32 ? 0xFFFFFFFFu : ((1u << nw) - 1u);
                 // ---- barcode + cut site: first 16 bases, bucket = first 4
                 const uint32_t key0 = __funnelshift_r(P[0], P[1], 2u * sh);
                 uint32_t tag_off = 0, blen = 0;
@@ -504,7 +523,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                                    Q3 = up ? P[4] : P[3], Q4 = up ? P[5] : P[4];
                     const uint32_t T0 = __funnelshift_r(Q0, Q1, bit), T1 = __funnelshift_r(Q1, Q2, bit),
                                    T2 = __funnelshift_r(Q2, Q3, bit), T3 = __funnelshift_r(Q3, Q4, bit);
-                    const uint64_t pre = (((uint64_t)T1 << 32) | T0) & lowmask(tagK);
+                    const uint64_t pre = (((uint64_t)T1 << 32) | T0) & tag_km;
                     uint32_t h = tag_hash(pre) & tag_mask;
                     for (;;) {
                         // two neighbouring slots per round trip
@@ -514,40 +533,38 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                         const uint4 k0 = __ldg(e0), m0 = __ldg(e0 + 1);
                         const uint4 k1 = __ldg(e1), m1 = __ldg(e1 + 1);
                         if (m0.x == TDG_EMPTY_LEN) break;
-                        {
-                            const uint32_t L = m0.x;
-                            uint32_t d = ((k0.x ^ T0) & lowmask32(L)) | ((k0.y ^ T1) & lowmask32(L > 16 ? L - 16 : 0));
-                            d |= ((k0.z ^ T2) & lowmask32(L > 32 ? L - 32 : 0)) | ((k0.w ^ T3) & lowmask32(L > 48 ? L - 48 : 0));
-                            if (d == 0) { col = (int32_t)m0.y; tlen = L; break; }
-                        }
+                        if (tag_differs(k0, m0.x, T0, T1, T2, T3) == 0) { col = (int32_t)m0.y; tlen = m0.x; break; }
                         if (m1.x == TDG_EMPTY_LEN) break;
-                        {
-                            const uint32_t L = m1.x;
-                            uint32_t d = ((k1.x ^ T0) & lowmask32(L)) | ((k1.y ^ T1) & lowmask32(L > 16 ? L - 16 : 0));
-                            d |= ((k1.z ^ T2) & lowmask32(L > 32 ? L - 32 : 0)) | ((k1.w ^ T3) & lowmask32(L > 48 ? L - 48 : 0));
-                            if (d == 0) { col = (int32_t)m1.y; tlen = L; break; }
-                        }
+                        if (tag_differs(k1, m1.x, T0, T1, T2, T3) == 0) { col = (int32_t)m1.y; tlen = m1.x; break; }
                         h = (h1 + 1) & tag_mask;
                     }
-                    (void)uniform_len;
                 }
-                if (row >= 0 && bm != 0) {
+                if (row >= 0 && gbm != 0) {
                     // some character is not a base: the matches stand only if they end before it
-                    const uint32_t fw = __ffs(bm) - 1u;
-                    uint32_t bad;
-                    (void)pack_word(wp[fw], bad);
-                    if (fw == 0) bad &= 0xFFFFFFFFu << (8u * sh);
-                    const uint32_t k = (bad & 0xFFu) ? 0u : (bad & 0xFF00u) ? 1u : (bad & 0xFF0000u) ? 2u : 3u;
-                    const uint32_t V = 4u * fw + k - sh;       // valid bases from the line start
+                    const uint32_t g0 = __ffs(gbm) - 1u;
+                    uint32_t V = 0xFFFFFFFFu;                  // valid bases from the line start
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; k++) {
+                        const uint32_t i = 4 * g0 + k;
+                        uint32_t bad;
+                        (void)pack_word(wp[i], bad);
+                        if (i == 0) bad &= 0xFFFFFFFFu << (8u * sh);
+                        if (V == 0xFFFFFFFFu && bad != 0 && i < nw) {
+                            const uint32_t kk = (bad & 0xFFu) ? 0u : (bad & 0xFF00u) ? 1u : (bad & 0xFF0000u) ? 2u : 3u;
+                            V = 4u * i + kk - sh;
+                        }
+                    }
                     if (blen > V) { row = -1; col = -1; }
                     else if (col >= 0 && tag_off + tlen > V) col = -1;
                 }
             } else {
+                const uint32_t se = off >= 2 * STAGE ? 2u : (off >= STAGE ? 1u : 0u);
+                const uint32_t p = off - se * STAGE;
                 const uint32_t tile = ws->tile[se];
                 const unsigned long long tile_off = (unsigned long long)tile * TILE;
                 const unsigned long long avail = a.n - tile_off;
                 const uint32_t staged = avail < copy_bytes ? (uint32_t)avail : copy_bytes;
-                MatchResult mr = match_general(eb, p, staged, a.bytes + tile_off, avail, need, bar, bent, &a.tags);
+                MatchResult mr = match_general(wbase + se * STAGE, p, staged, a.bytes + tile_off, avail, need, bar, bent, &a.tags);
                 row = mr.row;
                 col = mr.col;
             }
@@ -598,6 +615,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         const bool last_tile = t == a.num_tiles - 1;
 
         const uint8_t *buf = wbase + s * STAGE;
+        const uint32_t sbase = s * STAGE;
         const unsigned long long tile_off = (unsigned long long)t * TILE;
         const unsigned long long avail = a.n - tile_off;            // bytes from tile start to chunk end
         const uint32_t valid = avail < TILE ? (uint32_t)avail : TILE;
@@ -609,8 +627,10 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             else if (prev_kind == PREV_CR && buf[0] != '\n') extra = 1;
         }
 
-        // ---- scan: control-character mask of my 240 bytes ----------------------
-        uint32_t mk[8];
+        // ---- scan: control-character mask of my SPAN bytes ----------------------
+        // (lane l reads 16-byte units CHUNKS*l + i: with CHUNKS odd, eight consecutive
+        // lanes hit eight different bank groups, so every 128-bit load is conflict free)
+        uint32_t mk[MWORDS];
         {
             const uint4 *src = (const uint4 *)(buf + lane * SPAN);
 #pragma unroll
@@ -627,7 +647,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             const uint32_t first = lane * SPAN;
             const uint32_t keep = lim > first ? lim - first : 0;
 #pragma unroll
-            for (uint32_t j = 0; j < 8; j++) {
+            for (uint32_t j = 0; j < MWORDS; j++) {
                 uint32_t nb = keep > 32 * j ? keep - 32 * j : 0;
                 if (nb < 32) mk[j] &= (1u << nb) - 1u;
             }
@@ -636,33 +656,46 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 *a.last_kind = c == '\n' ? PREV_LF : (c == '\r' ? PREV_CR : PREV_OTHER);
             }
         }
+        // the candidate loops below walk the masks through shared memory (one loop
+        // over all candidates of a lane instead of one loop per mask word)
+        uint32_t cnt = 0, nz = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < MWORDS; j++) {
+            ws->mk[j][lane] = mk[j];
+            cnt += __popc(mk[j]);
+            if (mk[j]) nz |= 1u << j;
+        }
 
         // exact line ends: '\n' ends a line; '\r' ends one unless a '\n' follows
         // (Python universal newlines); every other control character is content.
         auto classify = [&]() {
-#pragma unroll
-            for (uint32_t j = 0; j < 8; j++) {
-                uint32_t m = mk[j];
+            uint32_t nzl = nz;
+            cnt = 0;
+            nz = 0;
+            while (nzl) {
+                const uint32_t j = __ffs(nzl) - 1u;
+                nzl &= nzl - 1u;
+                uint32_t m = ws->mk[j][lane], keepm = m;
                 while (m) {
-                    uint32_t b = __ffs(m) - 1u;
+                    const uint32_t b = __ffs(m) - 1u;
                     m &= m - 1u;
-                    uint32_t p = lane * SPAN + 32 * j + b;
-                    uint32_t c = buf[p];
+                    const uint32_t p = lane * SPAN + 32 * j + b;
+                    const uint32_t c = buf[p];
                     bool end = c == '\n';
                     // the byte after the last byte of the chunk is unknown: pending
                     if (c == '\r') end = (p + 1 < avail) && buf[p + 1] != '\n';
-                    if (!end) mk[j] &= ~(1u << b);
+                    if (!end) keepm &= ~(1u << b);
                 }
+                ws->mk[j][lane] = keepm;
+                cnt += __popc(keepm);
+                if (keepm) nz |= 1u << j;
             }
         };
         bool verified = false;
         if (classify_first || need_guess) { classify(); verified = true; }
 
-        uint32_t cnt, incl, total;
+        uint32_t incl, total;
         for (;;) {
-            cnt = 0;
-#pragma unroll
-            for (uint32_t j = 0; j < 8; j++) cnt += __popc(mk[j]);
             incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -679,12 +712,13 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 // sequence and quality lines of equal length).  Any answer is acceptable --
                 // a wrong one is found and repaired by verify_kernel + the fix pass.
                 {
-                    uint32_t r = rho0;
-#pragma unroll
-                    for (uint32_t j = 0; j < 8; j++) {
-                        uint32_t m = mk[j];
+                    uint32_t r = rho0, nzl = nz;
+                    while (nzl && r < GUESS_LINES + 5) {
+                        const uint32_t j = __ffs(nzl) - 1u;
+                        nzl &= nzl - 1u;
+                        uint32_t m = ws->mk[j][lane];
                         while (m && r < GUESS_LINES + 5) {
-                            uint32_t b = __ffs(m) - 1u;
+                            const uint32_t b = __ffs(m) - 1u;
                             m &= m - 1u;
                             ws->gs[r] = (uint16_t)(lane * SPAN + 32 * j + b + 1);
                             r++;
@@ -717,35 +751,53 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     nlive = nq < room ? nq : (uint32_t)room;
                 }
             }
+            // my first sequence line: `skip0` candidates on, ordinal `jj0` among the tile's
+            const uint32_t skip0 = (a4 - rho0) & 3u;
+            const uint32_t jj0 = (rho0 + skip0 - a4) >> 2;
             bool redo = false;
             for (uint32_t w0 = 0;;) {
                 const uint32_t room = nlive - w0 < PUSH_CAP ? nlive - w0 : PUSH_CAP;
-                const uint32_t qbase = q_head + q_len;
+                const uint32_t qbase = q_head + q_len - w0;           // slot of ordinal 0
                 bool bad = false;
-                uint32_t r = rho0;
-#pragma unroll
-                for (uint32_t j = 0; j < 8; j++) {
-                    uint32_t m = mk[j];
-                    while (m) {
-                        const uint32_t b = __ffs(m) - 1u;
-                        m &= m - 1u;
-                        const uint32_t p = lane * SPAN + 32 * j + b;
-                        if (!verified) bad |= buf[p] != '\n';
-                        const uint32_t d = r - a4;
-                        if ((d & 3u) == 0 && (d >> 2) - w0 < room)
-                            ws->q[(qbase + (d >> 2) - w0) & (QCAP - 1)] = (uint16_t)(s * STAGE + p + 1);
-                        r++;
+                uint32_t skip = skip0, jj = jj0, nzl = nz, cur = 0, pbase = 0;
+                for (;;) {
+                    if (cur == 0) {
+                        if (nzl == 0) break;
+                        const uint32_t j = __ffs(nzl) - 1u;
+                        nzl &= nzl - 1u;
+                        cur = ws->mk[j][lane];
+                        pbase = lane * SPAN + 32 * j;
+                    }
+                    const uint32_t p = pbase + __ffs(cur) - 1u;
+                    cur &= cur - 1u;
+                    if (!verified) bad |= buf[p] != '\n';
+                    if (skip == 0) {
+                        if (jj - w0 < room) ws->q[(qbase + jj) & (QCAP - 1)] = (uint16_t)(sbase + p + 1);
+                        jj++;
+                        skip = 3;
+                    } else {
+                        skip--;
                     }
                 }
-                if (lane == 0 && extra && a4 == 0 && w0 == 0 && room > 0) ws->q[qbase & (QCAP - 1)] = (uint16_t)(s * STAGE);
+                if (lane == 0 && extra && a4 == 0 && w0 == 0 && room > 0) ws->q[qbase & (QCAP - 1)] = (uint16_t)sbase;
                 if (!verified) {
                     if (__any_sync(FULL, bad)) { redo = true; break; }
                     verified = true;
                 }
                 __syncwarp();
                 q_len += room;
-                while (q_len >= 32) run_batch(32);
                 w0 += room;
+                // Match full warps.  After the tile's last round also drain what must not
+                // wait: entries that point into the previous tile's stage have to go
+                // before that stage is refilled, a segment's entries before its state
+                // (weight, limit) changes.
+                for (;;) {
+                    uint32_t nb;
+                    if (q_len >= 32) nb = 32;
+                    else if (w0 >= nlive && q_len > 0 && (seg_end || q_old > 0)) nb = q_len;
+                    else break;
+                    run_batch(nb);
+                }
                 if (w0 >= nlive) break;
             }
             if (redo) {
@@ -760,12 +812,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         }
         seg_lines += total;
 
-        if (MATCH) {
-            // Entries that point into the previous tile's stage must go before that
-            // stage is refilled; a segment's entries must go before its state changes.
-            while (q_len > 0 && (seg_end || q_old > 0)) run_batch(q_len < 32 ? q_len : 32);
-            q_old = q_len;
-        }
+        q_old = q_len;
         if (lane == 0 && a.mode == MODE_MAIN && seg_end) {
             SegInfo si;
             si.lines = seg_lines;
