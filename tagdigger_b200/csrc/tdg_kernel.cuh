@@ -160,9 +160,8 @@ inline uint32_t fast_words_for(const BarTable *bar, const TagTable &tt)
 struct WarpShared {           // per-warp control block in shared memory
     uint32_t mk[MWORDS][32];  // line-end masks of the tile being numbered: word j of lane l at [j][l]
     uint16_t q[QCAP];         // queued sequence-line starts: offsets into the warp's ring
-    uint32_t item[STAGES];    // work item of the tile in each stage (or NONE)
-    uint32_t tix[STAGES];     // tile index inside its segment
-    uint32_t tile[STAGES];    // tile index inside the chunk
+    uint32_t tile[STAGES];    // tile index (inside the chunk) of each stage
+    uint32_t spare[2 * STAGES];
     uint16_t gs[GUESS_LINES + 8];   // first line starts of a segment
     uint32_t pad[3];
 };
@@ -375,9 +374,12 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     const uint32_t copy_bytes = TILE + a.halo_bytes;
 
     // ---- producer: the next tile to request (state uniform across the warp) --------
+    // Stage metadata travels in registers (every lane holds the same values); only
+    // the tile index is also kept in shared memory, for the general matcher.
+    struct StageMeta { uint32_t item, tix, tile; };
     uint32_t p_item = NONE, p_seg = 0, p_tix = 0, p_ntiles = 0;
     bool p_done = false;
-    auto produce = [&](uint32_t s) {
+    auto produce = [&](uint32_t s) -> StageMeta {
         if (p_tix == p_ntiles && !p_done) {
             unsigned long long t = 0;
             if (lane == 0) t = atomicAdd(a.ticket, 1ull);
@@ -396,24 +398,26 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 p_done = true;
             }
         }
-        if (lane == 0) {
-            ws->item[s] = p_item;
-            ws->tix[s] = p_tix;
-            if (p_item != NONE) {
-                uint32_t tile = p_seg * a.seg_tiles + p_tix;
-                ws->tile[s] = tile;
-                unsigned long long off = (unsigned long long)tile * TILE;
+        StageMeta m;
+        m.item = p_item;
+        m.tix = p_tix;
+        m.tile = p_seg * a.seg_tiles + p_tix;
+        if (p_item != NONE) {
+            if (lane == 0) {
+                ws->tile[s] = m.tile;
+                unsigned long long off = (unsigned long long)m.tile * TILE;
                 unsigned long long left = a.n - off;
                 uint32_t bytes = copy_bytes;
                 if (left < bytes) bytes = ((uint32_t)left + 15u) & ~15u;
                 mbar_expect_tx(&full_bar[warp][s], bytes);
                 bulk_g2s(wbase + s * STAGE, a.bytes + off, bytes, &full_bar[warp][s]);
             }
+            p_tix++;
         }
-        if (p_item != NONE) p_tix++;
+        return m;
     };
-    produce(0);
-    produce(1);
+    StageMeta metaA = produce(0);          // the tile processed next
+    StageMeta metaB = produce(1);          // the one after it
 
     // ---- matcher set-up (uniform) -----------------------------------------------------
     const uint32_t nw = MATCH ? a.fast_words : 0;       // 0: general matcher only
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                             uint32_t bad;
                             x[k] = pack_word(wp[4 * g + k], bad);
                             if (g == 0 && k == 0) bad &= 0xFFFFFFFFu << (8u * sh);   // bytes before the line start
-                            if (4 * g + k < nw) gbad |= bad;
+                            gbad |= bad;      // words past nw may flag too: V below ignores them
                         }
                         if (gbad) gbm |= 1u << g;
                         P[g] = __byte_perm(__byte_perm(x[0], x[1], 0x0073), __byte_perm(x[2], x[3], 0x0073), 0x5410);
@@ -583,11 +587,10 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
 
     uint32_t s = 0, parity = 0;
     for (;;) {
-        __syncwarp();
-        const uint32_t item = ws->item[s];
+        const uint32_t item = metaA.item;
         if (item == NONE) break;
-        const uint32_t tix = ws->tix[s];
-        const uint32_t t = ws->tile[s];               // tile index in the chunk
+        const uint32_t tix = metaA.tix;
+        const uint32_t t = metaA.tile;                // tile index in the chunk
         cur_tile = t;
         mbar_wait(&full_bar[warp][s], parity);
 
@@ -754,34 +757,59 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             // my first sequence line: `skip0` candidates on, ordinal `jj0` among the tile's
             const uint32_t skip0 = (a4 - rho0) & 3u;
             const uint32_t jj0 = (rho0 + skip0 - a4) >> 2;
+            // Common case: everything fits one round, the read limit does not fall inside
+            // the tile and no lane holds more than two sequence-line starts.
+            const bool simple = nlive == nq && nq <= PUSH_CAP && !__any_sync(FULL, cnt > skip0 + 8u);
             bool redo = false;
             for (uint32_t w0 = 0;;) {
                 const uint32_t room = nlive - w0 < PUSH_CAP ? nlive - w0 : PUSH_CAP;
                 const uint32_t qbase = q_head + q_len - w0;           // slot of ordinal 0
-                bool bad = false;
-                uint32_t skip = skip0, jj = jj0, nzl = nz, cur = 0, pbase = 0;
-                for (;;) {
-                    if (cur == 0) {
-                        if (nzl == 0) break;
-                        const uint32_t j = __ffs(nzl) - 1u;
-                        nzl &= nzl - 1u;
-                        cur = ws->mk[j][lane];
-                        pbase = lane * SPAN + 32 * j;
+                uint32_t dev = 0;                                     // non-zero: a candidate is not '\n'
+                uint32_t nzl = nz, cur = 0, pbase = 0;
+                if (simple) {
+                    // one walk over my candidates: check them, remember the (at most two)
+                    // that start a sequence line
+                    uint32_t o = 0, qp0 = 0, qp1 = 0;
+                    while ((cur | nzl) != 0) {
+                        if (cur == 0) {
+                            const uint32_t j = __ffs(nzl) - 1u;
+                            nzl &= nzl - 1u;
+                            cur = ws->mk[j][lane];
+                            pbase = lane * SPAN + 32 * j;
+                        }
+                        const uint32_t p = pbase + __ffs(cur) - 1u;
+                        cur &= cur - 1u;
+                        dev |= (uint32_t)buf[p] ^ 0x0Au;
+                        if (o == skip0) qp0 = p;
+                        if (o == skip0 + 4u) qp1 = p;
+                        o++;
                     }
-                    const uint32_t p = pbase + __ffs(cur) - 1u;
-                    cur &= cur - 1u;
-                    if (!verified) bad |= buf[p] != '\n';
-                    if (skip == 0) {
-                        if (jj - w0 < room) ws->q[(qbase + jj) & (QCAP - 1)] = (uint16_t)(sbase + p + 1);
-                        jj++;
-                        skip = 3;
-                    } else {
-                        skip--;
+                    if (cnt > skip0) ws->q[(qbase + jj0) & (QCAP - 1)] = (uint16_t)(sbase + qp0 + 1);
+                    if (cnt > skip0 + 4u) ws->q[(qbase + jj0 + 1) & (QCAP - 1)] = (uint16_t)(sbase + qp1 + 1);
+                } else {
+                    uint32_t skip = skip0, jj = jj0;
+                    while ((cur | nzl) != 0) {
+                        if (cur == 0) {
+                            const uint32_t j = __ffs(nzl) - 1u;
+                            nzl &= nzl - 1u;
+                            cur = ws->mk[j][lane];
+                            pbase = lane * SPAN + 32 * j;
+                        }
+                        const uint32_t p = pbase + __ffs(cur) - 1u;
+                        cur &= cur - 1u;
+                        dev |= (uint32_t)buf[p] ^ 0x0Au;
+                        if (skip == 0) {
+                            if (jj - w0 < room) ws->q[(qbase + jj) & (QCAP - 1)] = (uint16_t)(sbase + p + 1);
+                            jj++;
+                            skip = 3;
+                        } else {
+                            skip--;
+                        }
                     }
                 }
                 if (lane == 0 && extra && a4 == 0 && w0 == 0 && room > 0) ws->q[qbase & (QCAP - 1)] = (uint16_t)sbase;
                 if (!verified) {
-                    if (__any_sync(FULL, bad)) { redo = true; break; }
+                    if (__any_sync(FULL, dev != 0)) { redo = true; break; }
                     verified = true;
                 }
                 __syncwarp();
@@ -823,10 +851,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         // ---- refill the stage of the previous tile (nothing points into it any more) ---
         __syncwarp();
         if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        {
-            const uint32_t sp = s == 0 ? STAGES - 1 : s - 1;
-            produce(sp);
-        }
+        metaA = metaB;
+        metaB = produce(s == 0 ? STAGES - 1 : s - 1);
         if (++s == STAGES) { s = 0; parity ^= 1u; }
     }
 
