@@ -276,9 +276,10 @@ def main():
     try:
         with open(os.path.join(REPO, "profiles", "traffic.json")) as fh:
             tj = json.load(fh)
-        if tj.get("reads_per_launch") == nreads:
-            traffic = tj.get("dram_bytes_per_launch")
-    except (OSError, ValueError):
+        # measured per launch with ncu on a smaller launch of the same workload
+        # (profiles/traffic.json); the kernel streams, so DRAM bytes scale with reads
+        traffic = int(round(float(tj["dram_bytes_per_read"]) * nreads))
+    except (OSError, ValueError, KeyError):
         pass
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic,
