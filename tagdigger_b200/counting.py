@@ -104,3 +104,105 @@ def find_tags_bytes(data, barcodes, tags, cutsite="TGCAG", maxreads=5e9, device=
     if totals is not None:
         totals[:] = tot
     return eng.read_matrix().tolist()
+
+
+def global_rows(bckeys):
+    """Sample names in output order and, for every file, the matrix row of each
+    of its barcodes -- the row layout combineReadCounts produces
+    (tagdigger_fun.py:1061-1098): files in sorted order, samples in key-file
+    order, one row per distinct sample name."""
+    samples, row_of, rows = [], {}, {}
+    for f in sorted(bckeys.keys()):
+        mine = []
+        for sample in bckeys[f][1]:
+            r = row_of.get(sample)
+            if r is None:
+                r = row_of[sample] = len(samples)
+                samples.append(sample)
+            mine.append(r)
+        rows[f] = mine
+    return samples, rows
+
+
+def count_files(bckeys, tags, cutsite="TGCAG", maxreads=5e9, device=None, rank=0, world=1, reduce=None,
+                totals=None):
+    """All files of a key (``readBarcodeKeyfile`` output) in one go: the batched
+    form of the loop at tagdigger_script.py:123-128.  Every file counts straight
+    into the GLOBAL sample rows of one device matrix, so the result equals
+    ``combineReadCounts({f: find_tags_fastq(f, ...)}, bckeys)`` without per-file
+    matrices; the tag table is uploaded once.
+
+    With ``world > 1`` (one process per GPU) the files are dealt to the ranks by
+    size (largest first, to the least loaded rank) and ``reduce(ptr, rows, cols,
+    engine)`` must sum the per-rank matrices in place (one NCCL all-reduce, see
+    :func:`nccl_reduce`); integer sums make the result independent of ``world``.
+
+    Returns ``[sample names, count rows]``; ``totals`` (optional dict) receives
+    ``{file: [reads, with barcode and cut site, with tag]}`` for this rank's files."""
+    files = sorted(bckeys.keys())
+    samples, rows = global_rows(bckeys)
+    limit = _native.limit_from_maxreads(maxreads)
+    plans = {}
+    for f in files:                               # set-up errors surface before any counting, file by file
+        plans[f] = matchset.plan(bckeys[f][0], tags, cutsite)
+        if plans[f].barnum == 0 or plans[f].ntags == 0:
+            raise IndexError("list index out of range")
+    ntags = len(tags)
+    eng = get_engine(device)
+    first = plans[files[0]]
+    eng.set_tags(first.tags.patterns, first.tags.index, any_base=first.tags.any_base)
+    eng.set_matrix(len(samples), ntags)
+    for f in assign_files(files, rank, world):
+        p = plans[f]
+        load_plan(eng, p, row_of=rows[f], set_tags=False)
+        tot = _run_file(eng, f, limit)
+        print("{0}: Reads: {1} With barcode and cut site: {2} With tag: {3}".format(f, tot[0], tot[1], tot[2]))
+        if totals is not None:
+            totals[f] = tot[:3]
+    if world > 1:
+        if reduce is None:
+            raise ValueError("count_files with world > 1 needs a reduce callable (see nccl_reduce)")
+        reduce(eng.matrix_ptr(), len(samples), ntags, eng)
+    return [samples, eng.read_matrix().tolist()]
+
+
+def assign_files(files, rank, world):
+    """The files rank ``rank`` of ``world`` counts: longest-processing-time-first
+    by file size, ties and unreadable sizes in name order (deterministic on every
+    rank)."""
+    if world <= 1:
+        return list(files)
+
+    def size(f):
+        try:
+            return os.path.getsize(f)
+        except OSError:
+            return 0
+    load = [0] * world
+    mine = []
+    for f in sorted(files, key=lambda f: (-size(f), f)):
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += max(size(f), 1)
+        if r == rank:
+            mine.append(f)
+    return sorted(mine)
+
+
+def nccl_reduce(ptr, rows, cols, eng):
+    """Sum the per-GPU count matrices in place with ONE all-reduce, issued in
+    stream order behind the last count kernel (the multi-GPU form of the sum in
+    combineReadCounts, tagdigger_fun.py:1088-1095).  Needs an initialised
+    torch.distributed process group (backend nccl)."""
+    import torch
+    import torch.distributed as dist
+
+    class _View(object):          # the library's matrix as a torch tensor, without copying
+        pass
+    v = _View()
+    v.__cuda_array_interface__ = {"shape": (rows, cols), "typestr": "<i4", "data": (ptr, False), "version": 3,
+                                  "strides": None}
+    t = torch.as_tensor(v, device=torch.device("cuda", eng.device))
+    stream = torch.cuda.current_stream().cuda_stream
+    eng.other_stream_wait(stream)
+    dist.all_reduce(t)
+    eng.stream_wait(stream)
