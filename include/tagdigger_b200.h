@@ -176,6 +176,25 @@ uint64_t    tdg_launch_count(const tdg_ctx *ctx);
 int         tdg_timing_begin(tdg_ctx *ctx);
 int         tdg_timing_end(tdg_ctx *ctx, double *kernel_ms, uint32_t *nlaunch);
 
+/* Trim decision of the barcode splitter (findAdapterSeq, tagdigger_fun.py:1251-1283,
+ * with the tables of build_adapter_tree, :1208-1249).  The host passes the two full
+ * restriction sites (common cutter, rare cutter), the common-cutter string a0 (site
+ * remnant + adapter), one rare-cutter string per barcode (a1, CSR offsets) and, per
+ * barcode, the REACHABLE adapter prefixes of the reference's reversed trie as
+ * (which string, length, slice index) triples -- tagdigger_b200/trimming.py derives
+ * them, including the reference's overlap fallback (:1237-1248). */
+int         tdg_set_trim(tdg_ctx *ctx, const char *site0, const char *site1, const char *a0,
+                         uint32_t nbar, const char *a1, const uint32_t *a1_off,
+                         const uint32_t *cand_off, const uint16_t *cand_len,
+                         const int16_t *cand_idx, const uint8_t *cand_which);
+/* slice2[i] = findAdapterSeq(seq_i, tables[bar[i]], site0, site1, start[i]) for n
+ * sequence lines given as HOST buffers (already stripped; case is folded on the
+ * device): position after the first full site at or after start[i] (the earlier of
+ * the two, the rare cutter on a tie), else the negative slice index of the adapter
+ * prefix the read ends with, else 999.  One warp per read; synchronous. */
+int         tdg_trim_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, const int32_t *bar,
+                           const uint32_t *start, uint32_t n, int32_t *slice2);
+
 /* Host-side self test of the packed tables: looks one read (a sequence line as
  * found in the file, without its line end) up in the tables exactly as the
  * kernel does (same inline code compiled for the host).  Returns the matrix

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.path.join(_HERE, "libtagdigger_b200.so")
-_SOURCES = ["tdg_api.cu", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h"]
+_SOURCES = ["tdg_api.cu", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h", "tdg_trim.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "20014,20011", "-shared"]
@@ -35,7 +35,7 @@ tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end
 tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
-tdg_timing_begin tdg_timing_end tdg_selftest_match tdg_create_hostonly""".split()
+tdg_timing_begin tdg_timing_end tdg_selftest_match tdg_create_hostonly tdg_set_trim tdg_trim_batch""".split()
 
 
 class TdgError(RuntimeError):
@@ -118,6 +118,8 @@ def lib():
         "tdg_timing_begin": (i32, [vp]),
         "tdg_timing_end": (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u32)]),
         "tdg_selftest_match": (ctypes.c_int64, [vp, ctypes.c_char_p, sz]),
+        "tdg_set_trim": (i32, [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, u32, vp, vp, vp, vp, vp, vp]),
+        "tdg_trim_batch": (i32, [vp, vp, vp, vp, vp, u32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -322,6 +324,35 @@ class Engine(object):
         n = ctypes.c_uint32(0)
         self._ck(self._L.tdg_timing_end(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    # -- trim decision ------------------------------------------------------
+    def set_trim(self, site0, site1, a0, a1_list, cands):
+        """cands[b]: list of (which, length, slice index) for barcode b (trimming.trim_tables)."""
+        a1_blob, a1_off = _csr(a1_list, np.uint32)
+        cand_off = np.zeros(len(cands) + 1, dtype=np.uint32)
+        if len(cands):
+            np.cumsum([len(c) for c in cands], out=cand_off[1:])
+        flat = [t for c in cands for t in c]
+        which = np.asarray([t[0] for t in flat], dtype=np.uint8)
+        clen = np.asarray([t[1] for t in flat], dtype=np.uint16)
+        cidx = np.asarray([t[2] for t in flat], dtype=np.int16)
+        self._ck(self._L.tdg_set_trim(self._h, site0.encode("ascii"), site1.encode("ascii"), a0.encode("ascii"),
+                                      len(cands), a1_blob, a1_off.ctypes.data, cand_off.ctypes.data,
+                                      clen.ctypes.data, cidx.ctypes.data, which.ctypes.data))
+
+    def trim_batch(self, seqs, bars, starts):
+        """seqs: list of bytes/str sequence lines; returns the list of slice2 values."""
+        raw = [x.encode("utf-8") if isinstance(x, str) else bytes(x) for x in seqs]
+        blob = b"".join(raw)
+        off = np.zeros(len(raw) + 1, dtype=np.uint64)
+        if raw:
+            np.cumsum([len(x) for x in raw], out=off[1:])
+        bar = np.asarray(list(bars), dtype=np.int32)
+        start = np.asarray(list(starts), dtype=np.uint32)
+        out = np.empty(len(raw), dtype=np.int32)
+        self._ck(self._L.tdg_trim_batch(self._h, blob, off.ctypes.data, bar.ctypes.data, start.ctypes.data,
+                                        len(raw), out.ctypes.data))
+        return [int(x) for x in out]
 
     def selftest_match(self, read):
         if isinstance(read, str):

@@ -17,6 +17,7 @@
 #include "../../include/tagdigger_b200.h"
 #include "tdg_kernel.cuh"
 #include "tdg_tables.h"
+#include "tdg_trim.cuh"
 
 static_assert(TDG_HALO_BYTES >= tdg::HALO, "the allocation slack promised by the header must cover the kernel halo");
 
@@ -80,6 +81,13 @@ struct tdg_ctx {
     int next_slot = 0;
     size_t carry_len = 0;        // bytes waiting in slot[next_slot].carry
     bool file_open = false;
+
+    // trim decision tables (tdg_set_trim): one device blob
+    uint8_t *d_trim = nullptr;
+    size_t d_trim_cap = 0;
+    tdg::TrimArgs trim;          // device pointers into d_trim
+    uint32_t trim_nbar = 0;
+    bool have_trim = false;
 
     // accounting
     uint64_t launches = 0;
@@ -481,6 +489,7 @@ void tdg_destroy(tdg_ctx *ctx)
         if (ctx->d_sync) cudaFree(ctx->d_sync);
         if (ctx->d_state) cudaFree(ctx->d_state);
         if (ctx->d_totals) cudaFree(ctx->d_totals);
+        if (ctx->d_trim) cudaFree(ctx->d_trim);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     }
@@ -984,6 +993,119 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     for (int i = 0; i < NBUF; i++) cudaFreeHost(bufs[i].p);
     if (result == TDG_OK && totals) result = tdg_file_totals(ctx, totals);
     return result;
+}
+
+// ---------------------------------------------------------------------------
+// Trim decision (barcode splitter), csrc/tdg_trim.cuh
+
+int tdg_set_trim(tdg_ctx *ctx, const char *site0, const char *site1, const char *a0, uint32_t nbar, const char *a1,
+                 const uint32_t *a1_off, const uint32_t *cand_off, const uint16_t *cand_len, const int16_t *cand_idx,
+                 const uint8_t *cand_which)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!site0 || !site1 || !a0 || !a1 || !a1_off || !cand_off || (cand_off[nbar] && (!cand_len || !cand_idx || !cand_which)))
+        return fail(ctx, TDG_ERR_ARG, "null argument");
+    ctx->have_trim = false;
+    const size_t l0 = strlen(site0), l1 = strlen(site1), la0 = strlen(a0);
+    if (l0 == 0 || l1 == 0) return fail(ctx, TDG_ERR_ARG, "tdg_set_trim: restriction sites must not be empty");
+    const uint32_t ncand = cand_off[nbar];
+    std::vector<tdg::TrimCand> cand(ncand);
+    for (uint32_t b = 0; b < nbar; b++) {
+        if (a1_off[b + 1] < a1_off[b] || cand_off[b + 1] < cand_off[b]) return fail(ctx, TDG_ERR_ARG, "offsets must be non-decreasing");
+        for (uint32_t c = cand_off[b]; c < cand_off[b + 1]; c++) {
+            size_t have = cand_which[c] ? (size_t)(a1_off[b + 1] - a1_off[b]) : la0;
+            if (cand_len[c] == 0 || cand_len[c] > have)
+                return fail(ctx, TDG_ERR_ARG, "tdg_set_trim: candidate " + std::to_string(c) + " is longer than its adapter string");
+            cand[c].len = cand_len[c];
+            cand[c].idx = cand_idx[c];
+            cand[c].which = cand_which[c] ? 1u : 0u;
+        }
+    }
+    // blob: site0 | site1 | a0 | a1 | a1_off | cand_off | cand   (each part 16-byte aligned)
+    size_t o_site0 = 0, o_site1 = round_up(o_site0 + l0, 16), o_a0 = round_up(o_site1 + l1, 16),
+           o_a1 = round_up(o_a0 + la0, 16), o_a1off = round_up(o_a1 + a1_off[nbar], 16),
+           o_coff = round_up(o_a1off + (nbar + 1) * sizeof(uint32_t), 16),
+           o_cand = round_up(o_coff + (nbar + 1) * sizeof(uint32_t), 16),
+           total = round_up(o_cand + ncand * sizeof(tdg::TrimCand), 16) + 16;
+    std::vector<uint8_t> blob(total, 0);
+    memcpy(blob.data() + o_site0, site0, l0);
+    memcpy(blob.data() + o_site1, site1, l1);
+    memcpy(blob.data() + o_a0, a0, la0);
+    if (a1_off[nbar]) memcpy(blob.data() + o_a1, a1, a1_off[nbar]);
+    memcpy(blob.data() + o_a1off, a1_off, (nbar + 1) * sizeof(uint32_t));
+    memcpy(blob.data() + o_coff, cand_off, (nbar + 1) * sizeof(uint32_t));
+    if (ncand) memcpy(blob.data() + o_cand, cand.data(), ncand * sizeof(tdg::TrimCand));
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (total > ctx->d_trim_cap) {
+        if (ctx->d_trim) CK(cudaFree(ctx->d_trim));
+        ctx->d_trim = nullptr;
+        CK(cudaMalloc(&ctx->d_trim, total));
+        ctx->d_trim_cap = total;
+    }
+    CK(cudaMemcpy(ctx->d_trim, blob.data(), total, cudaMemcpyHostToDevice));
+    tdg::TrimArgs &t = ctx->trim;
+    memset(&t, 0, sizeof(t));
+    t.site0 = ctx->d_trim + o_site0;
+    t.site1 = ctx->d_trim + o_site1;
+    t.len0 = (uint32_t)l0;
+    t.len1 = (uint32_t)l1;
+    t.a0 = ctx->d_trim + o_a0;
+    t.a1 = ctx->d_trim + o_a1;
+    t.a1_off = (const uint32_t *)(ctx->d_trim + o_a1off);
+    t.cand_off = (const uint32_t *)(ctx->d_trim + o_coff);
+    t.cand = (const tdg::TrimCand *)(ctx->d_trim + o_cand);
+    ctx->trim_nbar = nbar;
+    ctx->have_trim = true;
+    return TDG_OK;
+}
+
+int tdg_trim_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, const int32_t *bar, const uint32_t *start,
+                   uint32_t n, int32_t *slice2)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!ctx->have_trim) return fail(ctx, TDG_ERR_STATE, "tdg_set_trim has not been called");
+    if (n == 0) return TDG_OK;
+    if (!off || !bar || !start || !slice2 || (!seqs && off[n] != off[0])) return fail(ctx, TDG_ERR_ARG, "null argument");
+    for (uint32_t i = 0; i < n; i++) {
+        if (bar[i] < 0 || (uint32_t)bar[i] >= ctx->trim_nbar) return fail(ctx, TDG_ERR_ARG, "barcode index out of range");
+        if (off[i + 1] < off[i]) return fail(ctx, TDG_ERR_ARG, "offsets must be non-decreasing");
+    }
+    CK(cudaSetDevice(ctx->device));
+    const size_t nbytes = (size_t)(off[n] - off[0]);
+    const size_t o_off = round_up(nbytes + 16, 16), o_bar = o_off + round_up((n + 1) * sizeof(uint64_t), 16),
+                 o_start = o_bar + round_up(n * sizeof(int32_t), 16), o_out = o_start + round_up(n * sizeof(uint32_t), 16),
+                 total = o_out + round_up(n * sizeof(int32_t), 16);
+    uint8_t *d = nullptr;
+    CK(cudaMalloc(&d, total));
+    std::vector<unsigned long long> rel(n + 1);
+    for (uint32_t i = 0; i <= n; i++) rel[i] = off[i] - off[0];
+    cudaError_t e = cudaSuccess;
+    if (nbytes) e = cudaMemcpyAsync(d, seqs + off[0], nbytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_off, rel.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_bar, bar, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_start, start, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        tdg::TrimArgs t = ctx->trim;
+        t.seqs = d;
+        t.off = (const unsigned long long *)(d + o_off);
+        t.bar = (const int32_t *)(d + o_bar);
+        t.start = (const uint32_t *)(d + o_start);
+        t.n = n;
+        t.out = (int32_t *)(d + o_out);
+        const unsigned per = tdg::TRIM_THREADS / 32;
+        tdg::trim_kernel<<<(n + per - 1) / per, tdg::TRIM_THREADS, 0, ctx->stream>>>(t);
+        e = cudaGetLastError();
+        ctx->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(slice2, d + o_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, TDG_ERR_CUDA, std::string("tdg_trim_batch: ") + cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail(ctx, TDG_ERR_CUDA, std::string("tdg_trim_batch: ") + cudaGetErrorString(e2));
+    return TDG_OK;
 }
 
 }  // extern "C"
