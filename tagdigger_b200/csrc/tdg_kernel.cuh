@@ -463,15 +463,28 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                ((k.z ^ T2) & lowmask32(L > 32 ? L - 32 : 0)) | ((k.w ^ T3) & lowmask32(L > 48 ? L - 48 : 0));
     };
 
-    // Match up to 32 queued line starts, one per lane.
-    auto run_batch = [&](uint32_t nb) {
+    // ---- matching, software-pipelined ------------------------------------------------
+    // batch_front takes up to 32 queued line starts, one per lane: pack, barcode
+    // lookup, tag key, hash -- and ISSUES the loads of the first two table slots.
+    // batch_back, called just before the next front (i.e. after the next tile's
+    // scan), compares, finishes rare longer probe sequences and counts.  The L2
+    // round trip of the probe is hidden behind the scan instead of stalling the warp.
+    bool pb_pending = false;              // uniform: a batch is between front and back
+    int32_t pb_row = -1, pb_col = -1;     // per lane
+    bool pb_probe = false;                // per lane: slots loaded, compare still to do
+    uint32_t pb_T0 = 0, pb_T1 = 0, pb_T2 = 0, pb_T3 = 0, pb_h = 0, pb_V = 0xFFFFFFFFu, pb_end = 0;
+    uint4 pb_k0 = make_uint4(0, 0, 0, 0), pb_m0 = pb_k0, pb_k1 = pb_k0, pb_m1 = pb_k0;
+
+    auto batch_front = [&](uint32_t nb) {
         uint32_t off = 0;
         const bool have = lane < nb;
         if (have) off = ws->q[(q_head + lane) & (QCAP - 1)];
         q_head += nb;
         q_len -= nb;
         q_old = q_old > nb ? q_old - nb : 0;
-        int32_t row = -1, col = -1;
+        pb_row = -1;
+        pb_col = -1;
+        pb_probe = false;
         if (have) {
             const uint8_t *lp = wbase + off;          // the line start inside the ring
             const uint32_t c0 = lp[0];
@@ -503,6 +516,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 // ---- barcode + cut site: first 16 bases, bucket = first 4
                 const uint32_t key0 = __funnelshift_r(P[0], P[1], 2u * sh);
                 uint32_t tag_off = 0, blen = 0;
+                int32_t row = -1;
                 {
                     uint32_t b = key0 & 0xFFu;
                     uint32_t lo = bar->bucket[b], hi = bar->bucket[b + 1];
@@ -517,49 +531,46 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                         }
                     }
                 }
-                uint32_t tlen = 0;
                 if (row >= 0) {
-                    // ---- 128-bit tag key at tag_off, one probe sequence
-                    const uint32_t toff = sh + tag_off;
-                    const uint32_t bit = (toff & 15u) * 2u;
-                    const bool up = (toff >> 4) != 0;          // toff <= 31
-                    const uint32_t Q0 = up ? P[1] : P[0], Q1 = up ? P[2] : P[1], Q2 = up ? P[3] : P[2],
-                                   Q3 = up ? P[4] : P[3], Q4 = up ? P[5] : P[4];
-                    const uint32_t T0 = __funnelshift_r(Q0, Q1, bit), T1 = __funnelshift_r(Q1, Q2, bit),
-                                   T2 = __funnelshift_r(Q2, Q3, bit), T3 = __funnelshift_r(Q3, Q4, bit);
-                    const uint64_t pre = (((uint64_t)T1 << 32) | T0) & tag_km;
-                    uint32_t h = tag_hash(pre) & tag_mask;
-                    for (;;) {
-                        // two neighbouring slots per round trip
-                        const uint32_t h1 = (h + 1) & tag_mask;
-                        const uint4 *e0 = tag_entries + 2 * (size_t)(tag_base + h);
-                        const uint4 *e1 = tag_entries + 2 * (size_t)(tag_base + h1);
-                        const uint4 k0 = __ldg(e0), m0 = __ldg(e0 + 1);
-                        const uint4 k1 = __ldg(e1), m1 = __ldg(e1 + 1);
-                        if (m0.x == TDG_EMPTY_LEN) break;
-                        if (tag_differs(k0, m0.x, T0, T1, T2, T3) == 0) { col = (int32_t)m0.y; tlen = m0.x; break; }
-                        if (m1.x == TDG_EMPTY_LEN) break;
-                        if (tag_differs(k1, m1.x, T0, T1, T2, T3) == 0) { col = (int32_t)m1.y; tlen = m1.x; break; }
-                        h = (h1 + 1) & tag_mask;
-                    }
-                }
-                if (row >= 0 && gbm != 0) {
-                    // some character is not a base: the matches stand only if they end before it
-                    const uint32_t g0 = __ffs(gbm) - 1u;
+                    // some character is not a base: matches stand only if they end before it
                     uint32_t V = 0xFFFFFFFFu;                  // valid bases from the line start
+                    if (gbm != 0) {
+                        const uint32_t g0 = __ffs(gbm) - 1u;
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; k++) {
-                        const uint32_t i = 4 * g0 + k;
-                        uint32_t bad;
-                        (void)pack_word(wp[i], bad);
-                        if (i == 0) bad &= 0xFFFFFFFFu << (8u * sh);
-                        if (V == 0xFFFFFFFFu && bad != 0 && i < nw) {
-                            const uint32_t kk = (bad & 0xFFu) ? 0u : (bad & 0xFF00u) ? 1u : (bad & 0xFF0000u) ? 2u : 3u;
-                            V = 4u * i + kk - sh;
+                        for (uint32_t k = 0; k < 4; k++) {
+                            const uint32_t i = 4 * g0 + k;
+                            uint32_t bad;
+                            (void)pack_word(wp[i], bad);
+                            if (i == 0) bad &= 0xFFFFFFFFu << (8u * sh);
+                            if (V == 0xFFFFFFFFu && bad != 0 && i < nw) {
+                                const uint32_t kk = (bad & 0xFFu) ? 0u : (bad & 0xFF00u) ? 1u : (bad & 0xFF0000u) ? 2u : 3u;
+                                V = 4u * i + kk - sh;
+                            }
                         }
                     }
-                    if (blen > V) { row = -1; col = -1; }
-                    else if (col >= 0 && tag_off + tlen > V) col = -1;
+                    if (blen <= V) {
+                        // ---- 128-bit tag key at tag_off; fetch the first two slots of its probe sequence
+                        const uint32_t toff = sh + tag_off;
+                        const uint32_t bit = (toff & 15u) * 2u;
+                        const bool up = (toff >> 4) != 0;          // toff <= 31
+                        const uint32_t Q0 = up ? P[1] : P[0], Q1 = up ? P[2] : P[1], Q2 = up ? P[3] : P[2],
+                                       Q3 = up ? P[4] : P[3], Q4 = up ? P[5] : P[4];
+                        pb_T0 = __funnelshift_r(Q0, Q1, bit);
+                        pb_T1 = __funnelshift_r(Q1, Q2, bit);
+                        pb_T2 = __funnelshift_r(Q2, Q3, bit);
+                        pb_T3 = __funnelshift_r(Q3, Q4, bit);
+                        const uint64_t pre = (((uint64_t)pb_T1 << 32) | pb_T0) & tag_km;
+                        pb_h = tag_slot(pre, tag_mask);            // even: both slots share a 64-byte line
+                        const uint4 *e0 = tag_entries + 2 * (size_t)(tag_base + pb_h);
+                        pb_k0 = __ldg(e0);
+                        pb_m0 = __ldg(e0 + 1);
+                        pb_k1 = __ldg(e0 + 2);
+                        pb_m1 = __ldg(e0 + 3);
+                        pb_row = row;
+                        pb_V = V;
+                        pb_end = tag_off;
+                        pb_probe = true;
+                    }
                 }
             } else {
                 const uint32_t se = off >= 2 * STAGE ? 2u : (off >= STAGE ? 1u : 0u);
@@ -569,20 +580,44 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 const unsigned long long avail = a.n - tile_off;
                 const uint32_t staged = avail < copy_bytes ? (uint32_t)avail : copy_bytes;
                 MatchResult mr = match_general(wbase + se * STAGE, p, staged, a.bytes + tile_off, avail, need, bar, bent, &a.tags);
-                row = mr.row;
-                col = mr.col;
+                pb_row = mr.row;
+                pb_col = mr.col;
             }
         }
+        pb_pending = true;
+    };
+
+    auto batch_back = [&]() {
+        if (pb_probe) {
+            uint32_t tlen = 0;
+            uint32_t h = pb_h;
+            uint4 k0 = pb_k0, m0 = pb_m0, k1 = pb_k1, m1 = pb_m1;
+            for (;;) {
+                if (m0.x == TDG_EMPTY_LEN) break;
+                if (tag_differs(k0, m0.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { pb_col = (int32_t)m0.y; tlen = m0.x; break; }
+                if (m1.x == TDG_EMPTY_LEN) break;
+                if (tag_differs(k1, m1.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { pb_col = (int32_t)m1.y; tlen = m1.x; break; }
+                // rare: the sequence goes on; slots come in even-aligned pairs
+                h = (h + 2) & tag_mask;
+                const uint4 *e0 = tag_entries + 2 * (size_t)(tag_base + h);
+                k0 = __ldg(e0);
+                m0 = __ldg(e0 + 1);
+                k1 = __ldg(e0 + 2);
+                m1 = __ldg(e0 + 3);
+            }
+            if (pb_col >= 0 && pb_end + tlen > pb_V) pb_col = -1;     // the tag runs into a non-base
+        }
         __syncwarp();
-        if (row >= 0) my_bar += weight;
+        if (pb_row >= 0) my_bar += weight;
         // warp-aggregated count update: one red per distinct cell
         uint32_t cell = NONE;
-        if (col >= 0) {
+        if (pb_col >= 0) {
             my_tag += weight;
-            cell = (uint32_t)row * a.cols + (uint32_t)col;
+            cell = (uint32_t)pb_row * a.cols + (uint32_t)pb_col;
         }
         const uint32_t peers = __match_any_sync(FULL, cell);
         if (cell != NONE && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&a.matrix[cell], weight * (int32_t)__popc(peers));
+        pb_pending = false;
     };
 
     uint32_t s = 0, parity = 0;
@@ -820,11 +855,15 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 // before that stage is refilled, a segment's entries before its state
                 // (weight, limit) changes.
                 for (;;) {
-                    uint32_t nb;
+                    const bool last_round = w0 >= nlive;
+                    uint32_t nb = 0;
                     if (q_len >= 32) nb = 32;
-                    else if (w0 >= nlive && q_len > 0 && (seg_end || q_old > 0)) nb = q_len;
-                    else break;
-                    run_batch(nb);
+                    else if (last_round && (seg_end || q_old > 0)) nb = q_len;
+                    // finish the batch in flight right before the next one starts (as late as
+                    // possible), and before a segment's state changes
+                    if (pb_pending && (nb > 0 || (last_round && seg_end))) batch_back();
+                    if (nb == 0) break;
+                    batch_front(nb);
                 }
                 if (w0 >= nlive) break;
             }

@@ -81,6 +81,12 @@ TDG_HD uint32_t tag_hash(uint64_t prefix)
     uint64_t x = prefix * 0x9E3779B97F4A7C15ull;
     return (uint32_t)(x >> 32) ^ (uint32_t)x;
 }
+// First slot of a probe sequence: always even, so that one 64-byte line holds the
+// first two slots of every sequence (the kernel fetches both in one round trip).
+TDG_HD uint32_t tag_slot(uint64_t prefix, uint32_t mask)
+{
+    return tag_hash(prefix) & mask & ~1u;
+}
 
 // ---------------------------------------------------------------------------
 // Turning characters into 2-bit codes, 4 at a time.
@@ -179,7 +185,7 @@ TDG_HD MatchResult match_line(const Fetch &f, const BarTable *bar, const BarEntr
         if (V < tc.K) continue;
         uint64_t km = lowmask(tc.K);
         uint64_t pre = t0 & km;
-        uint32_t h = tag_hash(pre) & tc.mask;
+        uint32_t h = tag_slot(pre, tc.mask);
         for (;;) {
             TagEntry te = tt.entries[tc.base + h];
             if (te.len == TDG_EMPTY_LEN) break;

@@ -107,8 +107,13 @@ inline std::string build_tag_table(const char *bases, const uint64_t *off, const
         if (members[c].empty()) continue;
         uint32_t K = 32;
         for (uint32_t i : members[c]) K = std::min<uint32_t>(K, (uint32_t)(off[i + 1] - off[i]));
+        // load <= 1/8 while the table stays small next to the L2 (<= 32 MiB), else <= 1/4,
+        // else <= 1/2: short probe sequences, almost always inside the first 64-byte line
+        size_t n = members[c].size();
+        size_t want = 8 * n * sizeof(TagEntry) <= ((size_t)32 << 20) ? 8 * n
+                    : 4 * n * sizeof(TagEntry) <= ((size_t)64 << 20) ? 4 * n : 2 * n;
         uint32_t slots = 16;
-        while (slots < 4 * members[c].size()) slots <<= 1;   // load <= 1/4: short probe sequences
+        while (slots < want) slots <<= 1;
         TagClass &tc = out.t.cls[out.t.n_classes++];
         tc.K = K;
         tc.base = base;
@@ -137,7 +142,7 @@ inline std::string build_tag_table(const char *bases, const uint64_t *off, const
                 e.ext = (uint32_t)out.ext.size();
                 for (uint32_t p = 64; p < L; p += 32) out.ext.push_back(pack_bases(s, p, std::min<uint32_t>(L - p, 32)));
             }
-            uint32_t h = tag_hash(e.k0 & lowmask(K)) & tc.mask;
+            uint32_t h = tag_slot(e.k0 & lowmask(K), tc.mask);
             while (out.entries[base + h].len != TDG_EMPTY_LEN) h = (h + 1) & tc.mask;
             out.entries[base + h] = e;
         }
