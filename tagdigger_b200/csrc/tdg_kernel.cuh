@@ -594,9 +594,11 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             uint4 k0 = pb_k0, m0 = pb_m0, k1 = pb_k1, m1 = pb_m1;
             for (;;) {
                 if (m0.x == TDG_EMPTY_LEN) break;
-                if (tag_differs(k0, m0.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { pb_col = (int32_t)m0.y; tlen = m0.x; break; }
+                const uint32_t L0 = m0.x & TDG_LEN_MASK;
+                if (tag_differs(k0, L0, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { pb_col = (int32_t)m0.y; tlen = L0; break; }
                 if (m1.x == TDG_EMPTY_LEN) break;
                 if (tag_differs(k1, m1.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { pb_col = (int32_t)m1.y; tlen = m1.x; break; }
+                if (!(m0.x & TDG_LEN_MORE)) break;        // nothing was ever stored past this pair
                 // rare: the sequence goes on; slots come in even-aligned pairs
                 h = (h + 2) & tag_mask;
                 const uint4 *e0 = tag_entries + 2 * (size_t)(tag_base + h);
@@ -859,9 +861,13 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     uint32_t nb = 0;
                     if (q_len >= 32) nb = 32;
                     else if (last_round && (seg_end || q_old > 0)) nb = q_len;
+                    // Leave first when there is nothing to do: the code below consumes the
+                    // probe loads of the batch in flight, and the wait for them must not sit
+                    // on this common exit path.
+                    if (nb == 0 && !(pb_pending && last_round && seg_end)) break;
                     // finish the batch in flight right before the next one starts (as late as
                     // possible), and before a segment's state changes
-                    if (pb_pending && (nb > 0 || (last_round && seg_end))) batch_back();
+                    if (pb_pending) batch_back();
                     if (nb == 0) break;
                     batch_front(nb);
                 }

@@ -55,6 +55,12 @@ struct TagEntry {            // 32 bytes = one L2 sector
     uint32_t pad;
 };
 #define TDG_EMPTY_LEN 0xFFFFFFFFu
+// Flag in TagEntry::len of the FIRST slot of an even-aligned slot pair: some key whose
+// probe sequence passes through this pair was stored beyond it, so a lookup that found
+// both slots occupied without a match must go on.  Clear (the common case: a marker's
+// two alleles fill their pair exactly) ends the lookup after one 64-byte line.
+#define TDG_LEN_MORE  0x80000000u
+#define TDG_LEN_MASK  0x7FFFFFFFu
 #define TDG_MAX_CLASSES 4
 
 struct TagClass {
@@ -190,7 +196,7 @@ TDG_HD MatchResult match_line(const Fetch &f, const BarTable *bar, const BarEntr
             TagEntry te = tt.entries[tc.base + h];
             if (te.len == TDG_EMPTY_LEN) break;
             if ((te.k0 & km) == pre) {
-                uint32_t L = te.len;
+                uint32_t L = te.len & TDG_LEN_MASK;
                 uint32_t L64 = L < 64 ? L : 64;
                 bool ok = L64 <= V;
                 if (ok) {

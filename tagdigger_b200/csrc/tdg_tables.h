@@ -138,13 +138,17 @@ inline std::string build_tag_table(const char *bases, const uint64_t *off, const
             e.col = col[i];
             e.ext = 0;
             e.pad = 0;
+            if (L > TDG_LEN_MASK) return "tag " + std::to_string(i) + " is too long";
             if (L > 64) {
                 e.ext = (uint32_t)out.ext.size();
                 for (uint32_t p = 64; p < L; p += 32) out.ext.push_back(pack_bases(s, p, std::min<uint32_t>(L - p, 32)));
             }
-            uint32_t h = tag_slot(e.k0 & lowmask(K), tc.mask);
+            const uint32_t home = tag_slot(e.k0 & lowmask(K), tc.mask);
+            uint32_t h = home;
             while (out.entries[base + h].len != TDG_EMPTY_LEN) h = (h + 1) & tc.mask;
             out.entries[base + h] = e;
+            // every slot pair the sequence crossed before it found room must tell lookups to go on
+            for (uint32_t p2 = home; p2 != (h & ~1u); p2 = (p2 + 2) & tc.mask) out.entries[base + p2].len |= TDG_LEN_MORE;
         }
         base += slots;
     }
