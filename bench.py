@@ -366,15 +366,15 @@ def e2e_leg(args, eng, gen, dev, nbytes, nreads, first, matrix, world, local, di
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    nr = torch.tensor([want], dtype=torch.int64, device="cuda")
+    nr = torch.tensor([want, size, out.nbytes], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(nr)
+        dist.all_reduce(nr)                      # whole-job totals over all ranks
     dt = float(t.item())
-    total_reads = int(nr.item())
+    total_reads, total_h2d, total_d2h = (int(x) for x in nr.tolist())
     eng.host_free(host)
     return {"value": round(total_reads * steps / dt, 1), "unit": "reads/s",
-            "h2d_bytes_per_step": int(size), "d2h_bytes_per_step": int(out.nbytes),
+            "h2d_bytes_per_step": total_h2d, "d2h_bytes_per_step": total_d2h,
             "steps": steps, "reads_per_step": total_reads, "ms_per_step": round(dt / steps * 1e3, 3),
             "timing": "host wall clock between device synchronisations, max over ranks",
             "path": "tdg_submit from pinned host memory in 64 MiB pieces (H2D overlapped with kernels) + tdg_read_matrix"}
