@@ -63,6 +63,10 @@ struct tdg_ctx {
     bool own_matrix = false;
     uint32_t rows = 0, cols = 0;
     uint32_t max_row = 0, max_col = 0;   // largest indices the loaded tables refer to
+    // extra zero-initialised copies of a small matrix (see ChunkArgs::replicas); always all-zero between launches
+    int32_t *d_replicas = nullptr;
+    uint32_t n_replicas = 1;
+    size_t replicas_cap = 0;             // int32 elements allocated
 
     // per-launch scratch (ScratchHeader, SegInfo[], FixEntry[])
     unsigned long long *d_sync = nullptr;
@@ -227,6 +231,9 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
         a.tags.entries = ctx->d_entries;
         a.tags.ext = ctx->d_ext;
         a.matrix = ctx->d_matrix;
+        a.replicas = ctx->d_replicas;
+        a.n_replicas = ctx->n_replicas;
+        a.cells = ctx->rows * ctx->cols;
         a.totals = ctx->d_totals;
     }
     v.num_segs = (uint32_t)segs;
@@ -253,8 +260,40 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
         kern<<<(unsigned)fgrid, THREADS, smem, ctx->stream>>>(a);
         CK(cudaGetLastError());
         ctx->launches += 1;
+        if (ctx->n_replicas > 1) {
+            unsigned fold_grid = (unsigned)std::min<size_t>(((size_t)a.cells + 255) / 256, (size_t)ctx->sm_count * 8);
+            fold_kernel<<<fold_grid, 256, 0, ctx->stream>>>(ctx->d_matrix, ctx->d_replicas, a.cells, ctx->n_replicas - 1);
+            CK(cudaGetLastError());
+            ctx->launches += 1;
+        }
     }
     if (timed) CK(cudaEventRecord(ctx->tev[ctx->tev_used++], ctx->stream));
+    return TDG_OK;
+}
+
+// Small matrices get up to 16 copies (<= 4 MiB in total) that the warps update in turn;
+// fold_kernel adds them up after every launch.  With few rows (pre-split files: ONE row)
+// the most frequent tags would otherwise serialise all SMs on a handful of L2 addresses.
+int size_replicas(tdg_ctx *ctx)
+{
+    size_t cells = (size_t)ctx->rows * ctx->cols;
+    size_t bytes = cells * sizeof(int32_t);
+    uint32_t want = 1;
+    if (bytes && bytes <= ((size_t)2 << 20)) want = (uint32_t)std::min<size_t>(16, ((size_t)4 << 20) / bytes);
+    if (const char *e = getenv("TDG_REPLICAS")) want = (uint32_t)std::max(1, atoi(e));
+    ctx->n_replicas = 1;
+    if (want > 1) {
+        size_t need = (size_t)(want - 1) * cells;
+        if (need > ctx->replicas_cap) {
+            if (ctx->d_replicas) CK(cudaFree(ctx->d_replicas));
+            ctx->d_replicas = nullptr;
+            ctx->replicas_cap = 0;
+            CK(cudaMalloc(&ctx->d_replicas, need * sizeof(int32_t)));
+            ctx->replicas_cap = need;
+        }
+        CK(cudaMemsetAsync(ctx->d_replicas, 0, need * sizeof(int32_t), ctx->stream));
+        ctx->n_replicas = want;
+    }
     return TDG_OK;
 }
 
@@ -490,6 +529,7 @@ void tdg_destroy(tdg_ctx *ctx)
         if (ctx->d_state) cudaFree(ctx->d_state);
         if (ctx->d_totals) cudaFree(ctx->d_totals);
         if (ctx->d_trim) cudaFree(ctx->d_trim);
+        if (ctx->d_replicas) cudaFree(ctx->d_replicas);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     }
@@ -534,6 +574,7 @@ int tdg_set_tags(tdg_ctx *ctx, const char *bases, const uint64_t *off, const int
 int tdg_set_matrix(tdg_ctx *ctx, uint32_t rows, uint32_t cols)
 {
     if (!ctx || rows == 0 || cols == 0) return fail(ctx, TDG_ERR_ARG, "matrix must have at least one row and column");
+    if ((uint64_t)rows * cols >= 0xFFFFFFFFull) return fail(ctx, TDG_ERR_ARG, "matrix must have fewer than 2^32 - 1 cells");
     if (ctx->hostonly) {
         ctx->rows = rows;
         ctx->cols = cols;
@@ -547,6 +588,8 @@ int tdg_set_matrix(tdg_ctx *ctx, uint32_t rows, uint32_t cols)
     ctx->own_matrix = true;
     ctx->rows = rows;
     ctx->cols = cols;
+    int rc = size_replicas(ctx);
+    if (rc) return rc;
     return tdg_zero_matrix(ctx);
 }
 
@@ -555,6 +598,7 @@ int tdg_bind_matrix(tdg_ctx *ctx, void *dev_int32, uint32_t rows, uint32_t cols)
     int rc = need_device(ctx);
     if (rc) return rc;
     if (!dev_int32 || rows == 0 || cols == 0) return fail(ctx, TDG_ERR_ARG, "bad matrix");
+    if ((uint64_t)rows * cols >= 0xFFFFFFFFull) return fail(ctx, TDG_ERR_ARG, "matrix must have fewer than 2^32 - 1 cells");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_matrix && ctx->d_matrix) CK(cudaFree(ctx->d_matrix));
@@ -562,7 +606,7 @@ int tdg_bind_matrix(tdg_ctx *ctx, void *dev_int32, uint32_t rows, uint32_t cols)
     ctx->own_matrix = false;
     ctx->rows = rows;
     ctx->cols = cols;
-    return TDG_OK;
+    return size_replicas(ctx);
 }
 
 int tdg_zero_matrix(tdg_ctx *ctx)

@@ -57,7 +57,7 @@ namespace tdg {
 #define TDG_CHUNKS 11
 #endif
 #ifndef TDG_HALO
-#define TDG_HALO 256
+#define TDG_HALO 128
 #endif
 
 constexpr int      WARPS = TDG_WARPS;              // independent pipelines per CTA (one CTA per SM)
@@ -72,7 +72,7 @@ constexpr int      STAGES = 3;
 constexpr uint32_t RING = STAGES * STAGE;          // bytes of shared memory per warp
 constexpr uint32_t QCAP = 128;                     // queue slots (power of two)
 constexpr uint32_t PUSH_CAP = QCAP - 32;           // starts pushed per emission round
-constexpr uint32_t BAR_SMEM_MAX = 6144;            // barcode tables up to this size are copied to smem
+constexpr uint32_t BAR_SMEM_MAX = 10240;           // barcode tables up to this size (384-plex: 7.2 KB) are copied to smem
 constexpr uint32_t GUESS_LINES = 16;               // lines inspected for the FASTQ structure guess
 constexpr uint32_t FAST_WORDS_MAX = 24;            // 4-character words the fast matcher packs per read
 static_assert(CHUNKS % 2 == 1, "an odd chunk count keeps the 128-bit scan loads free of bank conflicts");
@@ -123,6 +123,9 @@ struct ChunkArgs {
     uint32_t fast_words;            // > 0: tables fit the fast matcher, which packs this many words
     TagTable tags;
     int32_t *matrix;
+    int32_t *replicas;              // [n_replicas - 1][cells] extra copies of a SMALL matrix (or null)
+    uint32_t n_replicas;            // warps spread their updates over the copies: hot cells stop serialising in L2
+    uint32_t cells;
     unsigned long long *totals;     // [3]: reads, barcode+cutsite hits, tag hits
 };
 
@@ -439,6 +442,12 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             UM3 = lowmask32(ulen > 48 ? ulen - 48 : 0);
         }
     }
+    // the copy of the count matrix this warp updates (copy 0 is the matrix itself)
+    int32_t *my_matrix = a.matrix;
+    if (MATCH && a.n_replicas > 1) {
+        const uint32_t rep = (blockIdx.x * WARPS + warp) % a.n_replicas;
+        if (rep) my_matrix = a.replicas + (size_t)(rep - 1) * a.cells;
+    }
     const uint64_t tag_km = lowmask(tagK);
     const uint4 *tag_entries = (const uint4 *)a.tags.entries;
     long long my_reads = 0;
@@ -618,7 +627,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             cell = (uint32_t)pb_row * a.cols + (uint32_t)pb_col;
         }
         const uint32_t peers = __match_any_sync(FULL, cell);
-        if (cell != NONE && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&a.matrix[cell], weight * (int32_t)__popc(peers));
+        if (cell != NONE && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&my_matrix[cell], weight * (int32_t)__popc(peers));
         pb_pending = false;
     };
 
@@ -913,6 +922,19 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             if (my_bar) atomicAdd(&a.totals[1], (unsigned long long)(long long)my_bar);
             if (my_tag) atomicAdd(&a.totals[2], (unsigned long long)(long long)my_tag);
         }
+    }
+}
+
+// Adds the extra copies of a small count matrix into the matrix and clears them.
+__global__ void __launch_bounds__(256) fold_kernel(int32_t *matrix, int32_t *replicas, uint32_t cells, uint32_t extra)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) {
+        int32_t sum = 0;
+        for (uint32_t r = 0; r < extra; r++) {
+            int32_t v = replicas[(size_t)r * cells + i];
+            if (v) { sum += v; replicas[(size_t)r * cells + i] = 0; }
+        }
+        if (sum) matrix[i] += sum;
     }
 }
 
