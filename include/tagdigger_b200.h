@@ -195,16 +195,6 @@ int         tdg_set_trim(tdg_ctx *ctx, const char *site0, const char *site1, con
 int         tdg_trim_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, const int32_t *bar,
                            const uint32_t *start, uint32_t n, int32_t *slice2);
 
-/* Host-side self test of the packed tables: looks one read (a sequence line as
- * found in the file, without its line end) up in the tables exactly as the
- * kernel does (same inline code compiled for the host).  Returns the matrix
- * cell (row*cols+col), -1 for barcode but no tag, -2 for no barcode.  For unit
- * tests of the table builders without a GPU; never used for counting. */
-int64_t     tdg_selftest_match(tdg_ctx *ctx, const char *read, size_t len);
-/* A context without a device, only usable with tdg_set_tags / tdg_begin_file /
- * tdg_set_matrix (host tables only) / tdg_selftest_match. */
-int         tdg_create_hostonly(tdg_ctx **out);
-
 #ifdef __cplusplus
 }
 #endif

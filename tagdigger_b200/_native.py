@@ -35,7 +35,7 @@ tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end
 tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
-tdg_timing_begin tdg_timing_end tdg_selftest_match tdg_create_hostonly tdg_set_trim tdg_trim_batch""".split()
+tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch""".split()
 
 
 class TdgError(RuntimeError):
@@ -89,7 +89,6 @@ def lib():
     sig = {
         "tdg_abi_version": (i32, []),
         "tdg_create": (i32, [ctypes.POINTER(vp), i32, sz]),
-        "tdg_create_hostonly": (i32, [ctypes.POINTER(vp)]),
         "tdg_destroy": (None, [vp]),
         "tdg_last_error": (ctypes.c_char_p, [vp]),
         "tdg_set_tags": (i32, [vp, vp, vp, vp, u32, u32]),
@@ -119,7 +118,6 @@ def lib():
         "tdg_launch_count": (u64, [vp]),
         "tdg_timing_begin": (i32, [vp]),
         "tdg_timing_end": (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u32)]),
-        "tdg_selftest_match": (ctypes.c_int64, [vp, ctypes.c_char_p, sz]),
         "tdg_set_trim": (i32, [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, u32, vp, vp, vp, vp, vp, vp]),
         "tdg_trim_batch": (i32, [vp, vp, vp, vp, vp, u32, vp]),
     }
@@ -159,14 +157,10 @@ def limit_from_maxreads(maxreads):
 class Engine(object):
     """One context = one CUDA device (include/tagdigger_b200.h)."""
 
-    def __init__(self, device=0, chunk_bytes=0, hostonly=False):
+    def __init__(self, device=0, chunk_bytes=0):
         self._L = lib()
         self._h = ctypes.c_void_p()
-        self.hostonly = hostonly
-        if hostonly:
-            rc = self._L.tdg_create_hostonly(ctypes.byref(self._h))
-        else:
-            rc = self._L.tdg_create(ctypes.byref(self._h), device, chunk_bytes)
+        rc = self._L.tdg_create(ctypes.byref(self._h), device, chunk_bytes)
         if rc != TDG_OK:
             msg = self._L.tdg_last_error(None).decode()
             self._h = ctypes.c_void_p()
@@ -355,8 +349,3 @@ class Engine(object):
         self._ck(self._L.tdg_trim_batch(self._h, blob, off.ctypes.data, bar.ctypes.data, start.ctypes.data,
                                         len(raw), out.ctypes.data))
         return [int(x) for x in out]
-
-    def selftest_match(self, read):
-        if isinstance(read, str):
-            read = read.encode("utf-8")
-        return int(self._L.tdg_selftest_match(self._h, read, len(read)))

@@ -38,7 +38,6 @@ struct Slot {
 }  // namespace
 
 struct tdg_ctx {
-    bool hostonly = false;
     int device = 0;
     int sm_count = 0;
     std::string err;
@@ -300,7 +299,6 @@ int size_replicas(tdg_ctx *ctx)
 int need_device(tdg_ctx *ctx)
 {
     if (!ctx) return TDG_ERR_ARG;
-    if (ctx->hostonly) return fail(ctx, TDG_ERR_STATE, "host-only context: no CUDA device behind it");
     return TDG_OK;
 }
 
@@ -456,16 +454,6 @@ int tdg_abi_version(void) { return TDG_ABI_VERSION; }
 
 const char *tdg_last_error(const tdg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-int tdg_create_hostonly(tdg_ctx **out)
-{
-    if (!out) return TDG_ERR_ARG;
-    tdg_ctx *ctx = new (std::nothrow) tdg_ctx();
-    if (!ctx) return fail(nullptr, TDG_ERR_NOMEM, "out of memory");
-    ctx->hostonly = true;
-    *out = ctx;
-    return TDG_OK;
-}
-
 int tdg_create(tdg_ctx **out, int device, size_t chunk_bytes)
 {
     if (!out) return TDG_ERR_ARG;
@@ -510,7 +498,7 @@ int tdg_create(tdg_ctx **out, int device, size_t chunk_bytes)
 void tdg_destroy(tdg_ctx *ctx)
 {
     if (!ctx) return;
-    if (!ctx->hostonly) {
+    {
         cudaSetDevice(ctx->device);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -548,7 +536,7 @@ int tdg_set_tags(tdg_ctx *ctx, const char *bases, const uint64_t *off, const int
         if (col[i] < 0) return fail(ctx, TDG_ERR_ARG, "tdg_set_tags: negative column");
         if ((uint32_t)col[i] > ctx->max_col) ctx->max_col = (uint32_t)col[i];
     }
-    if (!ctx->hostonly) {
+    {
         CK(cudaSetDevice(ctx->device));
         CK(cudaStreamSynchronize(ctx->stream));
         size_t ne = ctx->tags.entries.size(), nx = ctx->tags.ext.size();
@@ -575,11 +563,6 @@ int tdg_set_matrix(tdg_ctx *ctx, uint32_t rows, uint32_t cols)
 {
     if (!ctx || rows == 0 || cols == 0) return fail(ctx, TDG_ERR_ARG, "matrix must have at least one row and column");
     if ((uint64_t)rows * cols >= 0xFFFFFFFFull) return fail(ctx, TDG_ERR_ARG, "matrix must have fewer than 2^32 - 1 cells");
-    if (ctx->hostonly) {
-        ctx->rows = rows;
-        ctx->cols = cols;
-        return TDG_OK;
-    }
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_matrix && ctx->d_matrix) CK(cudaFree(ctx->d_matrix));
@@ -632,7 +615,7 @@ int tdg_begin_file(tdg_ctx *ctx, const char *bases, const uint32_t *off, const i
         if (row[i] < 0) return fail(ctx, TDG_ERR_ARG, "tdg_begin_file: negative row");
         if ((uint32_t)row[i] > ctx->max_row) ctx->max_row = (uint32_t)row[i];
     }
-    if (!ctx->hostonly) {
+    {
         CK(cudaSetDevice(ctx->device));
         // the previous file's kernels read the old table
         CK(cudaStreamSynchronize(ctx->stream));
@@ -792,7 +775,7 @@ int tdg_other_stream_wait(tdg_ctx *ctx, void *other_stream)
 
 void *tdg_host_alloc(tdg_ctx *ctx, size_t n)
 {
-    if (!ctx || ctx->hostonly) return nullptr;
+    if (!ctx) return nullptr;
     void *p = nullptr;
     cudaSetDevice(ctx->device);
     if (cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -808,7 +791,7 @@ void tdg_host_free(tdg_ctx *ctx, void *p)
 }
 void *tdg_device_alloc(tdg_ctx *ctx, size_t n)
 {
-    if (!ctx || ctx->hostonly) return nullptr;
+    if (!ctx) return nullptr;
     void *p = nullptr;
     cudaSetDevice(ctx->device);
     if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) {
@@ -875,34 +858,6 @@ int tdg_timing_end(tdg_ctx *ctx, double *kernel_ms, uint32_t *nlaunch)
     if (nlaunch) *nlaunch = (uint32_t)(ctx->tev_used / 2);
     ctx->timing = false;
     return TDG_OK;
-}
-
-int64_t tdg_selftest_match(tdg_ctx *ctx, const char *read, size_t len)
-{
-    if (!ctx || !ctx->have_tags || !ctx->have_bar) return -3;
-    const uint8_t *p = (const uint8_t *)read;
-    size_t pos = 0;
-    while (pos < len) {
-        uint32_t c = p[pos];
-        if (tdg::is_lead_space(c)) { pos++; continue; }
-        if (c >= 0xC2 && c <= 0xE3 && pos + 2 < len) {
-            uint32_t u = tdg::utf8_space(c, p[pos + 1], p[pos + 2]);
-            if (u) { pos += u; continue; }
-        }
-        break;
-    }
-    tdg::HostFetch f;
-    f.p = p + pos;
-    f.limit = (uint32_t)(len - pos);
-    tdg::TagTable tt = ctx->tags.t;
-    tt.entries = ctx->tags.entries.data();
-    tt.ext = ctx->tags.ext.data();
-    const tdg::BarTable *bar = (const tdg::BarTable *)ctx->bar_blob.data();
-    const tdg::BarEntry *bent = (const tdg::BarEntry *)(ctx->bar_blob.data() + sizeof(tdg::BarTable));
-    tdg::MatchResult r = tdg::match_line(f, bar, bent, tt);
-    if (r.row < 0) return -2;
-    if (r.col < 0) return -1;
-    return (int64_t)r.row * ctx->cols + r.col;
 }
 
 // ---------------------------------------------------------------------------

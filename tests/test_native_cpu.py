@@ -1,7 +1,8 @@
 """CPU-side checks of the native library: it builds/loads, exports every symbol
-the header declares, refuses to count without a GPU, and its packed tables +
-per-read match (compiled for the host by tdg_selftest_match) agree with the
-oracle.  No compute call needs a GPU here."""
+the header declares and refuses to count without a GPU; and the product's packed
+tables + per-read match code (csrc/tdg_tables.h, tdg_match.h, compiled for the host
+by the TEST harness tests/native/table_check.cpp) agree with the oracle.  No
+compute call needs a GPU here."""
 
 import os
 import random
@@ -12,6 +13,7 @@ import pytest
 from conftest import REPO, file_bytes, load_golden
 from helpers import rand_seq
 from oracle import tagdigger_oracle as orc
+from table_check import TableError, Tables
 from tagdigger_b200 import _native, counting, matchset
 
 
@@ -37,32 +39,41 @@ def test_no_cpu_fallback():
         counting.find_tags_fastq(__file__, ["AACG"], ["TGCAGCCCC"])
 
 
-def test_hostonly_context_cannot_count():
-    eng = _native.Engine(hostonly=True)
-    eng.set_tags(["ACGT"])
-    eng.set_matrix(1, 1)
-    eng.begin_file(["AC"], [0], [2])
-    with pytest.raises(_native.TdgError):
-        eng.submit(b"@x\nACACGT\n+\nIIIIII\n")
-    with pytest.raises(_native.TdgError):
-        eng.read_matrix()
-
-
 def test_table_builders_refuse_bad_sets():
-    eng = _native.Engine(hostonly=True)
-    with pytest.raises(_native.TdgError):
-        eng.set_tags(["ACGT", "ACGTA"])          # not prefix-free
-    with pytest.raises(_native.TdgError):
-        eng.set_tags(["ACGT", "ACGT"])           # duplicate
-    with pytest.raises(_native.TdgError):
-        eng.set_tags(["ACNT"])
-    with pytest.raises(_native.TdgError):
-        eng.set_tags([])
-    eng.set_tags(["ACGT"])
-    with pytest.raises(_native.TdgError):
-        eng.begin_file(["A" * 33], [0], [33])
-    with pytest.raises(_native.TdgError):
-        eng.begin_file(["AC", "ACG"], [0, 1], [2, 3])
+    t = Tables()
+    with pytest.raises(TableError):
+        t.set_tags(["ACGT", "ACGTA"])          # not prefix-free
+    with pytest.raises(TableError):
+        t.set_tags(["ACGT", "ACGT"])           # duplicate
+    with pytest.raises(TableError):
+        t.set_tags(["ACNT"])
+    with pytest.raises(TableError):
+        t.set_tags([])
+    t.set_tags(["ACGT"])
+    with pytest.raises(TableError):
+        t.set_bars(["A" * 33], [0], [33])
+    with pytest.raises(TableError):
+        t.set_bars(["AC", "ACG"], [0, 1], [2, 3])
+
+
+def test_probe_sequences_end_in_their_first_line():
+    """Biallelic pairs fill their slot pair exactly; only pairs that something was
+    stored beyond carry the 'more' flag, and they are few at the table's load."""
+    r = random.Random(3)
+    tags = []
+    for _ in range(3000):
+        a = "TGCAG" + rand_seq(r, 59)
+        j = r.randrange(40, 64)
+        b = a[:j] + ("A" if a[j] != "A" else "C") + a[j + 1:]
+        tags += [a, b]
+    t = Tables()
+    t.set_tags(tags)
+    st = t.stats()
+    assert st["used"] == len(tags) and st["slots"] >= 8 * len(tags)
+    assert st["more"] < 0.03 * len(tags)
+    for k, s in enumerate(tags[:200]):
+        t.set_bars(["AC"], [0], [2])
+        assert t.match("AC" + s + "GG") == k
 
 
 def _expected(seq, bt, tt, offs, ntags):
@@ -74,11 +85,9 @@ def _expected(seq, bt, tt, offs, ntags):
 
 
 def _host_engine(barcodes, tags, cutsite):
-    p = matchset.plan(barcodes, tags, cutsite)
-    eng = _native.Engine(hostonly=True)
-    eng.set_matrix(p.barnum, p.ntags)
-    counting.load_plan(eng, p)
-    return eng
+    t = Tables()
+    t.load_plan(matchset.plan(barcodes, tags, cutsite))
+    return t
 
 
 FIND = [c for c in load_golden("find_tags.json")
@@ -102,7 +111,7 @@ def test_selftest_match_on_golden_reads(i):
     lines = raw.decode("utf-8").replace("\r\n", "\n").replace("\r", "\n").split("\n")
     for n, line in enumerate(lines):
         if n % 4 == 1:
-            assert eng.selftest_match(line) == _expected(line.strip().upper(), bt, tt, offs, ntags), line
+            assert eng.match(line) == _expected(line.strip().upper(), bt, tt, offs, ntags), line
 
 
 @pytest.mark.parametrize("seed", range(120))
@@ -161,7 +170,7 @@ def test_selftest_match_random_sets(seed):
             rd = rd.lower()
         if r.random() < 0.1:
             rd = r.choice([" ", "\t", "  ", "\x0b\x1c", " ", "  "]) + rd + r.choice(["", " ", "\r"])
-        assert eng.selftest_match(rd) == _expected(rd.strip().upper(), bt, tt, offs, ntags), rd
+        assert eng.match(rd) == _expected(rd.strip().upper(), bt, tt, offs, ntags), rd
 
 
 @pytest.mark.parametrize("seed", range(40))
