@@ -195,6 +195,16 @@ int         tdg_set_trim(tdg_ctx *ctx, const char *site0, const char *site1, con
 int         tdg_trim_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, const int32_t *bar,
                            const uint32_t *start, uint32_t n, int32_t *slice2);
 
+/* The two decisions barcodeSplitter takes per read (tagdigger_fun.py:1333-1343), for n
+ * sequence lines given as HOST buffers (stripped; case is folded on the device):
+ * bar_out[i] = sequence_index_lookup(seq_i, barcuttree) -- the barcode table is the one
+ * loaded by tdg_begin_file with rows = barcode indices -- and, where that is >= 0,
+ * slice2[i] = findAdapterSeq(seq_i, adaptertrees[bar], site0, site1, bar_len[bar] + cutlen)
+ * (tables from tdg_set_trim); 999 elsewhere.  One warp per read; synchronous. */
+int         tdg_split_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, uint32_t n,
+                            const uint32_t *bar_len, uint32_t nbar, uint32_t cutlen,
+                            int32_t *bar_out, int32_t *slice2);
+
 #ifdef __cplusplus
 }
 #endif

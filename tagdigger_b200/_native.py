@@ -35,7 +35,7 @@ tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end
 tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
-tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch""".split()
+tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch""".split()
 
 
 class TdgError(RuntimeError):
@@ -120,6 +120,7 @@ def lib():
         "tdg_timing_end": (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u32)]),
         "tdg_set_trim": (i32, [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, u32, vp, vp, vp, vp, vp, vp]),
         "tdg_trim_batch": (i32, [vp, vp, vp, vp, vp, u32, vp]),
+        "tdg_split_batch": (i32, [vp, vp, vp, u32, vp, u32, u32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -349,3 +350,18 @@ class Engine(object):
         self._ck(self._L.tdg_trim_batch(self._h, blob, off.ctypes.data, bar.ctypes.data, start.ctypes.data,
                                         len(raw), out.ctypes.data))
         return [int(x) for x in out]
+
+    def split_batch(self, seqs, bar_lens, cutlen):
+        """seqs: list of stripped sequence lines (bytes/str).  Returns (barcode index or -1,
+        slice2 or 999) arrays -- the two per-read decisions of barcodeSplitter."""
+        raw = [x.encode("utf-8") if isinstance(x, str) else bytes(x) for x in seqs]
+        blob = b"".join(raw)
+        off = np.zeros(len(raw) + 1, dtype=np.uint64)
+        if raw:
+            np.cumsum([len(x) for x in raw], out=off[1:])
+        blen = np.asarray(list(bar_lens), dtype=np.uint32)
+        bar = np.empty(len(raw), dtype=np.int32)
+        cut = np.empty(len(raw), dtype=np.int32)
+        self._ck(self._L.tdg_split_batch(self._h, blob, off.ctypes.data, len(raw), blen.ctypes.data, len(blen),
+                                         cutlen, bar.ctypes.data, cut.ctypes.data))
+        return bar, cut

@@ -1107,4 +1107,55 @@ int tdg_trim_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, const in
     return TDG_OK;
 }
 
+int tdg_split_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, uint32_t n, const uint32_t *bar_len,
+                    uint32_t nbar, uint32_t cutlen, int32_t *bar_out, int32_t *slice2)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!ctx->have_trim) return fail(ctx, TDG_ERR_STATE, "tdg_set_trim has not been called");
+    if (!ctx->have_bar) return fail(ctx, TDG_ERR_STATE, "tdg_begin_file has not been called");
+    if (nbar != ctx->trim_nbar || ctx->max_row >= nbar)
+        return fail(ctx, TDG_ERR_ARG, "barcode table, trim tables and bar_len disagree on the number of barcodes");
+    if (n == 0) return TDG_OK;
+    if (!off || !bar_len || !bar_out || !slice2 || (!seqs && off[n] != off[0])) return fail(ctx, TDG_ERR_ARG, "null argument");
+    for (uint32_t i = 0; i < n; i++)
+        if (off[i + 1] < off[i]) return fail(ctx, TDG_ERR_ARG, "offsets must be non-decreasing");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nbytes = (size_t)(off[n] - off[0]);
+    const size_t o_off = round_up(nbytes + 16, 16), o_len = o_off + round_up((n + 1) * sizeof(uint64_t), 16),
+                 o_bar = o_len + round_up(nbar * sizeof(uint32_t), 16), o_out = o_bar + round_up(n * sizeof(int32_t), 16),
+                 total = o_out + round_up(n * sizeof(int32_t), 16);
+    uint8_t *d = nullptr;
+    CK(cudaMalloc(&d, total));
+    std::vector<unsigned long long> rel(n + 1);
+    for (uint32_t i = 0; i <= n; i++) rel[i] = off[i] - off[0];
+    cudaError_t e = cudaSuccess;
+    if (nbytes) e = cudaMemcpyAsync(d, seqs + off[0], nbytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_off, rel.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_len, bar_len, nbar * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        tdg::SplitArgs a;
+        a.t = ctx->trim;
+        a.t.seqs = d;
+        a.t.off = (const unsigned long long *)(d + o_off);
+        a.t.n = n;
+        a.t.out = (int32_t *)(d + o_out);
+        a.bar = (const tdg::BarTable *)ctx->d_bar;
+        a.bar_len = (const uint32_t *)(d + o_len);
+        a.cutlen = cutlen;
+        a.bar_out = (int32_t *)(d + o_bar);
+        const unsigned per = tdg::TRIM_THREADS / 32;
+        tdg::split_kernel<<<(n + per - 1) / per, tdg::TRIM_THREADS, 0, ctx->stream>>>(a);
+        e = cudaGetLastError();
+        ctx->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bar_out, d + o_bar, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(slice2, d + o_out, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, TDG_ERR_CUDA, std::string("tdg_split_batch: ") + cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail(ctx, TDG_ERR_CUDA, std::string("tdg_split_batch: ") + cudaGetErrorString(e2));
+    return TDG_OK;
+}
+
 }  // extern "C"

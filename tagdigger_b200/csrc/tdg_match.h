@@ -143,6 +143,33 @@ struct MatchResult {
     int32_t col;     // >= 0 when a tag matched as well
 };
 
+// Barcode + cut site at the start of the line: the row of the unique pattern that
+// prefixes it (-1 if none); tag_off receives where the tag comparison starts.
+template <class Fetch>
+TDG_HD int32_t match_barcode(const Fetch &f, const BarTable *bar, const BarEntry *bent, uint32_t *tag_off_out = nullptr)
+{
+    uint32_t v0;
+    uint64_t key0 = pack32(f, 0, v0);
+    if (bar->any_base) {
+        if (v0 < 1) return -1;
+        if (tag_off_out) *tag_off_out = bar->any_tag_off;
+        return bar->any_row;
+    }
+    // bucket = first four bases; a read with fewer valid bases looks in the
+    // bucket its valid prefix padded with A would fall into (patterns
+    // shorter than four bases are listed in every bucket they can start)
+    uint32_t b = (uint32_t)key0 & 0xFFu & (uint32_t)lowmask(v0 < 4 ? v0 : 4);
+    uint32_t lo = bar->bucket[b], hi = bar->bucket[b + 1];
+    for (uint32_t e = lo; e < hi; e++) {
+        BarEntry be = bent[e];
+        if (be.len <= v0 && ((key0 ^ be.key) & lowmask(be.len)) == 0) {
+            if (tag_off_out) *tag_off_out = be.tag_off;
+            return be.row;
+        }
+    }
+    return -1;
+}
+
 template <class Fetch>
 TDG_HD MatchResult match_line(const Fetch &f, const BarTable *bar, const BarEntry *bent,
                               const TagTable &tt)
@@ -150,30 +177,9 @@ TDG_HD MatchResult match_line(const Fetch &f, const BarTable *bar, const BarEntr
     MatchResult r;
     r.row = -1;
     r.col = -1;
-    uint32_t v0;
-    uint64_t key0 = pack32(f, 0, v0);
-    uint32_t tag_off;
-    if (bar->any_base) {
-        if (v0 < 1) return r;
-        r.row = bar->any_row;
-        tag_off = bar->any_tag_off;
-    } else {
-        // bucket = first four bases; a read with fewer valid bases looks in the
-        // bucket its valid prefix padded with A would fall into (patterns
-        // shorter than four bases are listed in every bucket they can start)
-        uint32_t b = (uint32_t)key0 & 0xFFu & (uint32_t)lowmask(v0 < 4 ? v0 : 4);
-        uint32_t lo = bar->bucket[b], hi = bar->bucket[b + 1];
-        tag_off = 0;
-        for (uint32_t e = lo; e < hi; e++) {
-            BarEntry be = bent[e];
-            if (be.len <= v0 && ((key0 ^ be.key) & lowmask(be.len)) == 0) {
-                r.row = be.row;
-                tag_off = be.tag_off;
-                break;
-            }
-        }
-        if (r.row < 0) return r;
-    }
+    uint32_t tag_off = 0;
+    r.row = match_barcode(f, bar, bent, &tag_off);
+    if (r.row < 0) return r;
     // ---- tag at tag_off ----
     uint32_t tv0;
     uint64_t t0 = pack32(f, tag_off, tv0);

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "tdg_match.h"
 
 namespace tdg {
 
@@ -45,26 +46,41 @@ struct TrimArgs {
 
 #if defined(__CUDACC__)
 
+// 32-character window read byte by byte from global memory (any alignment)
+struct GlobalBytes {
+    const uint8_t *p;
+    uint32_t limit;
+    __device__ __forceinline__ void load8(uint32_t off, uint32_t w[8]) const
+    {
+#pragma unroll 1
+        for (int i = 0; i < 8; i++) {
+            uint32_t v = 0;
+            for (int k = 0; k < 4; k++) {
+                uint32_t o = off + 4 * i + k;
+                uint32_t c = o < limit ? p[o] : 0u;
+                v |= c << (8 * k);
+            }
+            w[i] = v;
+        }
+    }
+};
+
 __device__ __forceinline__ uint32_t fold_upper(uint32_t c)      // str.upper() for ASCII
 {
     return (c >= 'a' && c <= 'z') ? c - 32u : c;
 }
 
-__global__ void __launch_bounds__(TRIM_THREADS) trim_kernel(const TrimArgs t)
+// The decision for one read, computed by a whole warp (all lanes return the result).
+__device__ __forceinline__ int32_t trim_decide(const TrimArgs &t, const uint8_t *s, uint32_t n, uint32_t start, int32_t b,
+                                               uint32_t lane)
 {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t r = blockIdx.x * (TRIM_THREADS / 32) + (threadIdx.x >> 5);
-    if (r >= t.n) return;
-    const uint8_t *s = t.seqs + t.off[r];
-    const uint32_t n = (uint32_t)(t.off[r + 1] - t.off[r]);
-    const uint32_t start = t.start[r];
     int32_t result = TRIM_NONE;
     bool done = false;
 
     // ---- full restriction sites, 32 positions per step --------------------------
     for (uint32_t base = start; base < n && !done; base += 32) {
         const uint32_t p = base + lane;
-        bool m0 = p + t.len0 <= n && t.len0 > 0, m1 = p + t.len1 <= n && t.len1 > 0;
+        bool m0 = p + t.len0 <= n, m1 = p + t.len1 <= n;
         for (uint32_t i = 0; m0 && i < t.len0; i++) m0 = fold_upper(s[p + i]) == t.site0[i];
         for (uint32_t i = 0; m1 && i < t.len1; i++) m1 = fold_upper(s[p + i]) == t.site1[i];
         const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, m0), b1 = __ballot_sync(0xFFFFFFFFu, m1);
@@ -77,7 +93,6 @@ __global__ void __launch_bounds__(TRIM_THREADS) trim_kernel(const TrimArgs t)
     }
     // ---- adapter at the very end of the read -------------------------------------
     if (!done) {
-        const int32_t b = t.bar[r];
         const uint32_t lo = t.cand_off[b], hi = t.cand_off[b + 1];
         const uint8_t *a1 = t.a1 + t.a1_off[b];
         for (uint32_t cbase = lo; cbase < hi && !done; cbase += 32) {
@@ -102,7 +117,54 @@ __global__ void __launch_bounds__(TRIM_THREADS) trim_kernel(const TrimArgs t)
             }
         }
     }
+    return result;
+}
+
+__global__ void __launch_bounds__(TRIM_THREADS) trim_kernel(const TrimArgs t)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t r = blockIdx.x * (TRIM_THREADS / 32) + (threadIdx.x >> 5);
+    if (r >= t.n) return;
+    const uint8_t *s = t.seqs + t.off[r];
+    const uint32_t n = (uint32_t)(t.off[r + 1] - t.off[r]);
+    const int32_t result = trim_decide(t, s, n, t.start[r], t.bar[r], lane);
     if (lane == 0) t.out[r] = result;
+}
+
+// Barcode splitter decisions for one batch of sequence lines: which barcode (the
+// reference's sequence_index_lookup(sequence, barcuttree), tagdigger_fun.py:1333) and,
+// for reads that have one, where to cut (findAdapterSeq with searchstart = barcode
+// length + cut-site length, :1337-1339).  bar_out = -1: no barcode.
+struct SplitArgs {
+    TrimArgs t;                      // t.bar / t.start unused; t.out = slice2
+    const BarTable *bar;             // barcode+cutsite table of the file (rows = barcode indices)
+    const uint32_t *bar_len;         // [nbar] barcode lengths
+    uint32_t cutlen;
+    int32_t *bar_out;                // [n]
+};
+
+__global__ void __launch_bounds__(TRIM_THREADS) split_kernel(const SplitArgs a)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t r = blockIdx.x * (TRIM_THREADS / 32) + (threadIdx.x >> 5);
+    if (r >= a.t.n) return;
+    const uint8_t *s = a.t.seqs + a.t.off[r];
+    const uint32_t n = (uint32_t)(a.t.off[r + 1] - a.t.off[r]);
+    // barcode + cut site at the start of the read: the counting path's lookup, barcode part
+    int32_t b = -1;
+    {
+        GlobalBytes f;
+        f.p = s;
+        f.limit = n;
+        const BarEntry *bent = (const BarEntry *)((const uint8_t *)a.bar + sizeof(BarTable));
+        b = match_barcode(f, a.bar, bent);
+    }
+    int32_t cut = TRIM_NONE;
+    if (b >= 0) cut = trim_decide(a.t, s, n, a.bar_len[b] + a.cutlen, b, lane);
+    if (lane == 0) {
+        a.bar_out[r] = b;
+        a.t.out[r] = cut;
+    }
 }
 
 #endif  // __CUDACC__

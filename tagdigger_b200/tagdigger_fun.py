@@ -3,7 +3,8 @@ as tagdigger_fun`` gives a user of TagDigger's counting workflow the functions t
 today (/root/reference/tagdigger_fun.py), with ``find_tags_fastq`` running on the GPU.
 
 Host-side functions live in :mod:`tagdigger_b200.hostio`, the counting entry points in
-:mod:`tagdigger_b200.counting`, the pattern-set rules in :mod:`tagdigger_b200.matchset`.
+:mod:`tagdigger_b200.counting`, the pattern-set rules in :mod:`tagdigger_b200.matchset`,
+the barcode splitter in :mod:`tagdigger_b200.splitter`.
 """
 
 from .counting import count_files, find_tags_fastq                                   # noqa: F401
@@ -13,3 +14,4 @@ from .hostio import (adapters, combine_barcode_and_cutsite, combineReadCounts, c
                      readTags_Stacks, readTags_TASSELSAM, readTags_UNEAK_FASTA, reverseComplement,
                      sanitizeTags, writeCounts, writeDiploidGeno)
 from .matchset import enumerate_cut_sites                                            # noqa: F401
+from .splitter import barcodeSplitter, writeMD5sums                                  # noqa: F401
