@@ -487,111 +487,130 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     auto batch_front = [&](uint32_t nb) {
         uint32_t off = 0;
         const bool have = lane < nb;
-        if (have) off = ws->q[(q_head + lane) & (QCAP - 1)];
+        if (have) off = ws->q[(q_head + lane) & (QCAP - 1)];      // lanes without a read work on offset 0, results dropped
         q_head += nb;
         q_len -= nb;
         q_old = q_old > nb ? q_old - nb : 0;
         pb_row = -1;
         pb_col = -1;
         pb_probe = false;
-        if (have) {
-            const uint8_t *lp = wbase + off;          // the line start inside the ring
-            const uint32_t c0 = lp[0];
-            // the last tiles of a chunk may hold lines cut by the end of the data
-            bool slow = nw == 0 || cur_tile + 2 >= a.num_tiles || c0 >= 0x80 || is_lead_space(c0);
-            if (!slow) {
-                // ---- fast matcher: pack the first 4*nw characters (from the aligned
-                // word that holds the line start) once, 2 bits per base
-                const uint32_t sh = off & 3u;
-                const uint32_t *wp = (const uint32_t *)(wbase + (off & ~3u));
-                uint32_t P[FAST_WORDS_MAX / 4];
-                uint32_t gbm = 0;         // bit g: words 4g..4g+3 hold a character outside ACGTacgt
+        const uint32_t c0 = wbase[off];
+        // the general matcher takes: table shapes outside the fast envelope, the last tiles of a
+        // chunk (lines may be cut by the end of the data), leading whitespace, non-ASCII
+        // (evaluated without short-circuit branches: the warp must stay converged for the pack)
+        const bool lead = (c0 == 0x09) | (c0 == 0x0b) | (c0 == 0x0c) | ((c0 - 0x1cu) <= 4u) | (c0 >= 0x80);
+        const bool slow = have & ((nw == 0) | (cur_tile + 2 >= a.num_tiles) | lead);
+        __syncwarp();
+        if (nw != 0) {
+            // ---- fast matcher, ALL lanes in lock step (the results of `slow` lanes and of lanes
+            // without a read are discarded): pack the first 4*nw characters, from the aligned
+            // word that holds the line start, once, 2 bits per base
+            const uint32_t sh = off & 3u;
+            const uint32_t *wp = (const uint32_t *)(wbase + (off & ~3u));
+            uint32_t P[FAST_WORDS_MAX / 4];
+            uint32_t gbm = 0;         // bit g: words 4g..4g+3 hold a character outside ACGTacgt
+            auto pack_group = [&](uint32_t g) {
+                uint32_t x[4], gbad = 0;
 #pragma unroll
-                for (uint32_t g = 0; g < FAST_WORDS_MAX / 4; g++) {
-                    P[g] = 0;
-                    if (4 * g < nw) {
-                        uint32_t x[4], gbad = 0;
+                for (uint32_t k = 0; k < 4; k++) {
+                    uint32_t bad;
+                    x[k] = pack_word(wp[4 * g + k], bad);
+                    if (g == 0 && k == 0) bad &= 0xFFFFFFFFu << (8u * sh);   // bytes before the line start
+                    gbad |= bad;      // words past nw may flag too: V below ignores them
+                }
+                if (gbad) gbm |= 1u << g;
+                P[g] = __byte_perm(__byte_perm(x[0], x[1], 0x0073), __byte_perm(x[2], x[3], 0x0073), 0x5410);
+            };
+            // groups 0..3 (64 characters) hold the barcode, the cut site and the first 32 bases
+            // of the tag, which is all the hash needs: the probe loads go out before the rest
 #pragma unroll
-                        for (uint32_t k = 0; k < 4; k++) {
-                            uint32_t bad;
-                            x[k] = pack_word(wp[4 * g + k], bad);
-                            if (g == 0 && k == 0) bad &= 0xFFFFFFFFu << (8u * sh);   // bytes before the line start
-                            gbad |= bad;      // words past nw may flag too: V below ignores them
-                        }
-                        if (gbad) gbm |= 1u << g;
-                        P[g] = __byte_perm(__byte_perm(x[0], x[1], 0x0073), __byte_perm(x[2], x[3], 0x0073), 0x5410);
+            for (uint32_t g = 0; g < FAST_WORDS_MAX / 4; g++) P[g] = 0;
+#pragma unroll
+            for (uint32_t g = 0; g < 4; g++)
+                if (4 * g < nw) pack_group(g);
+            // ---- barcode + cut site: first 16 bases, bucket = first 4
+            const uint32_t key0 = __funnelshift_r(P[0], P[1], 2u * sh);
+            uint32_t tag_off = 0, blen = 0;
+            int32_t row = -1;
+            {
+                uint32_t b = key0 & 0xFFu;
+                uint32_t lo = bar->bucket[b], hi = bar->bucket[b + 1];
+                for (uint32_t e = lo; e < hi; e++) {
+                    uint4 be = *(const uint4 *)(bent + e);       // key lo, key hi, row, len | tag_off << 16
+                    uint32_t len = be.w & 0xFFFFu;
+                    if (((key0 ^ be.x) & lowmask32(len)) == 0) {
+                        row = (int32_t)be.z;
+                        blen = len;
+                        tag_off = be.w >> 16;
+                        break;
                     }
                 }
-                // ---- barcode + cut site: first 16 bases, bucket = first 4
-                const uint32_t key0 = __funnelshift_r(P[0], P[1], 2u * sh);
-                uint32_t tag_off = 0, blen = 0;
-                int32_t row = -1;
-                {
-                    uint32_t b = key0 & 0xFFu;
-                    uint32_t lo = bar->bucket[b], hi = bar->bucket[b + 1];
-                    for (uint32_t e = lo; e < hi; e++) {
-                        uint4 be = *(const uint4 *)(bent + e);       // key lo, key hi, row, len | tag_off << 16
-                        uint32_t len = be.w & 0xFFFFu;
-                        if (((key0 ^ be.x) & lowmask32(len)) == 0) {
-                            row = (int32_t)be.z;
-                            blen = len;
-                            tag_off = be.w >> 16;
-                            break;
-                        }
-                    }
-                }
-                if (row >= 0) {
-                    // some character is not a base: matches stand only if they end before it
-                    uint32_t V = 0xFFFFFFFFu;                  // valid bases from the line start
-                    if (gbm != 0) {
-                        const uint32_t g0 = __ffs(gbm) - 1u;
-#pragma unroll
-                        for (uint32_t k = 0; k < 4; k++) {
-                            const uint32_t i = 4 * g0 + k;
-                            uint32_t bad;
-                            (void)pack_word(wp[i], bad);
-                            if (i == 0) bad &= 0xFFFFFFFFu << (8u * sh);
-                            if (V == 0xFFFFFFFFu && bad != 0 && i < nw) {
-                                const uint32_t kk = (bad & 0xFFu) ? 0u : (bad & 0xFF00u) ? 1u : (bad & 0xFF0000u) ? 2u : 3u;
-                                V = 4u * i + kk - sh;
-                            }
-                        }
-                    }
-                    if (blen <= V) {
-                        // ---- 128-bit tag key at tag_off; fetch the first two slots of its probe sequence
-                        const uint32_t toff = sh + tag_off;
-                        const uint32_t bit = (toff & 15u) * 2u;
-                        const bool up = (toff >> 4) != 0;          // toff <= 31
-                        const uint32_t Q0 = up ? P[1] : P[0], Q1 = up ? P[2] : P[1], Q2 = up ? P[3] : P[2],
-                                       Q3 = up ? P[4] : P[3], Q4 = up ? P[5] : P[4];
-                        pb_T0 = __funnelshift_r(Q0, Q1, bit);
-                        pb_T1 = __funnelshift_r(Q1, Q2, bit);
-                        pb_T2 = __funnelshift_r(Q2, Q3, bit);
-                        pb_T3 = __funnelshift_r(Q3, Q4, bit);
-                        const uint64_t pre = (((uint64_t)pb_T1 << 32) | pb_T0) & tag_km;
-                        pb_h = tag_slot(pre, tag_mask);            // even: both slots share a 64-byte line
-                        const uint4 *e0 = tag_entries + 2 * (size_t)(tag_base + pb_h);
-                        pb_k0 = __ldg(e0);
-                        pb_m0 = __ldg(e0 + 1);
-                        pb_k1 = __ldg(e0 + 2);
-                        pb_m1 = __ldg(e0 + 3);
-                        pb_row = row;
-                        pb_V = V;
-                        pb_end = tag_off;
-                        pb_probe = true;
-                    }
-                }
-            } else {
-                const uint32_t se = off >= 2 * STAGE ? 2u : (off >= STAGE ? 1u : 0u);
-                const uint32_t p = off - se * STAGE;
-                const uint32_t tile = ws->tile[se];
-                const unsigned long long tile_off = (unsigned long long)tile * TILE;
-                const unsigned long long avail = a.n - tile_off;
-                const uint32_t staged = avail < copy_bytes ? (uint32_t)avail : copy_bytes;
-                MatchResult mr = match_general(wbase + se * STAGE, p, staged, a.bytes + tile_off, avail, need, bar, bent, &a.tags);
-                pb_row = mr.row;
-                pb_col = mr.col;
             }
+            __syncwarp();             // the bucket walks have different lengths: reconverge here
+            // ---- tag key at tag_off: the first 32 bases give the slot; fetch the first two
+            // slots of the probe sequence right away (speculatively: validity is checked below)
+            const uint32_t toff = sh + tag_off;
+            const uint32_t bit = (toff & 15u) * 2u;
+            const bool up = (toff >> 4) != 0;          // toff <= 31
+            {
+                const uint32_t Q0 = up ? P[1] : P[0], Q1 = up ? P[2] : P[1], Q2 = up ? P[3] : P[2];
+                pb_T0 = __funnelshift_r(Q0, Q1, bit);
+                pb_T1 = __funnelshift_r(Q1, Q2, bit);
+            }
+            const uint64_t pre = (((uint64_t)pb_T1 << 32) | pb_T0) & tag_km;
+            pb_h = tag_slot(pre, tag_mask);            // even: both slots share a 64-byte line
+            const bool want = have & !slow & (row >= 0);
+            {
+                // unconditional (lanes that do not probe read slot 0): a predicated load would be
+                // staged through temporaries and copied, and the copy waits for the data at once
+                const uint4 *e0 = tag_entries + 2 * (size_t)(tag_base + (want ? pb_h : 0u));
+                pb_k0 = __ldg(e0);
+                pb_m0 = __ldg(e0 + 1);
+                pb_k1 = __ldg(e0 + 2);
+                pb_m1 = __ldg(e0 + 3);
+            }
+            // ---- the rest of the tag (bases 32..63) while the loads are in flight
+#pragma unroll
+            for (uint32_t g = 4; g < FAST_WORDS_MAX / 4; g++)
+                if (4 * g < nw) pack_group(g);
+            {
+                const uint32_t Q2 = up ? P[3] : P[2], Q3 = up ? P[4] : P[3], Q4 = up ? P[5] : P[4];
+                pb_T2 = __funnelshift_r(Q2, Q3, bit);
+                pb_T3 = __funnelshift_r(Q3, Q4, bit);
+            }
+            // some character is not a base: matches stand only if they end before it
+            uint32_t V = 0xFFFFFFFFu;                  // valid bases from the line start
+            if (gbm != 0) {
+                // first character that is not a base, inside the first flagged group of four words
+                const uint32_t i0 = 4u * (__ffs(gbm) - 1u);
+                uint32_t firstbad = 0, at = 0;
+#pragma unroll
+                for (int k = 3; k >= 0; k--) {
+                    uint32_t bad;
+                    (void)pack_word(wp[i0 + k], bad);
+                    if (i0 + k == 0) bad &= 0xFFFFFFFFu << (8u * sh);
+                    if (bad != 0 && i0 + k < nw) { firstbad = bad; at = i0 + k; }
+                }
+                if (firstbad) V = 4u * at + ((uint32_t)(__ffs(firstbad) - 1) >> 3) - sh;
+            }
+            __syncwarp();
+            pb_probe = want & (blen <= V);
+            if (pb_probe) {
+                pb_row = row;
+                pb_V = V;
+                pb_end = tag_off;
+            }
+        }
+        if (slow) {
+            const uint32_t se = off >= 2 * STAGE ? 2u : (off >= STAGE ? 1u : 0u);
+            const uint32_t p = off - se * STAGE;
+            const uint32_t tile = ws->tile[se];
+            const unsigned long long tile_off = (unsigned long long)tile * TILE;
+            const unsigned long long avail = a.n - tile_off;
+            const uint32_t staged = avail < copy_bytes ? (uint32_t)avail : copy_bytes;
+            MatchResult mr = match_general(wbase + se * STAGE, p, staged, a.bytes + tile_off, avail, need, bar, bent, &a.tags);
+            pb_row = mr.row;
+            pb_col = mr.col;
         }
         pb_pending = true;
     };
