@@ -199,6 +199,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // TMA bulk copy global -> shared, completion signalled on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -651,13 +665,233 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     };
 
     uint32_t s = 0, parity = 0;
+    // The loop is rotated: an iteration FINISHES the tile that the previous iteration opened
+    // (ranks, emission, batch_front) and then OPENS the next one (wait for its bytes, scan).
+    // batch_back sits after the scan, so that the probe loads issued by batch_front are
+    // consumed a whole scan later with only straight-line code in between.
+    uint32_t tix = 0, t = 0, extra = 0, sbase = 0;
+    bool seg_end = false, last_tile = false, opened = false;
+    const uint8_t *buf = wbase;
+    unsigned long long avail = 0;
+    uint32_t mk[MWORDS];
+#pragma unroll
+    for (uint32_t j = 0; j < MWORDS; j++) mk[j] = 0;
     for (;;) {
+        if (opened) {
+            // the candidate loops below walk the masks through shared memory (one loop
+            // over all candidates of a lane instead of one loop per mask word)
+            uint32_t cnt = 0, nz = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < MWORDS; j++) {
+                ws->mk[j][lane] = mk[j];
+                cnt += __popc(mk[j]);
+                if (mk[j]) nz |= 1u << j;
+            }
+
+            // exact line ends: '\n' ends a line; '\r' ends one unless a '\n' follows
+            // (Python universal newlines); every other control character is content.
+            auto classify = [&]() {
+                uint32_t nzl = nz;
+                cnt = 0;
+                nz = 0;
+                while (nzl) {
+                    const uint32_t j = __ffs(nzl) - 1u;
+                    nzl &= nzl - 1u;
+                    uint32_t m = ws->mk[j][lane], keepm = m;
+                    while (m) {
+                        const uint32_t b = __ffs(m) - 1u;
+                        m &= m - 1u;
+                        const uint32_t p = lane * SPAN + 32 * j + b;
+                        const uint32_t c = buf[p];
+                        bool end = c == '\n';
+                        // the byte after the last byte of the chunk is unknown: pending
+                        if (c == '\r') end = (p + 1 < avail) && buf[p + 1] != '\n';
+                        if (!end) keepm &= ~(1u << b);
+                    }
+                    ws->mk[j][lane] = keepm;
+                    cnt += __popc(keepm);
+                    if (keepm) nz |= 1u << j;
+                }
+            };
+            bool verified = false;
+            if (classify_first || need_guess) { classify(); verified = true; }
+
+            uint32_t incl, total;
+            for (;;) {
+                incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t o = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= (uint32_t)d) incl += o;
+                }
+                total = extra + __shfl_sync(FULL, incl, 31);
+                if (!MATCH) break;
+                const uint32_t rho0 = extra + incl - cnt;       // rank of the line start after my first line end
+
+                if (need_guess) {
+                    // First lines of a segment whose position in the file is not known yet:
+                    // find a line that looks like a FASTQ header ('@', then '+' two lines on,
+                    // sequence and quality lines of equal length).  Any answer is acceptable --
+                    // a wrong one is found and repaired by verify_kernel + the fix pass.
+                    {
+                        uint32_t r = rho0, nzl = nz;
+                        while (nzl && r < GUESS_LINES + 5) {
+                            const uint32_t j = __ffs(nzl) - 1u;
+                            nzl &= nzl - 1u;
+                            uint32_t m = ws->mk[j][lane];
+                            while (m && r < GUESS_LINES + 5) {
+                                const uint32_t b = __ffs(m) - 1u;
+                                m &= m - 1u;
+                                ws->gs[r] = (uint16_t)(lane * SPAN + 32 * j + b + 1);
+                                r++;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t have = total < GUESS_LINES + 5 ? total : GUESS_LINES + 5;
+                    bool hit = false;
+                    if (lane < GUESS_LINES && lane + 4 < have) {
+                        uint32_t p0 = ws->gs[lane], p1 = ws->gs[lane + 1], p2 = ws->gs[lane + 2], p3 = ws->gs[lane + 3],
+                                 p4 = ws->gs[lane + 4];
+                        hit = buf[p0] == '@' && buf[p2] == '+' && p2 - p1 == p4 - p3;
+                    }
+                    const uint32_t hits = __ballot_sync(FULL, hit);
+                    guess = hits ? ((4u - ((uint32_t)(__ffs(hits) - 1) & 3u)) & 3u) : 0u;   // that line has index 0 mod 4
+                    seg_first = guess;
+                    need_guess = false;
+                }
+
+                // ---- emission: queue the starts of sequence lines (index % 4 == 1) -----------
+                const unsigned long long F = seg_first + seg_lines;        // index of rank 0 of this tile
+                const uint32_t a4 = (1u - (uint32_t)F) & 3u;                 // first rank that is a sequence line
+                const uint32_t nq = total > a4 ? (total - a4 + 3u) >> 2 : 0u;
+                uint32_t nlive = 0;                                          // those below the read limit (a prefix)
+                {
+                    const unsigned long long first_idx = (F + a4) >> 2;
+                    if (nq && first_idx < limit) {
+                        unsigned long long room = limit - first_idx;
+                        nlive = nq < room ? nq : (uint32_t)room;
+                    }
+                }
+                // my first sequence line: `skip0` candidates on, ordinal `jj0` among the tile's
+                const uint32_t skip0 = (a4 - rho0) & 3u;
+                const uint32_t jj0 = (rho0 + skip0 - a4) >> 2;
+                // Common case: everything fits one round, the read limit does not fall inside
+                // the tile and no lane holds more than two sequence-line starts.
+                const bool simple = nlive == nq && nq <= PUSH_CAP && !__any_sync(FULL, cnt > skip0 + 8u);
+                bool redo = false;
+                for (uint32_t w0 = 0;;) {
+                    const uint32_t room = nlive - w0 < PUSH_CAP ? nlive - w0 : PUSH_CAP;
+                    const uint32_t qbase = q_head + q_len - w0;           // slot of ordinal 0
+                    uint32_t dev = 0;                                     // non-zero: a candidate is not '\n'
+                    uint32_t nzl = nz, cur = 0, pbase = 0;
+                    if (simple) {
+                        // one walk over my candidates: check them, remember the (at most two)
+                        // that start a sequence line
+                        uint32_t o = 0, qp0 = 0, qp1 = 0;
+                        while ((cur | nzl) != 0) {
+                            if (cur == 0) {
+                                const uint32_t j = __ffs(nzl) - 1u;
+                                nzl &= nzl - 1u;
+                                cur = ws->mk[j][lane];
+                                pbase = lane * SPAN + 32 * j;
+                            }
+                            const uint32_t p = pbase + __ffs(cur) - 1u;
+                            cur &= cur - 1u;
+                            dev |= (uint32_t)buf[p] ^ 0x0Au;
+                            if (o == skip0) qp0 = p;
+                            if (o == skip0 + 4u) qp1 = p;
+                            o++;
+                        }
+                        if (cnt > skip0) ws->q[(qbase + jj0) & (QCAP - 1)] = (uint16_t)(sbase + qp0 + 1);
+                        if (cnt > skip0 + 4u) ws->q[(qbase + jj0 + 1) & (QCAP - 1)] = (uint16_t)(sbase + qp1 + 1);
+                    } else {
+                        uint32_t skip = skip0, jj = jj0;
+                        while ((cur | nzl) != 0) {
+                            if (cur == 0) {
+                                const uint32_t j = __ffs(nzl) - 1u;
+                                nzl &= nzl - 1u;
+                                cur = ws->mk[j][lane];
+                                pbase = lane * SPAN + 32 * j;
+                            }
+                            const uint32_t p = pbase + __ffs(cur) - 1u;
+                            cur &= cur - 1u;
+                            dev |= (uint32_t)buf[p] ^ 0x0Au;
+                            if (skip == 0) {
+                                if (jj - w0 < room) ws->q[(qbase + jj) & (QCAP - 1)] = (uint16_t)(sbase + p + 1);
+                                jj++;
+                                skip = 3;
+                            } else {
+                                skip--;
+                            }
+                        }
+                    }
+                    if (lane == 0 && extra && a4 == 0 && w0 == 0 && room > 0) ws->q[qbase & (QCAP - 1)] = (uint16_t)sbase;
+                    if (!verified) {
+                        if (__any_sync(FULL, dev != 0)) { redo = true; break; }
+                        verified = true;
+                    }
+                    __syncwarp();
+                    q_len += room;
+                    w0 += room;
+                    // Match full warps.  After the tile's last round also drain what must not
+                    // wait: entries that point into the previous tile's stage have to go
+                    // before that stage is refilled, a segment's entries before its state
+                    // (weight, limit) changes.
+                    for (;;) {
+                        const bool last_round = w0 >= nlive;
+                        uint32_t nb = 0;
+                        if (q_len >= 32) nb = 32;
+                        else if (last_round && (seg_end || q_old > 0)) nb = q_len;
+                        // the segment ends: nothing may stay in flight
+                        const bool finish = pb_pending && last_round && seg_end;
+                        if (nb == 0 && !finish) break;
+                        if (pb_pending) batch_back();      // rare here: a second batch from one tile, or a flush
+                        if (nb == 0) break;
+                        batch_front(nb);
+                        // Common case: nothing more to do for this tile.  Leave through a forward
+                        // branch -- ptxas waits for outstanding loads at loop headers, and the
+                        // probe loads just issued must stay in flight until batch_back.
+                        const bool again = q_len >= 32 || (last_round && (seg_end || (q_old > 0 && q_len > 0)));
+                        if (!again) break;
+                    }
+                    if (w0 >= nlive) break;
+                }
+                if (redo) {
+                    classify();
+                    verified = true;
+                    classify_first = true;
+                    continue;
+                }
+                // reads numbered in this tile (those below the limit)
+                my_reads += weight * (long long)nlive;
+                break;
+            }
+            seg_lines += total;
+
+            q_old = q_len;
+            if (lane == 0 && a.mode == MODE_MAIN && seg_end) {
+                SegInfo si;
+                si.lines = seg_lines;
+                si.guess = guess;
+                a.seginfo[seg] = si;
+            }
+
+            // ---- refill the stage of the previous tile (nothing points into it any more) ---
+            __syncwarp();
+            if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            metaA = metaB;
+            metaB = produce(s == 0 ? STAGES - 1 : s - 1);
+            if (++s == STAGES) { s = 0; parity ^= 1u; }
+        }
+
+        // ---- open the next tile ------------------------------------------------------
         const uint32_t item = metaA.item;
         if (item == NONE) break;
-        const uint32_t tix = metaA.tix;
-        const uint32_t t = metaA.tile;                // tile index in the chunk
+        tix = metaA.tix;
+        t = metaA.tile;                               // tile index in the chunk
         cur_tile = t;
-        mbar_wait(&full_bar[warp][s], parity);
+        if (!mbar_test(&full_bar[warp][s], parity)) mbar_wait(&full_bar[warp][s], parity);   // usually there already
 
         if (tix == 0) {                    // a new segment starts
             seg_lines = 0;
@@ -679,17 +913,17 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             uint32_t left = a.num_tiles - first_tile;
             seg_ntiles = left < a.seg_tiles ? left : a.seg_tiles;
         }
-        const bool seg_end = tix == seg_ntiles - 1;
-        const bool last_tile = t == a.num_tiles - 1;
+        seg_end = tix == seg_ntiles - 1;
+        last_tile = t == a.num_tiles - 1;
 
-        const uint8_t *buf = wbase + s * STAGE;
-        const uint32_t sbase = s * STAGE;
+        buf = wbase + s * STAGE;
+        sbase = s * STAGE;
         const unsigned long long tile_off = (unsigned long long)t * TILE;
-        const unsigned long long avail = a.n - tile_off;            // bytes from tile start to chunk end
+        avail = a.n - tile_off;                                     // bytes from tile start to chunk end
         const uint32_t valid = avail < TILE ? (uint32_t)avail : TILE;
 
         // An implicit line end just before byte 0 of the chunk?
-        uint32_t extra = 0;
+        extra = 0;
         if (t == 0) {
             if (prev_kind == PREV_NONE || prev_kind == PREV_LF) extra = 1;
             else if (prev_kind == PREV_CR && buf[0] != '\n') extra = 1;
@@ -698,7 +932,6 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         // ---- scan: control-character mask of my SPAN bytes ----------------------
         // (lane l reads 16-byte units CHUNKS*l + i: with CHUNKS odd, eight consecutive
         // lanes hit eight different bank groups, so every 128-bit load is conflict free)
-        uint32_t mk[MWORDS];
         {
             const uint4 *src = (const uint4 *)(buf + lane * SPAN);
 #pragma unroll
@@ -724,209 +957,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 *a.last_kind = c == '\n' ? PREV_LF : (c == '\r' ? PREV_CR : PREV_OTHER);
             }
         }
-        // the candidate loops below walk the masks through shared memory (one loop
-        // over all candidates of a lane instead of one loop per mask word)
-        uint32_t cnt = 0, nz = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < MWORDS; j++) {
-            ws->mk[j][lane] = mk[j];
-            cnt += __popc(mk[j]);
-            if (mk[j]) nz |= 1u << j;
-        }
-
-        // exact line ends: '\n' ends a line; '\r' ends one unless a '\n' follows
-        // (Python universal newlines); every other control character is content.
-        auto classify = [&]() {
-            uint32_t nzl = nz;
-            cnt = 0;
-            nz = 0;
-            while (nzl) {
-                const uint32_t j = __ffs(nzl) - 1u;
-                nzl &= nzl - 1u;
-                uint32_t m = ws->mk[j][lane], keepm = m;
-                while (m) {
-                    const uint32_t b = __ffs(m) - 1u;
-                    m &= m - 1u;
-                    const uint32_t p = lane * SPAN + 32 * j + b;
-                    const uint32_t c = buf[p];
-                    bool end = c == '\n';
-                    // the byte after the last byte of the chunk is unknown: pending
-                    if (c == '\r') end = (p + 1 < avail) && buf[p + 1] != '\n';
-                    if (!end) keepm &= ~(1u << b);
-                }
-                ws->mk[j][lane] = keepm;
-                cnt += __popc(keepm);
-                if (keepm) nz |= 1u << j;
-            }
-        };
-        bool verified = false;
-        if (classify_first || need_guess) { classify(); verified = true; }
-
-        uint32_t incl, total;
-        for (;;) {
-            incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(FULL, incl, d);
-                if (lane >= (uint32_t)d) incl += o;
-            }
-            total = extra + __shfl_sync(FULL, incl, 31);
-            if (!MATCH) break;
-            const uint32_t rho0 = extra + incl - cnt;       // rank of the line start after my first line end
-
-            if (need_guess) {
-                // First lines of a segment whose position in the file is not known yet:
-                // find a line that looks like a FASTQ header ('@', then '+' two lines on,
-                // sequence and quality lines of equal length).  Any answer is acceptable --
-                // a wrong one is found and repaired by verify_kernel + the fix pass.
-                {
-                    uint32_t r = rho0, nzl = nz;
-                    while (nzl && r < GUESS_LINES + 5) {
-                        const uint32_t j = __ffs(nzl) - 1u;
-                        nzl &= nzl - 1u;
-                        uint32_t m = ws->mk[j][lane];
-                        while (m && r < GUESS_LINES + 5) {
-                            const uint32_t b = __ffs(m) - 1u;
-                            m &= m - 1u;
-                            ws->gs[r] = (uint16_t)(lane * SPAN + 32 * j + b + 1);
-                            r++;
-                        }
-                    }
-                }
-                __syncwarp();
-                const uint32_t have = total < GUESS_LINES + 5 ? total : GUESS_LINES + 5;
-                bool hit = false;
-                if (lane < GUESS_LINES && lane + 4 < have) {
-                    uint32_t p0 = ws->gs[lane], p1 = ws->gs[lane + 1], p2 = ws->gs[lane + 2], p3 = ws->gs[lane + 3],
-                             p4 = ws->gs[lane + 4];
-                    hit = buf[p0] == '@' && buf[p2] == '+' && p2 - p1 == p4 - p3;
-                }
-                const uint32_t hits = __ballot_sync(FULL, hit);
-                guess = hits ? ((4u - ((uint32_t)(__ffs(hits) - 1) & 3u)) & 3u) : 0u;   // that line has index 0 mod 4
-                seg_first = guess;
-                need_guess = false;
-            }
-
-            // ---- emission: queue the starts of sequence lines (index % 4 == 1) -----------
-            const unsigned long long F = seg_first + seg_lines;        // index of rank 0 of this tile
-            const uint32_t a4 = (1u - (uint32_t)F) & 3u;                 // first rank that is a sequence line
-            const uint32_t nq = total > a4 ? (total - a4 + 3u) >> 2 : 0u;
-            uint32_t nlive = 0;                                          // those below the read limit (a prefix)
-            {
-                const unsigned long long first_idx = (F + a4) >> 2;
-                if (nq && first_idx < limit) {
-                    unsigned long long room = limit - first_idx;
-                    nlive = nq < room ? nq : (uint32_t)room;
-                }
-            }
-            // my first sequence line: `skip0` candidates on, ordinal `jj0` among the tile's
-            const uint32_t skip0 = (a4 - rho0) & 3u;
-            const uint32_t jj0 = (rho0 + skip0 - a4) >> 2;
-            // Common case: everything fits one round, the read limit does not fall inside
-            // the tile and no lane holds more than two sequence-line starts.
-            const bool simple = nlive == nq && nq <= PUSH_CAP && !__any_sync(FULL, cnt > skip0 + 8u);
-            bool redo = false;
-            for (uint32_t w0 = 0;;) {
-                const uint32_t room = nlive - w0 < PUSH_CAP ? nlive - w0 : PUSH_CAP;
-                const uint32_t qbase = q_head + q_len - w0;           // slot of ordinal 0
-                uint32_t dev = 0;                                     // non-zero: a candidate is not '\n'
-                uint32_t nzl = nz, cur = 0, pbase = 0;
-                if (simple) {
-                    // one walk over my candidates: check them, remember the (at most two)
-                    // that start a sequence line
-                    uint32_t o = 0, qp0 = 0, qp1 = 0;
-                    while ((cur | nzl) != 0) {
-                        if (cur == 0) {
-                            const uint32_t j = __ffs(nzl) - 1u;
-                            nzl &= nzl - 1u;
-                            cur = ws->mk[j][lane];
-                            pbase = lane * SPAN + 32 * j;
-                        }
-                        const uint32_t p = pbase + __ffs(cur) - 1u;
-                        cur &= cur - 1u;
-                        dev |= (uint32_t)buf[p] ^ 0x0Au;
-                        if (o == skip0) qp0 = p;
-                        if (o == skip0 + 4u) qp1 = p;
-                        o++;
-                    }
-                    if (cnt > skip0) ws->q[(qbase + jj0) & (QCAP - 1)] = (uint16_t)(sbase + qp0 + 1);
-                    if (cnt > skip0 + 4u) ws->q[(qbase + jj0 + 1) & (QCAP - 1)] = (uint16_t)(sbase + qp1 + 1);
-                } else {
-                    uint32_t skip = skip0, jj = jj0;
-                    while ((cur | nzl) != 0) {
-                        if (cur == 0) {
-                            const uint32_t j = __ffs(nzl) - 1u;
-                            nzl &= nzl - 1u;
-                            cur = ws->mk[j][lane];
-                            pbase = lane * SPAN + 32 * j;
-                        }
-                        const uint32_t p = pbase + __ffs(cur) - 1u;
-                        cur &= cur - 1u;
-                        dev |= (uint32_t)buf[p] ^ 0x0Au;
-                        if (skip == 0) {
-                            if (jj - w0 < room) ws->q[(qbase + jj) & (QCAP - 1)] = (uint16_t)(sbase + p + 1);
-                            jj++;
-                            skip = 3;
-                        } else {
-                            skip--;
-                        }
-                    }
-                }
-                if (lane == 0 && extra && a4 == 0 && w0 == 0 && room > 0) ws->q[qbase & (QCAP - 1)] = (uint16_t)sbase;
-                if (!verified) {
-                    if (__any_sync(FULL, dev != 0)) { redo = true; break; }
-                    verified = true;
-                }
-                __syncwarp();
-                q_len += room;
-                w0 += room;
-                // Match full warps.  After the tile's last round also drain what must not
-                // wait: entries that point into the previous tile's stage have to go
-                // before that stage is refilled, a segment's entries before its state
-                // (weight, limit) changes.
-                for (;;) {
-                    const bool last_round = w0 >= nlive;
-                    uint32_t nb = 0;
-                    if (q_len >= 32) nb = 32;
-                    else if (last_round && (seg_end || q_old > 0)) nb = q_len;
-                    // Leave first when there is nothing to do: the code below consumes the
-                    // probe loads of the batch in flight, and the wait for them must not sit
-                    // on this common exit path.
-                    if (nb == 0 && !(pb_pending && last_round && seg_end)) break;
-                    // finish the batch in flight right before the next one starts (as late as
-                    // possible), and before a segment's state changes
-                    if (pb_pending) batch_back();
-                    if (nb == 0) break;
-                    batch_front(nb);
-                }
-                if (w0 >= nlive) break;
-            }
-            if (redo) {
-                classify();
-                verified = true;
-                classify_first = true;
-                continue;
-            }
-            // reads numbered in this tile (those below the limit)
-            my_reads += weight * (long long)nlive;
-            break;
-        }
-        seg_lines += total;
-
-        q_old = q_len;
-        if (lane == 0 && a.mode == MODE_MAIN && seg_end) {
-            SegInfo si;
-            si.lines = seg_lines;
-            si.guess = guess;
-            a.seginfo[seg] = si;
-        }
-
-        // ---- refill the stage of the previous tile (nothing points into it any more) ---
-        __syncwarp();
-        if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        metaA = metaB;
-        metaB = produce(s == 0 ? STAGES - 1 : s - 1);
-        if (++s == STAGES) { s = 0; parity ^= 1u; }
+        opened = true;
+        if (MATCH && pb_pending) batch_back();       // its probe loads went out before the refill and this scan
     }
 
     if (MATCH) {
