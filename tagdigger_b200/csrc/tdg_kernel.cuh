@@ -329,11 +329,11 @@ __device__ __noinline__ MatchResult match_general(const uint8_t *buf, uint32_t p
 // byte of the result; `bad` non-zero iff a character is not one of ACGTacgt.
 __device__ __forceinline__ uint32_t pack_word(uint32_t w, uint32_t &bad)
 {
-    uint32_t cf = w & 0xDFDFDFDFu;                    // fold case (exact for ASCII letters)
-    uint32_t c2 = (w >> 1) & 0x03030303u;             // A0 C1 T2 G3
+    uint32_t c2 = (w >> 1) & 0x03030303u;             // A0 C1 T2 G3 (bits 1-2 of the character)
     uint32_t m = (c2 >> 1) & ~c2 & 0x01010101u;       // 1 where code == 2 (T)
-    uint32_t e = 0x41414141u + 2u * c2 + 15u * m;     // the letter that code stands for
-    bad = e ^ cf;
+    // With bits 1-2 accounted for by the code and bit 5 (case) ignored, the remaining bits
+    // 0,3,4,6,7 of a base are 0x41 for A/C/G and 0x50 for T.
+    bad = (w & 0xD9D9D9D9u) ^ (0x41414141u ^ (m * 0x11u));
     return c2 * 0x01041040u;                          // byte 3 = c0 | c1<<2 | c2<<4 | c3<<6
 }
 
@@ -527,10 +527,13 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 uint32_t x[4], gbad = 0;
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++) {
-                    uint32_t bad;
-                    x[k] = pack_word(wp[4 * g + k], bad);
-                    if (g == 0 && k == 0) bad &= 0xFFFFFFFFu << (8u * sh);   // bytes before the line start
-                    gbad |= bad;      // words past nw may flag too: V below ignores them
+                    x[k] = 0;
+                    if (g < 4 || 4 * g + k < nw) {           // past group 3 only the words that are needed
+                        uint32_t bad;
+                        x[k] = pack_word(wp[4 * g + k], bad);
+                        if (g == 0 && k == 0) bad &= 0xFFFFFFFFu << (8u * sh);   // bytes before the line start
+                        gbad |= bad;      // words past nw (groups 0-3) may flag too: V below ignores them
+                    }
                 }
                 if (gbad) gbm |= 1u << g;
                 P[g] = __byte_perm(__byte_perm(x[0], x[1], 0x0073), __byte_perm(x[2], x[3], 0x0073), 0x5410);
