@@ -231,13 +231,28 @@ __device__ __forceinline__ uint32_t ctl4(uint32_t w)
     uint32_t t = (w & 0x7F7F7F7Fu) + 0x60606060u;
     return ~(t | w) & 0x80808080u;
 }
+// The same test in two instructions when every byte of the word is ASCII (< 0x80):
+// without the masking a byte >= 0xA0 would carry into its neighbour, so callers OR the
+// words they test into `seen` and fall back to ctl4 when a top bit shows up.
+__device__ __forceinline__ uint32_t ctl4_ascii(uint32_t w)
+{
+    return ~(w + 0x60606060u) & 0x80808080u;
+}
 // 16 bytes -> 16-bit mask of control characters.  A byte-wise dot product with
 // the weights 1,2,4,..,128 gathers the 0x80 flags of two words into eight
 // adjacent bits (scaled by 128): one IDP.4A per word.
-__device__ __forceinline__ uint32_t ctl_mask16(uint4 q)
+template <bool ASCII>
+__device__ __forceinline__ uint32_t ctl_mask16(uint4 q, uint32_t &seen)
 {
-    uint32_t lo = __dp4a(ctl4(q.y), 0x80402010u, __dp4a(ctl4(q.x), 0x08040201u, 0u));   // flags of bytes 0-7, << 7
-    uint32_t hi = __dp4a(ctl4(q.w), 0x80402010u, __dp4a(ctl4(q.z), 0x08040201u, 0u));   // flags of bytes 8-15, << 7
+    uint32_t fx, fy, fz, fw;
+    if (ASCII) {
+        fx = ctl4_ascii(q.x); fy = ctl4_ascii(q.y); fz = ctl4_ascii(q.z); fw = ctl4_ascii(q.w);
+        seen |= (q.x | q.y) | (q.z | q.w);
+    } else {
+        fx = ctl4(q.x); fy = ctl4(q.y); fz = ctl4(q.z); fw = ctl4(q.w);
+    }
+    uint32_t lo = __dp4a(fy, 0x80402010u, __dp4a(fx, 0x08040201u, 0u));   // flags of bytes 0-7, << 7
+    uint32_t hi = __dp4a(fw, 0x80402010u, __dp4a(fz, 0x08040201u, 0u));   // flags of bytes 8-15, << 7
     return (hi * 256u + lo) >> 7;
 }
 
@@ -423,9 +438,11 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             if (lane == 0) {
                 ws->tile[s] = m.tile;
                 unsigned long long off = (unsigned long long)m.tile * TILE;
-                unsigned long long left = a.n - off;
                 uint32_t bytes = copy_bytes;
-                if (left < bytes) bytes = ((uint32_t)left + 15u) & ~15u;
+                if (m.tile + 2 >= a.num_tiles) {              // only the last tiles can run past the data
+                    unsigned long long left = a.n - off;
+                    if (left < bytes) bytes = ((uint32_t)left + 15u) & ~15u;
+                }
                 mbar_expect_tx(&full_bar[warp][s], bytes);
                 bulk_g2s(wbase + s * STAGE, a.bytes + off, bytes, &full_bar[warp][s]);
             }
@@ -768,9 +785,10 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 const unsigned long long F = seg_first + seg_lines;        // index of rank 0 of this tile
                 const uint32_t a4 = (1u - (uint32_t)F) & 3u;                 // first rank that is a sequence line
                 const uint32_t nq = total > a4 ? (total - a4 + 3u) >> 2 : 0u;
-                uint32_t nlive = 0;                                          // those below the read limit (a prefix)
-                {
+                uint32_t nlive = nq;                                         // those below the read limit (a prefix)
+                if (limit != ~0ull) {                                        // only the fix pass applies a limit
                     const unsigned long long first_idx = (F + a4) >> 2;
+                    nlive = 0;
                     if (nq && first_idx < limit) {
                         unsigned long long room = limit - first_idx;
                         nlive = nq < room ? nq : (uint32_t)room;
@@ -937,10 +955,22 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         // lanes hit eight different bank groups, so every 128-bit load is conflict free)
         {
             const uint4 *src = (const uint4 *)(buf + lane * SPAN);
+            uint32_t seen = 0;
 #pragma unroll
             for (uint32_t i = 0; i < CHUNKS; i++) {
-                uint32_t m16 = ctl_mask16(src[i]);
+                uint32_t m16 = ctl_mask16<true>(src[i], seen);
                 if (i & 1u) mk[i >> 1] |= m16 << 16; else mk[i >> 1] = m16;
+            }
+            if (__any_sync(FULL, (seen & 0x80808080u) != 0)) {
+                // some byte of the tile is not ASCII: test again with the carry-safe form
+#pragma unroll 1
+                for (uint32_t i = 0; i < CHUNKS; i++) {
+                    uint32_t m16 = ctl_mask16<false>(src[i], seen);
+                    uint32_t word = i >> 1, sh16 = (i & 1u) * 16u;
+#pragma unroll
+                    for (uint32_t j = 0; j < MWORDS; j++)
+                        if (j == word) mk[j] = (mk[j] & ~(0xFFFFu << sh16)) | (m16 << sh16);
+                }
             }
         }
         if (last_tile) {
