@@ -205,6 +205,15 @@ int         tdg_split_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off,
                             const uint32_t *bar_len, uint32_t nbar, uint32_t cutlen,
                             int32_t *bar_out, int32_t *slice2);
 
+/* Per-read results of the matcher for n sequence lines given as HOST buffers (stripped;
+ * case is folded on the device): row_out[i] = the barcode row (sequence_index_lookup on
+ * barcuttree, tagdigger_fun.py:257) or -1, col_out[i] = the tag column (:260-261) or -1.
+ * For callers that must see individual reads: find_tags_fastq(tassel_tagcount=True) adds
+ * the count= weight of each read's header line (:251-253, :264-265) on the host.
+ * Uses the tables of tdg_set_tags / tdg_begin_file; synchronous. */
+int         tdg_match_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, uint32_t n,
+                            int32_t *row_out, int32_t *col_out);
+
 #ifdef __cplusplus
 }
 #endif

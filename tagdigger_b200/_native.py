@@ -35,7 +35,7 @@ tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end
 tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
-tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch""".split()
+tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch tdg_match_batch""".split()
 
 
 class TdgError(RuntimeError):
@@ -121,6 +121,7 @@ def lib():
         "tdg_set_trim": (i32, [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, u32, vp, vp, vp, vp, vp, vp]),
         "tdg_trim_batch": (i32, [vp, vp, vp, vp, vp, u32, vp]),
         "tdg_split_batch": (i32, [vp, vp, vp, u32, vp, u32, u32, vp, vp]),
+        "tdg_match_batch": (i32, [vp, vp, vp, u32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -365,3 +366,15 @@ class Engine(object):
         self._ck(self._L.tdg_split_batch(self._h, blob, off.ctypes.data, len(raw), blen.ctypes.data, len(blen),
                                          cutlen, bar.ctypes.data, cut.ctypes.data))
         return bar, cut
+
+    def match_batch(self, seqs):
+        """seqs: list of stripped sequence lines (bytes/str).  Returns (row, col) arrays, -1 = no match."""
+        raw = [x.encode("utf-8") if isinstance(x, str) else bytes(x) for x in seqs]
+        blob = b"".join(raw)
+        off = np.zeros(len(raw) + 1, dtype=np.uint64)
+        if raw:
+            np.cumsum([len(x) for x in raw], out=off[1:])
+        row = np.empty(len(raw), dtype=np.int32)
+        col = np.empty(len(raw), dtype=np.int32)
+        self._ck(self._L.tdg_match_batch(self._h, blob, off.ctypes.data, len(raw), row.ctypes.data, col.ctypes.data))
+        return row, col

@@ -67,10 +67,9 @@ def find_tags_fastq(fqfile, barcodes, tags, cutsite="TGCAG", maxreads=5e9, tasse
 
     ``totals`` (optional list) receives [reads, reads with barcode and cut
     site, reads with tag] -- the running totals the reference prints."""
-    if tassel_tagcount:
-        raise NotImplementedError("tassel_tagcount=True (count= weights, tagdigger_fun.py:251-253) "
-                                  "is not implemented on the GPU path yet")
     p = matchset.plan(barcodes, tags, cutsite)
+    if tassel_tagcount:
+        return _find_tags_weighted(fqfile, p, maxreads, device, totals)
     limit = _native.limit_from_maxreads(maxreads)
     if p.barnum == 0 or p.ntags == 0:
         # the reference's trie builder indexes an empty list (tagdigger_fun.py:76)
@@ -83,6 +82,59 @@ def find_tags_fastq(fqfile, barcodes, tags, cutsite="TGCAG", maxreads=5e9, tasse
     if totals is not None:
         totals[:] = tot[:3]
     return counts.tolist()
+
+
+TASSEL_BLOCK = 200000         # reads matched per GPU call in tassel_tagcount mode
+
+
+def _find_tags_weighted(fqfile, p, maxreads, device, totals):
+    """find_tags_fastq with tassel_tagcount=True (tagdigger_fun.py:251-253, :264-265): every
+    header line carries ``count=N`` and a matching read adds N instead of 1.  Such files list
+    each distinct tag once, so they are small; the host reads the text and evaluates
+    ``int(...)`` exactly as the reference does (including its ValueError for a header without
+    a parsable count), the GPU matches a block of reads per call (``tdg_match_batch``) and the
+    weights are added as Python integers (no overflow)."""
+    if p.barnum == 0 or p.ntags == 0:
+        raise IndexError("list index out of range")
+    eng = get_engine(device)
+    load_plan(eng, p, nrows=p.barnum)
+    counts = [[0] * p.ntags for _ in range(p.barnum)]
+    tot = [0, 0, 0]
+
+    def flush(seqs, weights):
+        rows, cols = eng.match_batch(seqs)
+        for r, c, w in zip(rows.tolist(), cols.tolist(), weights):
+            if r > -1:
+                tot[1] += 1
+                if c > -1:
+                    tot[2] += 1
+                    counts[r][c] += w
+
+    con = gzip.open(fqfile, "rt") if _is_gz(fqfile) else open(fqfile, "r")
+    try:
+        seqs, weights = [], []
+        weight = 0
+        for lineindex, line in enumerate(con):
+            phase = lineindex % 4
+            if phase == 0:
+                weight = int(line[line.find("count=") + 6:].strip())
+            elif phase == 1:
+                tot[0] += 1
+                seqs.append(line.strip().upper())
+                weights.append(weight)
+                if len(seqs) >= TASSEL_BLOCK:
+                    flush(seqs, weights)
+                    seqs, weights = [], []
+                if tot[0] >= maxreads:
+                    break
+        if seqs:
+            flush(seqs, weights)
+    finally:
+        con.close()
+    print("Reads: {0} With barcode and cut site: {1} With tag: {2}".format(*tot))
+    if totals is not None:
+        totals[:] = tot
+    return counts
 
 
 def find_tags_bytes(data, barcodes, tags, cutsite="TGCAG", maxreads=5e9, device=None, totals=None,

@@ -1158,4 +1158,49 @@ int tdg_split_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, uint32_
     return TDG_OK;
 }
 
+int tdg_match_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, uint32_t n, int32_t *row_out, int32_t *col_out)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!ctx->have_tags) return fail(ctx, TDG_ERR_STATE, "tdg_set_tags has not been called");
+    if (!ctx->have_bar) return fail(ctx, TDG_ERR_STATE, "tdg_begin_file has not been called");
+    if (n == 0) return TDG_OK;
+    if (!off || !row_out || !col_out || (!seqs && off[n] != off[0])) return fail(ctx, TDG_ERR_ARG, "null argument");
+    for (uint32_t i = 0; i < n; i++)
+        if (off[i + 1] < off[i]) return fail(ctx, TDG_ERR_ARG, "offsets must be non-decreasing");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nbytes = (size_t)(off[n] - off[0]);
+    const size_t o_off = round_up(nbytes + 16, 16), o_row = o_off + round_up((n + 1) * sizeof(uint64_t), 16),
+                 o_col = o_row + round_up(n * sizeof(int32_t), 16), total = o_col + round_up(n * sizeof(int32_t), 16);
+    uint8_t *d = nullptr;
+    CK(cudaMalloc(&d, total));
+    std::vector<unsigned long long> rel(n + 1);
+    for (uint32_t i = 0; i <= n; i++) rel[i] = off[i] - off[0];
+    cudaError_t e = cudaSuccess;
+    if (nbytes) e = cudaMemcpyAsync(d, seqs + off[0], nbytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_off, rel.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        tdg::MatchArgs a;
+        a.seqs = d;
+        a.off = (const unsigned long long *)(d + o_off);
+        a.n = n;
+        a.bar = (const tdg::BarTable *)ctx->d_bar;
+        a.tags = ctx->tags.t;
+        a.tags.entries = ctx->d_entries;
+        a.tags.ext = ctx->d_ext;
+        a.row_out = (int32_t *)(d + o_row);
+        a.col_out = (int32_t *)(d + o_col);
+        tdg::match_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(a);
+        e = cudaGetLastError();
+        ctx->launches += 1;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(row_out, d + o_row, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(col_out, d + o_col, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, TDG_ERR_CUDA, std::string("tdg_match_batch: ") + cudaGetErrorString(e));
+    if (e2 != cudaSuccess) return fail(ctx, TDG_ERR_CUDA, std::string("tdg_match_batch: ") + cudaGetErrorString(e2));
+    return TDG_OK;
+}
+
 }  // extern "C"

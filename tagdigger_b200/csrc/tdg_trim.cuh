@@ -167,6 +167,32 @@ __global__ void __launch_bounds__(TRIM_THREADS) split_kernel(const SplitArgs a)
     }
 }
 
+// Per-read results of the counting path's matcher for a batch of (stripped) sequence
+// lines: row = barcode index or -1, col = tag column or -1.  Used where the host has to
+// see individual reads (find_tags_fastq with tassel_tagcount=True adds a per-read weight
+// taken from the header line, tagdigger_fun.py:251-253,264-265).  One thread per read.
+struct MatchArgs {
+    const uint8_t *seqs;
+    const unsigned long long *off;   // [n + 1]
+    uint32_t n;
+    const BarTable *bar;
+    TagTable tags;
+    int32_t *row_out, *col_out;      // [n]
+};
+
+__global__ void __launch_bounds__(128) match_kernel(const MatchArgs a)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.n) return;
+    GlobalBytes f;
+    f.p = a.seqs + a.off[r];
+    f.limit = (uint32_t)(a.off[r + 1] - a.off[r]);
+    const BarEntry *bent = (const BarEntry *)((const uint8_t *)a.bar + sizeof(BarTable));
+    const MatchResult m = match_line(f, a.bar, bent, a.tags);
+    a.row_out[r] = m.row;
+    a.col_out[r] = m.col;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace tdg

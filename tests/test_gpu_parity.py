@@ -19,7 +19,7 @@ from tagdigger_b200 import _native, counting, matchset, synth
 
 pytestmark = pytest.mark.gpu
 
-FIND = [c for c in load_golden("find_tags.json") if not c["kwargs"].get("tassel_tagcount")]
+FIND = load_golden("find_tags.json")          # includes the tassel_tagcount=True cases
 
 
 @pytest.fixture(scope="module")
@@ -405,3 +405,31 @@ def test_general_matcher_table_shapes(monkeypatch):
         assert got == want, shape
         assert tot[:3] == wtot, shape
     eng.close()
+
+
+def test_tassel_tagcount_weights(tmp_path, monkeypatch):
+    """tassel_tagcount=True: count= weights from the header lines, Python int() grammar,
+    ValueError for a header without a parsable count, maxreads, several GPU blocks."""
+    monkeypatch.setattr(counting, "TASSEL_BLOCK", 300)
+    r = random.Random(17)
+    barcodes, tags = small_setup(r, nbar=5, ntag=14)
+    recs = []
+    for i in range(1500):
+        s = r.choice(barcodes) + (r.choice(tags) if r.random() < 0.7 else "TGCAG" + rand_seq(r, 30)) + rand_seq(r, 10)
+        w = r.choice(["1", "7", " 12 ", "+3", "-2", "1_000", "00042", str(r.randrange(10 ** 12))])
+        recs.append("@tag%d length=64 count=%s\n%s\n+\n%s\n" % (i, w, s, "I" * len(s)))
+    path = str(tmp_path / "tassel.fq")
+    for maxreads in (5e9, 777):
+        with open(path, "w") as fh:
+            fh.write("".join(recs))
+        want = orc.find_tags_fastq(path, barcodes, tags, maxreads=maxreads, tassel_tagcount=True)
+        tot = []
+        got = counting.find_tags_fastq(path, barcodes, tags, maxreads=maxreads, tassel_tagcount=True, totals=tot)
+        assert got == want
+        assert sum(map(sum, want)) != 0
+    with open(path, "w") as fh:
+        fh.write("".join(recs[:40]) + "@no weight here\nACGT\n+\nIIII\n")
+    with pytest.raises(ValueError):
+        counting.find_tags_fastq(path, barcodes, tags, tassel_tagcount=True)
+    with pytest.raises(ValueError):
+        orc.find_tags_fastq(path, barcodes, tags, tassel_tagcount=True)
