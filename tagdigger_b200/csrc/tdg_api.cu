@@ -16,6 +16,7 @@
 
 #include "../../include/tagdigger_b200.h"
 #include "tdg_kernel.cuh"
+#include "tdg_feed.h"
 #include "tdg_tables.h"
 #include "tdg_trim.cuh"
 
@@ -894,18 +895,11 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     size_t chunk = ctx->chunk_bytes;
 
     std::thread reader([&]() {
-        FILE *fp = nullptr;
-        gzFile zf = nullptr;
-        if (gz) {
-            zf = gzopen(path, "rb");
-            if (!zf) { io_err = TDG_ERR_IO; io_msg = std::string("cannot open ") + path; }
-            else gzbuffer(zf, 1 << 20);
-        } else {
-            fp = fopen(path, "rb");
-            if (!fp) { io_err = TDG_ERR_IO; io_msg = std::string("cannot open ") + path; }
-        }
+        // host feed: parallel pread / parallel BGZF inflate / zlib, see tdg_feed.h
+        tdg::Feeder feed;
+        int orc = feed.open(path, gz != 0);
+        if (orc) { io_err = orc; io_msg = feed.error(); }
         int bi = 0;
-        bool first = true;
         while (!io_err) {
             Buf &b = bufs[bi];
             {
@@ -913,33 +907,10 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
                 cv.wait(lk, [&] { return b.state == 0 || stop; });
                 if (stop) break;
             }
+            long long r = feed.fill(b.p, chunk);
             size_t got = 0;
-            if (gz) {
-                while (got < chunk) {
-                    unsigned want = (unsigned)std::min<size_t>(chunk - got, 1u << 30);
-                    int r = gzread(zf, b.p + got, want);
-                    if (r < 0) {
-                        int en = 0;
-                        const char *m = gzerror(zf, &en);
-                        io_err = TDG_ERR_GZIP;
-                        io_msg = std::string("gzip error in ") + path + ": " + (m ? m : "?");
-                        break;
-                    }
-                    if (r == 0) break;
-                    got += (size_t)r;
-                    if (first) {
-                        first = false;
-                        if (gzdirect(zf)) {   // the reference's gzip.open raises on a non-gzip file
-                            io_err = TDG_ERR_GZIP;
-                            io_msg = std::string("Not a gzipped file: ") + path;
-                            break;
-                        }
-                    }
-                }
-            } else {
-                got = fread(b.p, 1, chunk, fp);
-                if (got < chunk && ferror(fp)) { io_err = TDG_ERR_IO; io_msg = std::string("read error on ") + path; }
-            }
+            if (r < 0) { io_err = (int)r; io_msg = feed.error(); }
+            else got = (size_t)r;
             {
                 std::lock_guard<std::mutex> lk(mu);
                 b.n = got;
@@ -955,8 +926,6 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
             eof = true;
             cv.notify_all();
         }
-        if (fp) fclose(fp);
-        if (zf) gzclose(zf);
     });
 
     int bi = 0;

@@ -217,7 +217,11 @@ def test_files_plain_and_gzip(tmp_path):
     cut = fq.index(b"\n", len(fq) // 2) + 1
     with open(multi, "wb") as fh:
         fh.write(gzip.compress(fq[:cut]) + gzip.compress(fq[cut:]))
-    for path in (plain, gz, multi):
+    from feed_check import bgzf_compress
+    bg = str(tmp_path / "blocked.fastq.gz")         # BGZF: inflated in parallel by the host feeder
+    with open(bg, "wb") as fh:
+        fh.write(bgzf_compress(fq, block=20000))
+    for path in (plain, gz, multi, bg):
         tot = []
         assert counting.find_tags_fastq(path, bcs, tags, totals=tot) == want, path
         assert tot == wtot
