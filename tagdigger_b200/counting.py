@@ -195,8 +195,13 @@ def count_files(bckeys, tags, cutsite="TGCAG", maxreads=5e9, device=None, rank=0
     samples, rows = global_rows(bckeys)
     limit = _native.limit_from_maxreads(maxreads)
     plans = {}
+    tagplan = None
     for f in files:                               # set-up errors surface before any counting, file by file
-        plans[f] = matchset.plan(bckeys[f][0], tags, cutsite)
+        if tagplan is None:
+            plans[f] = matchset.plan(bckeys[f][0], tags, cutsite)
+            tagplan = matchset.plan_tags(tags, cutsite)       # shared by the other files of the key
+        else:
+            plans[f] = matchset.plan(bckeys[f][0], tags, cutsite, tagplan=tagplan)
         if plans[f].barnum == 0 or plans[f].ntags == 0:
             raise IndexError("list index out of range")
     ntags = len(tags)

@@ -93,6 +93,10 @@ struct tdg_ctx {
     uint32_t trim_nbar = 0;
     bool have_trim = false;
 
+    // pinned buffers of tdg_count_file (kept between files: pinning 192 MiB costs ~0.1 s)
+    uint8_t *file_buf[3] = {nullptr, nullptr, nullptr};
+    size_t file_buf_cap = 0;
+
     // accounting
     uint64_t launches = 0;
     bool timing = false;
@@ -519,6 +523,8 @@ void tdg_destroy(tdg_ctx *ctx)
         if (ctx->d_totals) cudaFree(ctx->d_totals);
         if (ctx->d_trim) cudaFree(ctx->d_trim);
         if (ctx->d_replicas) cudaFree(ctx->d_replicas);
+        for (int i = 0; i < 3; i++)
+            if (ctx->file_buf[i]) cudaFreeHost(ctx->file_buf[i]);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     }
@@ -880,13 +886,26 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
         size_t n = 0;
         int state = 0;   // 0 free, 1 full
     } bufs[NBUF];
-    for (int i = 0; i < NBUF; i++) {
-        cudaError_t e = cudaHostAlloc(&bufs[i].p, ctx->chunk_bytes, cudaHostAllocDefault);
-        if (e != cudaSuccess) {
-            for (int k = 0; k < i; k++) cudaFreeHost(bufs[k].p);
-            return fail(ctx, TDG_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    static_assert(NBUF == 3, "tdg_ctx::file_buf holds three buffers");
+    if (ctx->file_buf_cap < ctx->chunk_bytes) {
+        for (int i = 0; i < NBUF; i++) {
+            if (ctx->file_buf[i]) cudaFreeHost(ctx->file_buf[i]);
+            ctx->file_buf[i] = nullptr;
         }
+        ctx->file_buf_cap = 0;
+        for (int i = 0; i < NBUF; i++) {
+            cudaError_t e = cudaHostAlloc(&ctx->file_buf[i], ctx->chunk_bytes, cudaHostAllocDefault);
+            if (e != cudaSuccess) {
+                for (int k = 0; k <= i; k++) {
+                    if (ctx->file_buf[k]) cudaFreeHost(ctx->file_buf[k]);
+                    ctx->file_buf[k] = nullptr;
+                }
+                return fail(ctx, TDG_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+            }
+        }
+        ctx->file_buf_cap = ctx->chunk_bytes;
     }
+    for (int i = 0; i < NBUF; i++) bufs[i].p = ctx->file_buf[i];
     std::mutex mu;
     std::condition_variable cv;
     bool eof = false, stop = false;
@@ -958,7 +977,6 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     if (result != TDG_OK) ctx->carry_len = 0;
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < NBUF; i++) cudaFreeHost(bufs[i].p);
     if (result == TDG_OK && totals) result = tdg_file_totals(ctx, totals);
     return result;
 }

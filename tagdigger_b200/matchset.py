@@ -107,14 +107,45 @@ class CountPlan(object):
     __slots__ = ("barnum", "ntags", "bar", "bar_tag_off", "tags")
 
 
-def plan(barcodes, tags, cutsite):
-    """Set-up half of find_tags_fastq (tagdigger_fun.py:198-233): same asserts,
-    same pattern lists, same offsets; the two tries become effective sets."""
-    assert all([set(b.upper()) <= set("ACGT") for b in barcodes]), "Non-ACGT barcode."
+class TagPlan(object):
+    """The tag half of a CountPlan: depends on (tags, cutsite) only, so one key file's worth of
+    FASTQ files can share it (the reference rebuilds its tag trie for every file)."""
+
+    __slots__ = ("ntags", "tags", "strip", "shift", "sites", "cutlen")
+
+
+def plan_tags(tags, cutsite):
+    """tagdigger_fun.py:200-204, :207, :221-233 -- everything that does not involve barcodes."""
     cutsite = cutsite.upper()
     assert set(cutsite) <= set("ACGTNRYKMSWBDHV"), "Invalid cut site."
     tags = [t.upper() for t in tags]
     assert all([set(t) <= set("ACGT") for t in tags]), "Non-ACGT tag."
+    cutlen = len(cutsite)
+    sites = enumerate_cut_sites(cutsite)
+    tp = TagPlan()
+    tp.ntags = len(tags)
+    tp.sites = sites
+    tp.cutlen = cutlen
+    tp.strip = tp.shift = False
+    if set(t[:cutlen] for t in tags) <= set(sites):
+        if len(sites) == 1:
+            tags = [t[cutlen:] for t in tags]       # one site: it is stripped from every tag
+            tp.strip = True
+        else:
+            tp.shift = True                         # several sites: tags stay whole, comparison starts AT the site
+    tp.tags = effective_set(tags, len(tags))
+    return tp
+
+
+def plan(barcodes, tags, cutsite, tagplan=None):
+    """Set-up half of find_tags_fastq (tagdigger_fun.py:198-233): same asserts in the same
+    order, same pattern lists, same offsets; the two tries become effective sets.
+    ``tagplan`` (from :func:`plan_tags` for the same tags and cut site) skips the tag half."""
+    assert all([set(b.upper()) <= set("ACGT") for b in barcodes]), "Non-ACGT barcode."
+    assert set(cutsite.upper()) <= set("ACGTNRYKMSWBDHV"), "Invalid cut site."
+    if tagplan is None:
+        assert all([set(t.upper()) <= set("ACGT") for t in tags]), "Non-ACGT tag."
+    cutsite = cutsite.upper()
     cutlen = len(cutsite)
     offsets = [len(b) + cutlen for b in barcodes]
     barnum = len(barcodes)
@@ -122,13 +153,11 @@ def plan(barcodes, tags, cutsite):
     barcut = [(b + site).upper() for site in sites for b in barcodes]
     p = CountPlan()
     p.barnum = barnum
-    p.ntags = len(tags)
-    p.bar = effective_set(barcut, barnum)
-    if set(t[:cutlen] for t in tags) <= set(sites):
-        if len(sites) == 1:
-            tags = [t[cutlen:] for t in tags]
-        else:
-            offsets = [o - cutlen for o in offsets]
+    p.bar = effective_set(barcut, barnum)           # barcode trie first, as in the reference (:219)
+    tp = tagplan if tagplan is not None else plan_tags(tags, cutsite)
+    p.ntags = tp.ntags
+    if tp.shift:
+        offsets = [o - cutlen for o in offsets]
     p.bar_tag_off = [offsets[r] for r in p.bar.index]
-    p.tags = effective_set(tags, len(tags))
+    p.tags = tp.tags
     return p
