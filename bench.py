@@ -60,7 +60,7 @@ class ClockSampler(object):
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
         except OSError:
             self.proc = None
@@ -207,6 +207,9 @@ def main():
             dist.all_reduce(matrix)
             eng.stream_wait(tstream)                # next step's memset after the all-reduce
 
+    # clocks are sampled over the warm-up and the timed steps (identical work; a timed region of
+    # tens of milliseconds alone would give nvidia-smi time for one or two samples)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     eng.sync()
@@ -215,7 +218,6 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     eng.timing_begin()
