@@ -64,11 +64,13 @@ class ClockSampler(object):
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, universal_newlines=True)
         except OSError:
             self.proc = None
+        if self.proc is not None:
+            time.sleep(0.3)            # nvidia-smi needs a moment before its first sample
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
