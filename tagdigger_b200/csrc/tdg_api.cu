@@ -174,9 +174,10 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
     }
     size_t max_grid = (size_t)per_sm * ctx->sm_count;
     size_t workers = max_grid * WARPS;      // every warp is an independent pipeline
-    // segments: runs of consecutive tiles handed to one warp; about 8 per warp for
-    // load balance, at most 64 tiles (the fix pass redoes whole segments)
-    size_t seg_tiles = tiles / (workers * 8);
+    // segments: runs of consecutive tiles handed to one warp; about 32 per warp so that the
+    // last, partly filled round of segments is a small part of the launch, at most 64 tiles
+    // (the fix pass redoes whole segments; each segment start costs one exact classification)
+    size_t seg_tiles = tiles / (workers * 32);
     if (seg_tiles < 1) seg_tiles = 1;
     if (seg_tiles > 64) seg_tiles = 64;
     if (ctx->force_seg_tiles) seg_tiles = ctx->force_seg_tiles;
