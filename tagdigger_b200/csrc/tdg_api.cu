@@ -379,7 +379,7 @@ int submit_piece(tdg_ctx *ctx, const uint8_t *bytes, size_t n, size_t cut, uint6
     size_t total = ctx->carry_len + cut;
     int nxt = (si + 1) % NSLOT;
     Slot &sn = ctx->slot[nxt];
-    if (total > 0) {
+    if (cut > 0) {      // the piece holds a line end: carried bytes + everything up to the cut form whole lines
         // the slot's previous kernel must be finished before its buffer is overwritten
         CK(cudaStreamWaitEvent(ctx->copy_stream, s.done, 0));
         if (ctx->carry_len) CK(cudaMemcpyAsync(s.dev, s.carry, ctx->carry_len, cudaMemcpyHostToDevice, ctx->copy_stream));

@@ -437,3 +437,47 @@ def test_tassel_tagcount_weights(tmp_path, monkeypatch):
         counting.find_tags_fastq(path, barcodes, tags, tassel_tagcount=True)
     with pytest.raises(ValueError):
         orc.find_tags_fastq(path, barcodes, tags, tassel_tagcount=True)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fuzz_byte_soup(seed):
+    """Random bytes over a small alphabet (bases, line ends of all kinds, FASTQ punctuation,
+    whitespace, NUL, a non-ASCII byte pair), random lengths around the kernel's tile and halo
+    sizes, one and several device chunks: bit-exact against the C oracle, totals and line
+    counts included."""
+    r = random.Random(1000 + seed)
+    eng = _native.Engine(0)
+    barcodes, tags = small_setup(r, nbar=5, ntag=10, tag_len=(4, 30))
+    p = matchset.plan(barcodes, tags, "TGCAG")
+    alphabet = [b"A", b"C", b"G", b"T"] * 6 + [b"\n"] * 3 + [b"\r", b"\r\n", b"@", b"+", b" ", b"\t", b"N", b"a", b"c",
+                                                          b"\x00", b"\x0b", "é".encode(), b"I", b"#"]
+    hits = [(r.choice(barcodes) + t).encode() for t in tags]
+    for _ in range(25):
+        n = r.choice([0, 1, 5, 127, 128, 129, 175, 176, 177, 5631, 5632, 5633, 5760, 11264, 17000, 40000]) + r.randint(0, 3)
+        parts = []
+        size = 0
+        while size < n:
+            piece = r.choice(hits) if r.random() < 0.08 else r.choice(alphabet)
+            parts.append(piece)
+            size += len(piece)
+        data = b"".join(parts)[:n]
+        try:
+            data.decode("utf-8")
+        except UnicodeDecodeError:
+            data = data[:-1]                       # do not cut the two-byte character in half
+        want, wtot, wlines = _oracle(data, barcodes, tags)
+        counting.load_plan(eng, p, nrows=p.barnum)
+        if data:
+            dev, nb = eng.upload(data)
+            eng.count_device(dev, nb)
+            got = eng.read_matrix().tolist()
+            tot = eng.file_totals()
+            eng.device_free(dev)
+            assert got == want, (seed, n)
+            assert tot[:3] == wtot and tot[3] == wlines
+        # the same bytes through the streaming entry point, cut at random places
+        cuts = sorted(r.sample(range(1, max(2, len(data))), min(3, max(0, len(data) - 1)))) if len(data) > 2 else []
+        tot2 = []
+        assert counting.find_tags_bytes(data, barcodes, tags, totals=tot2, pieces=cuts) == want
+        assert tot2[:3] == wtot
+    eng.close()
