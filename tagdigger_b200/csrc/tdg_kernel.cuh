@@ -544,13 +544,10 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 uint32_t x[4], gbad = 0;
 #pragma unroll
                 for (uint32_t k = 0; k < 4; k++) {
-                    x[k] = 0;
-                    if (g < 4 || 4 * g + k < nw) {           // past group 3 only the words that are needed
-                        uint32_t bad;
-                        x[k] = pack_word(wp[4 * g + k], bad);
-                        if (g == 0 && k == 0) bad &= 0xFFFFFFFFu << (8u * sh);   // bytes before the line start
-                        gbad |= bad;      // words past nw (groups 0-3) may flag too: V below ignores them
-                    }
+                    uint32_t bad;
+                    x[k] = pack_word(wp[4 * g + k], bad);
+                    if (g == 0 && k == 0) bad &= 0xFFFFFFFFu << (8u * sh);   // bytes before the line start
+                    gbad |= bad;          // words past nw may flag too: V below ignores them
                 }
                 if (gbad) gbm |= 1u << g;
                 P[g] = __byte_perm(__byte_perm(x[0], x[1], 0x0073), __byte_perm(x[2], x[3], 0x0073), 0x5410);
