@@ -214,6 +214,21 @@ int         tdg_split_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off,
 int         tdg_match_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, uint32_t n,
                             int32_t *row_out, int32_t *col_out);
 
+/* CSV output with host threads, for count matrices held as int32 arrays (writeCounts,
+ * tagdigger_fun.py:1100-1111, and writeDiploidGeno, :1144-1180; byte-identical to Python's
+ * csv.writer).  `header` is the finished header line including "\r\n"; row r starts with
+ * labels[label_off[r] .. label_off[r+1]) (the CSV-escaped sample name), followed by
+ * ",cell" for every column and "\r\n".  Genotype cells: '0' if only the marker's allele-0
+ * column is > 0, '1' if both, '2' if only allele 1, empty otherwise.  No context needed;
+ * on failure the message is returned by tdg_last_error(NULL). */
+int         tdg_write_counts_csv(const char *path, const int32_t *matrix, uint32_t rows, uint32_t cols,
+                                 const char *header, size_t header_len, const char *labels,
+                                 const uint64_t *label_off, int threads);
+int         tdg_write_geno_csv(const char *path, const int32_t *matrix, uint32_t rows, uint32_t cols,
+                               const uint32_t *col0, const uint32_t *col1, uint32_t nmarkers,
+                               const char *header, size_t header_len, const char *labels,
+                               const uint64_t *label_off, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TDG_LIB") or os.path.join(_HERE, "libtagdigger_b200.so")   # TDG_LIB: tuning builds (scripts/sweep.py)
-_SOURCES = ["tdg_api.cu", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h", "tdg_trim.cuh", "tdg_feed.h"]
+_SOURCES = ["tdg_api.cu", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h", "tdg_trim.cuh", "tdg_feed.h", "tdg_csv.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "20014,20011", "-shared"]
@@ -35,7 +35,7 @@ tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end
 tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
-tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch tdg_match_batch""".split()
+tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch tdg_match_batch tdg_write_counts_csv tdg_write_geno_csv""".split()
 
 
 class TdgError(RuntimeError):
@@ -122,6 +122,8 @@ def lib():
         "tdg_trim_batch": (i32, [vp, vp, vp, vp, vp, u32, vp]),
         "tdg_split_batch": (i32, [vp, vp, vp, u32, vp, u32, u32, vp, vp]),
         "tdg_match_batch": (i32, [vp, vp, vp, u32, vp, vp]),
+        "tdg_write_counts_csv": (i32, [ctypes.c_char_p, vp, u32, u32, ctypes.c_char_p, sz, ctypes.c_char_p, vp, i32]),
+        "tdg_write_geno_csv": (i32, [ctypes.c_char_p, vp, u32, u32, vp, vp, u32, ctypes.c_char_p, sz, ctypes.c_char_p, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -154,6 +156,54 @@ def limit_from_maxreads(maxreads):
     if lim < m:
         lim += 1
     return max(1, lim)
+
+
+def _csv_line(fields):
+    """One row as Python's csv.writer (default dialect) writes it, as bytes."""
+    import csv
+    import io
+    buf = io.StringIO(newline="")
+    csv.writer(buf).writerow(fields)
+    return buf.getvalue().encode("utf-8")
+
+
+def _csv_labels(names):
+    """CSV-escaped first fields of rows that have more fields after them."""
+    out = []
+    for n in names:
+        line = _csv_line([n, "x"])
+        out.append(line[:-len(b",x\r\n")])
+    blob = b"".join(out)
+    off = np.zeros(len(out) + 1, dtype=np.uint64)
+    if out:
+        np.cumsum([len(x) for x in out], out=off[1:])
+    return blob, off
+
+
+def write_counts_csv(path, matrix, samnames, tagnames, threads=8):
+    """writeCounts for an int32 ndarray [samples x tags]: native, multithreaded, byte-identical."""
+    m = np.ascontiguousarray(matrix, dtype=np.int32)
+    header = _csv_line([""] + list(tagnames))
+    blob, off = _csv_labels(samnames)
+    L = lib()
+    rc = L.tdg_write_counts_csv(os.fsencode(path), m.ctypes.data, m.shape[0], m.shape[1] if m.ndim == 2 else 0,
+                                header, len(header), blob, off.ctypes.data, threads)
+    if rc != TDG_OK:
+        raise OSError(L.tdg_last_error(None).decode())
+
+
+def write_geno_csv(path, matrix, samnames, markers, col0, col1, threads=8):
+    """writeDiploidGeno for an int32 ndarray: marker m is called from columns col0[m], col1[m]."""
+    m = np.ascontiguousarray(matrix, dtype=np.int32)
+    header = _csv_line([""] + list(markers))
+    blob, off = _csv_labels(samnames)
+    c0 = np.asarray(col0, dtype=np.uint32)
+    c1 = np.asarray(col1, dtype=np.uint32)
+    L = lib()
+    rc = L.tdg_write_geno_csv(os.fsencode(path), m.ctypes.data, m.shape[0], m.shape[1] if m.ndim == 2 else 0,
+                              c0.ctypes.data, c1.ctypes.data, len(c0), header, len(header), blob, off.ctypes.data, threads)
+    if rc != TDG_OK:
+        raise OSError(L.tdg_last_error(None).decode())
 
 
 class Engine(object):

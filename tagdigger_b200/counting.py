@@ -177,7 +177,7 @@ def global_rows(bckeys):
 
 
 def count_files(bckeys, tags, cutsite="TGCAG", maxreads=5e9, device=None, rank=0, world=1, reduce=None,
-                totals=None):
+                totals=None, as_array=False):
     """All files of a key (``readBarcodeKeyfile`` output) in one go: the batched
     form of the loop at tagdigger_script.py:123-128.  Every file counts straight
     into the GLOBAL sample rows of one device matrix, so the result equals
@@ -189,8 +189,11 @@ def count_files(bckeys, tags, cutsite="TGCAG", maxreads=5e9, device=None, rank=0
     engine)`` must sum the per-rank matrices in place (one NCCL all-reduce, see
     :func:`nccl_reduce`); integer sums make the result independent of ``world``.
 
-    Returns ``[sample names, count rows]``; ``totals`` (optional dict) receives
-    ``{file: [reads, with barcode and cut site, with tag]}`` for this rank's files."""
+    Returns ``[sample names, count rows]`` -- rows as lists of int like combineReadCounts, or,
+    with ``as_array=True``, as one int32 ndarray (hostio.writeCounts / writeDiploidGeno format
+    that with native threads; a 384 x 500,000 matrix is 768 MB as an array and several GB as
+    Python integers).  ``totals`` (optional dict) receives ``{file: [reads, with barcode and
+    cut site, with tag]}`` for this rank's files."""
     files = sorted(bckeys.keys())
     samples, rows = global_rows(bckeys)
     limit = _native.limit_from_maxreads(maxreads)
@@ -220,7 +223,8 @@ def count_files(bckeys, tags, cutsite="TGCAG", maxreads=5e9, device=None, rank=0
         if reduce is None:
             raise ValueError("count_files with world > 1 needs a reduce callable (see nccl_reduce)")
         reduce(eng.matrix_ptr(), len(samples), ntags, eng)
-    return [samples, eng.read_matrix().tolist()]
+    matrix = eng.read_matrix()
+    return [samples, matrix if as_array else matrix.tolist()]
 
 
 def assign_files(files, rank, world):

@@ -16,6 +16,7 @@
 
 #include "../../include/tagdigger_b200.h"
 #include "tdg_kernel.cuh"
+#include "tdg_csv.h"
 #include "tdg_feed.h"
 #include "tdg_tables.h"
 #include "tdg_trim.cuh"
@@ -1188,6 +1189,40 @@ int tdg_match_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, uint32_
     cudaFree(d);
     if (e != cudaSuccess) return fail(ctx, TDG_ERR_CUDA, std::string("tdg_match_batch: ") + cudaGetErrorString(e));
     if (e2 != cudaSuccess) return fail(ctx, TDG_ERR_CUDA, std::string("tdg_match_batch: ") + cudaGetErrorString(e2));
+    return TDG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// CSV output (host threads), csrc/tdg_csv.h.  No context needed: errors go to the
+// message returned by tdg_last_error(NULL).
+
+int tdg_write_counts_csv(const char *path, const int32_t *matrix, uint32_t rows, uint32_t cols, const char *header,
+                         size_t header_len, const char *labels, const uint64_t *label_off, int threads)
+{
+    if (!path || (!matrix && rows && cols) || !header || !label_off || (!labels && rows && label_off[rows] != label_off[0]))
+        return fail(nullptr, TDG_ERR_ARG, "null argument");
+    std::string why = tdg::write_table(path, header, header_len, rows, cols, labels, label_off, threads,
+                                       [=](char *p, uint32_t r, uint32_t c) { return tdg::put_int(p, matrix[(size_t)r * cols + c]); });
+    if (!why.empty()) return fail(nullptr, TDG_ERR_IO, why);
+    return TDG_OK;
+}
+
+int tdg_write_geno_csv(const char *path, const int32_t *matrix, uint32_t rows, uint32_t cols, const uint32_t *col0,
+                       const uint32_t *col1, uint32_t nmarkers, const char *header, size_t header_len, const char *labels,
+                       const uint64_t *label_off, int threads)
+{
+    if (!path || (!matrix && rows && cols) || !header || !label_off || (nmarkers && (!col0 || !col1)))
+        return fail(nullptr, TDG_ERR_ARG, "null argument");
+    for (uint32_t m = 0; m < nmarkers; m++)
+        if (col0[m] >= cols || col1[m] >= cols) return fail(nullptr, TDG_ERR_ARG, "marker column outside the matrix");
+    std::string why = tdg::write_table(path, header, header_len, rows, nmarkers, labels, label_off, threads,
+                                       [=](char *p, uint32_t r, uint32_t m) {
+                                           // writeDiploidGeno, tagdigger_fun.py:1160-1167
+                                           const bool a = matrix[(size_t)r * cols + col0[m]] > 0, b = matrix[(size_t)r * cols + col1[m]] > 0;
+                                           if (a || b) *p++ = a && b ? '1' : (a ? '0' : '2');
+                                           return p;
+                                       });
+    if (!why.empty()) return fail(nullptr, TDG_ERR_IO, why);
     return TDG_OK;
 }
 

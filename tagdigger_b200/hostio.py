@@ -604,11 +604,26 @@ def writeCounts(filename, counts, samnames, tagnames):
     csv default dialect, i.e. \\r\\n line ends (tagdigger_fun.py:1100-1111)."""
     assert len(samnames) == len(counts), "Length of samnames should be the same as length of counts."
     assert len(tagnames) == len(counts[0]), "Length of tagnames should be length of second dimension of counts."
+    if _is_int_array(counts):
+        # an int32 matrix straight from the device: multithreaded native formatter, same bytes
+        from . import _native
+        _native.write_counts_csv(filename, counts, samnames, tagnames)
+        return
     with open(filename, "w", newline="") as out:
         w = csv.writer(out)
         w.writerow([""] + tagnames)
         for name, row in zip(samnames, counts):
             w.writerow([name] + row)
+
+
+def _is_int_array(counts):
+    """True for a 2-D numpy integer array (the script keeps the device matrix in that form:
+    config 4's 192 M cells would be gigabytes of Python integers)."""
+    try:
+        import numpy as np
+    except ImportError:
+        return False
+    return isinstance(counts, np.ndarray) and counts.ndim == 2 and counts.dtype.kind in "iu"
 
 
 def extractMarkers(tagnames):
@@ -639,6 +654,12 @@ def writeDiploidGeno(filename, counts, samnames, tagnames):
     try:
         if not all(set(g[0]) <= {"0", "1"} for g in groups):
             raise Exception("All allele names must be '0' or '1'.")
+        if _is_int_array(counts):
+            from . import _native
+            columns = [(g[1][g[0].index("0")], g[1][g[0].index("1")]) for g in groups] if len(samnames) else []
+            _native.write_geno_csv(filename, counts, samnames, markers if columns else [],
+                                   [c[0] for c in columns], [c[1] for c in columns])
+            return None
         columns = None
         rows = []
         for sample, row in zip(samnames, counts):

@@ -132,7 +132,8 @@ def main(argv=None):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl")
         reduce = nccl_reduce
-    samples, counts = tdf.count_files(bckeys, tags[1], cutsite=cutsite, rank=rank, world=world, reduce=reduce)
+    samples, counts = tdf.count_files(bckeys, tags[1], cutsite=cutsite, rank=rank, world=world, reduce=reduce,
+                                      as_array=True)
     if rank == 0:
         tdf.writeCounts(args.outputcounts, counts, samples, tags[0])
         if args.outputgen is not None:
