@@ -6,6 +6,7 @@ asserts and return shape); the per-read loop runs on the GPU through
 reads on the CPU.
 """
 
+import ctypes
 import gzip
 import os
 
@@ -177,7 +178,7 @@ def global_rows(bckeys):
 
 
 def count_files(bckeys, tags, cutsite="TGCAG", maxreads=5e9, device=None, rank=0, world=1, reduce=None,
-                totals=None, as_array=False):
+                totals=None, as_array=False, gather=None):
     """All files of a key (``readBarcodeKeyfile`` output) in one go: the batched
     form of the loop at tagdigger_script.py:123-128.  Every file counts straight
     into the GLOBAL sample rows of one device matrix, so the result equals
@@ -187,7 +188,9 @@ def count_files(bckeys, tags, cutsite="TGCAG", maxreads=5e9, device=None, rank=0
     With ``world > 1`` (one process per GPU) the files are dealt to the ranks by
     size (largest first, to the least loaded rank) and ``reduce(ptr, rows, cols,
     engine)`` must sum the per-rank matrices in place (one NCCL all-reduce, see
-    :func:`nccl_reduce`); integer sums make the result independent of ``world``.
+    :func:`nccl_reduce`); integer sums make the result independent of ``world``.  When there are
+    fewer files than ranks, plain files are sharded by byte range instead (:func:`count_file_range`),
+    which needs ``gather(list_of_ints) -> list of every rank's list`` (:func:`dist_gather`).
 
     Returns ``[sample names, count rows]`` -- rows as lists of int like combineReadCounts, or,
     with ``as_array=True``, as one int32 ndarray (hostio.writeCounts / writeDiploidGeno format
@@ -212,7 +215,15 @@ def count_files(bckeys, tags, cutsite="TGCAG", maxreads=5e9, device=None, rank=0
     first = plans[files[0]]
     eng.set_tags(first.tags.patterns, first.tags.index, any_base=first.tags.any_base)
     eng.set_matrix(len(samples), ntags)
-    for f in assign_files(files, rank, world):
+    # Fewer files than GPUs: a plain (uncompressed) file is cut into one byte range per rank
+    # (cut at line ends); otherwise whole files are dealt to the ranks.
+    split = [f for f in files if world > 1 and len(files) < world and not _is_gz(f) and shardable(f, world)]
+    for f in split:
+        load_plan(eng, plans[f], row_of=rows[f], set_tags=False)
+        tot = count_file_range(eng, f, rank, world, limit, gather)
+        if totals is not None:
+            totals[f] = tot[:3]
+    for f in assign_files([f for f in files if f not in split], rank, world):
         p = plans[f]
         load_plan(eng, p, row_of=rows[f], set_tags=False)
         tot = _run_file(eng, f, limit)
@@ -225,6 +236,105 @@ def count_files(bckeys, tags, cutsite="TGCAG", maxreads=5e9, device=None, rank=0
         reduce(eng.matrix_ptr(), len(samples), ntags, eng)
     matrix = eng.read_matrix()
     return [samples, matrix if as_array else matrix.tolist()]
+
+
+SHARD_MIN_BYTES = 1 << 20     # files smaller than this per rank are not worth cutting up
+
+
+def shardable(f, world):
+    try:
+        return os.path.getsize(f) >= SHARD_MIN_BYTES * world
+    except OSError:
+        return False
+
+
+def range_bounds(path, world):
+    """Byte offsets b[0..world] that cut ``path`` into ``world`` ranges of whole lines: b[r] is
+    the position after the first '\n' at or beyond r * size / world (b[0] = 0, b[world] = size).
+    None when a nominal boundary is followed by no '\n' within 16 MiB (a file with lone-'\r' line
+    ends or giant lines: count it on one rank)."""
+    size = os.path.getsize(path)
+    bounds = [0]
+    with open(path, "rb") as fh:
+        for r in range(1, world):
+            pos = max(bounds[-1], size * r // world)
+            fh.seek(pos)
+            found = -1
+            scanned = 0
+            while scanned < (16 << 20):
+                block = fh.read(1 << 16)
+                if not block:
+                    break
+                k = block.find(b"\n")
+                if k >= 0:
+                    found = pos + scanned + k + 1
+                    break
+                scanned += len(block)
+            if found < 0:
+                return None
+            bounds.append(min(found, size))
+    bounds.append(size)
+    return bounds
+
+
+def count_file_range(eng, path, rank, world, limit, gather):
+    """One rank's share of a plain FASTQ file that is sharded across ``world`` GPUs.
+
+    The file is cut at line ends into one byte range per rank.  Which lines are sequence lines
+    depends on the line index from the start of the FILE (tagdigger_fun.py:250-254), so every
+    rank first counts the lines of its range on its GPU (``tdg_count_lines_device``: the scan
+    half of the kernel), the counts are exchanged (``gather``), and the range is then counted
+    with its true first line index (``tdg_count_device``).  ``maxreads`` works unchanged: read
+    indices are global.  Returns this rank's [reads, with barcode and cut site, with tag]."""
+    if gather is None:
+        raise ValueError("sharding a file across ranks needs a gather callable (see dist_gather)")
+    bounds = range_bounds(path, world)
+    ok = gather([0 if bounds is None else 1])
+    if not all(x[0] for x in ok):                       # every rank must take the same decision
+        bounds = None
+    if bounds is None:
+        tot = [0, 0, 0, 0]
+        if rank == 0:
+            tot = _run_file(eng, path, limit)
+        return tot
+    lo, hi = bounds[rank], bounds[rank + 1]
+    n = hi - lo
+    cap = (n + _native.TDG_TILE_BYTES - 1) // _native.TDG_TILE_BYTES * _native.TDG_TILE_BYTES + _native.TDG_HALO_BYTES
+    dev = eng.device_alloc(cap)
+    try:
+        piece = 256 << 20
+        host = eng.host_alloc(min(piece, max(n, 1)))
+        try:
+            view = (ctypes.c_ubyte * min(piece, max(n, 1))).from_address(host)
+            with open(path, "rb", buffering=0) as fh:
+                done = 0
+                while done < n:
+                    want = min(piece, n - done)
+                    got = os.preadv(fh.fileno(), [memoryview(view)[:want]], lo + done)
+                    if got <= 0:
+                        raise OSError("short read on " + path)
+                    eng.memcpy_h2d(dev + done, host, got)
+                    done += got
+        finally:
+            eng.host_free(host)
+        lines, _last = eng.count_lines_device(dev, n, 0, _native.TDG_PREV_NONE if rank == 0 else _native.TDG_PREV_LF)
+        every = gather([lines])
+        base = sum(x[0] for x in every[:rank])
+        eng.reset_file()
+        eng.count_device(dev, n, base, _native.TDG_PREV_NONE if rank == 0 else _native.TDG_PREV_LF, limit)
+        tot = eng.file_totals()
+    finally:
+        eng.device_free(dev)
+    print("{0} [bytes {1}-{2}]: Reads: {3} With barcode and cut site: {4} With tag: {5}".format(path, lo, hi, *tot[:3]))
+    return tot
+
+
+def dist_gather(values):
+    """all_gather of a short list of ints over the default torch.distributed group."""
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, list(values))
+    return out
 
 
 def assign_files(files, rank, world):

@@ -123,17 +123,18 @@ def main(argv=None):
     # one process per GPU under torchrun; a single process otherwise
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    reduce = None
+    reduce = gather = None
     if world > 1:
         import torch
         import torch.distributed as dist
-        from .counting import nccl_reduce
+        from .counting import dist_gather, nccl_reduce
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl")
         reduce = nccl_reduce
+        gather = dist_gather
     samples, counts = tdf.count_files(bckeys, tags[1], cutsite=cutsite, rank=rank, world=world, reduce=reduce,
-                                      as_array=True)
+                                      gather=gather, as_array=True)
     if rank == 0:
         tdf.writeCounts(args.outputcounts, counts, samples, tags[0])
         if args.outputgen is not None:

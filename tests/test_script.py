@@ -89,3 +89,25 @@ def test_batched_equals_per_file(in_tmp):
     per_file = {f: counting.find_tags_fastq(f, bckeys[f][0], tags[1]) for f in bckeys}
     want = hostio.combineReadCounts(per_file, bckeys)
     assert counting.count_files(bckeys, tags[1]) == want
+
+
+def test_range_bounds_cut_at_line_ends(tmp_path):
+    """Byte ranges for sharding one file across ranks: whole lines, covering the file, for LF
+    and CRLF; None when no line end follows a nominal boundary (lone-CR files)."""
+    import random
+    r = random.Random(4)
+    for newline in (b"\n", b"\r\n"):
+        lines = [bytes(r.choice(b"ACGT@+I") for _ in range(r.randint(0, 200))) for _ in range(3000)]
+        data = newline.join(lines) + newline
+        p = tmp_path / "x.fq"
+        p.write_bytes(data)
+        for world in (2, 3, 8):
+            b = counting.range_bounds(str(p), world)
+            assert b[0] == 0 and b[-1] == len(data) and b == sorted(b) and len(b) == world + 1
+            for cut in b[1:-1]:
+                assert data[cut - 1:cut] == b"\n"
+    p.write_bytes(b"\r".join(lines))
+    assert counting.range_bounds(str(p), 4) is None
+    p.write_bytes(b"ACGT\n")
+    assert counting.range_bounds(str(p), 3) == [0, 5, 5, 5]
+    assert not counting.shardable(str(p), 2)
