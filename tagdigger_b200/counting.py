@@ -264,6 +264,7 @@ def range_bounds(path, world):
             while scanned < (16 << 20):
                 block = fh.read(1 << 16)
                 if not block:
+                    found = size                   # end of file: the tail belongs to the previous range
                     break
                 k = block.find(b"\n")
                 if k >= 0:
