@@ -93,7 +93,7 @@ def test_batched_equals_per_file(in_tmp):
 
 def test_range_bounds_cut_at_line_ends(tmp_path):
     """Byte ranges for sharding one file across ranks: whole lines, covering the file, for LF
-    and CRLF; None when no line end follows a nominal boundary (lone-CR files)."""
+    and CRLF; a file without any '\\n' (lone-CR line ends) goes to rank 0 whole."""
     import random
     r = random.Random(4)
     for newline in (b"\n", b"\r\n"):
@@ -106,8 +106,9 @@ def test_range_bounds_cut_at_line_ends(tmp_path):
             assert b[0] == 0 and b[-1] == len(data) and b == sorted(b) and len(b) == world + 1
             for cut in b[1:-1]:
                 assert data[cut - 1:cut] == b"\n"
-    p.write_bytes(b"\r".join(lines))
-    assert counting.range_bounds(str(p), 4) is None
+    p.write_bytes(b"\r".join(lines))                  # lone-CR file: no '\n' to cut at, rank 0 takes it all
+    n = len(b"\r".join(lines))
+    assert counting.range_bounds(str(p), 4) == [0, n, n, n, n]
     p.write_bytes(b"ACGT\n")
     assert counting.range_bounds(str(p), 3) == [0, 5, 5, 5]
     assert not counting.shardable(str(p), 2)
