@@ -9,6 +9,7 @@ reads on the CPU.
 import ctypes
 import gzip
 import os
+import zlib
 
 import numpy as np
 
@@ -41,6 +42,17 @@ def load_plan(eng, p, row_of=None, nrows=None, set_tags=True):
     eng.begin_file(p.bar.patterns, rows, p.bar_tag_off, any_base=p.bar.any_base)
 
 
+def _gzip_exception(message):
+    """The exception gzip.open(...).read() of the reference (tagdigger_fun.py:240-241) raises for
+    the same defect: EOFError for a stream that stops early, zlib.error for invalid deflate data,
+    BadGzipFile for bad headers and CRC / length mismatches."""
+    if "unexpected end of file" in message:
+        return EOFError("Compressed file ended before the end-of-stream marker was reached (%s)" % message)
+    if "invalid" in message or "compressed data error" in message:
+        return zlib.error("Error -3 while decompressing data: %s" % message)
+    return gzip.BadGzipFile(message)
+
+
 def _is_gz(name):
     return name[-2:].lower() == "gz"            # tagdigger_fun.py:240
 
@@ -54,7 +66,7 @@ def _run_file(eng, fqfile, limit):
         return eng.count_file(fqfile, _is_gz(fqfile), limit)
     except _native.TdgError as e:
         if e.code == _native.TDG_ERR_GZIP:
-            raise gzip.BadGzipFile(e.message)
+            raise _gzip_exception(e.message)
         if e.code == _native.TDG_ERR_IO:
             raise OSError(e.message)
         raise

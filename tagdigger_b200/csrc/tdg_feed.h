@@ -7,11 +7,16 @@
 //   - BGZF files (bgzip: gzip members of <= 64 KiB that carry their own size in a 'BC'
 //     extra field): members are found without inflating and inflated in parallel, each
 //     straight into its place in the chunk, CRC32 checked;
-//   - any other gzip stream (a single member cannot be inflated in parallel): zlib's
-//     gzread on one thread, which also handles concatenated members like Python's gzip.
+//   - any other gzip file of some size: speculative parallel inflate of the one deflate stream
+//     (tdg_pgz.h: block-start search, 16-bit marker symbols for the unknown window, chained and
+//     CRC-checked);
+//   - small gzip files, one I/O thread, and everything tdg_pgz.h declines to judge (corrupt or
+//     unusual streams): zlib's gzread on one thread, which also handles concatenated members
+//     like Python's gzip.
 // A BGZF file that turns into ordinary gzip members half way is continued sequentially.
 #pragma once
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -24,11 +29,13 @@
 #include <thread>
 #include <vector>
 
+#include "tdg_pgz.h"
+
 namespace tdg {
 
 class Feeder {
 public:
-    enum Mode { PLAIN, PLAIN_SEQ, BGZF, GZ };
+    enum Mode { PLAIN, PLAIN_SEQ, BGZF, GZ, PGZ };
 
     ~Feeder() { close(); }
 
@@ -56,6 +63,24 @@ public:
             uint32_t csize = 0, hlen = 0;
             if (n >= 18 && bgzf_header(head, (size_t)n, csize, hlen)) mode_ = BGZF;
         }
+        if (mode_ == GZ && regular && threads_ > 1) {
+            // parallel inflate of an ordinary gzip stream (TDG_PGZ_MIN: smallest file, TDG_PGZ_CHUNK:
+            // nominal compressed bytes per thread and round; both for tests)
+            uint64_t min_size = (uint64_t)4 << 20;
+            size_t pchunk = (size_t)2 << 20;
+            if (const char *e = getenv("TDG_PGZ_MIN")) min_size = strtoull(e, nullptr, 10);
+            if (const char *e = getenv("TDG_PGZ_CHUNK")) pchunk = (size_t)strtoull(e, nullptr, 10);
+            if (size_ >= min_size && size_ > 18) {
+                void *m = mmap(nullptr, (size_t)size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+                if (m != MAP_FAILED) {
+                    map_ = (const uint8_t *)m;
+                    madvise(m, (size_t)size_, MADV_SEQUENTIAL);
+                    pgz_.reset(new pgz::Reader());
+                    if (pgz_->open(map_, (size_t)size_, threads_, pchunk)) mode_ = PGZ;
+                    else unmap();
+                }
+            }
+        }
         if (mode_ == GZ) return open_gz(0);
         return 0;
     }
@@ -71,6 +96,7 @@ public:
         case PLAIN: return fill_plain(p, cap);
         case PLAIN_SEQ: return fill_seq(p, cap);
         case BGZF: return fill_bgzf(p, cap);
+        case PGZ: return fill_pgz(p, cap);
         default: return fill_gz(p, cap);
         }
     }
@@ -79,6 +105,7 @@ public:
     {
         if (zf_) gzclose(zf_);
         zf_ = nullptr;
+        unmap();
         if (fd_ >= 0) ::close(fd_);
         fd_ = -1;
     }
@@ -195,7 +222,14 @@ private:
                 const char *m = gzerror(zf_, &en);
                 return fail(-6, "gzip error in " + path_ + ": " + (m ? m : "?"));
             }
-            if (r == 0) break;
+            if (r == 0) {
+                // a stream that stops before its end-of-stream marker or inside its trailer: gzread
+                // hands out what it has and only notes Z_BUF_ERROR; Python's gzip raises EOFError
+                int en = 0;
+                const char *m = gzerror(zf_, &en);
+                if (en == Z_BUF_ERROR) return fail(-6, "gzip error in " + path_ + ": " + (m && *m ? m : "unexpected end of file"));
+                break;
+            }
             got += (size_t)r;
             if (gz_first_) {
                 gz_first_ = false;
@@ -203,6 +237,33 @@ private:
             }
         }
         return (long long)got;
+    }
+
+    void unmap()
+    {
+        pgz_.reset();
+        if (map_) munmap(const_cast<uint8_t *>(map_), (size_t)size_);
+        map_ = nullptr;
+    }
+
+    long long fill_pgz(uint8_t *p, size_t cap)
+    {
+        long long r;
+        try {
+            r = pgz_->read(p, cap);
+        } catch (const std::bad_alloc &) {
+            return fail(-3, "out of memory while inflating " + path_);
+        }
+        if (r >= 0) return r;
+        if (r == -2) return fail(-6, "gzip error in " + path_ + ": incorrect data check");
+        // something tdg_pgz.h leaves to zlib: continue sequentially at the offset reached
+        const uint64_t at = pgz_->delivered();
+        unmap();
+        mode_ = GZ;
+        int rc = open_gz(at);
+        if (rc) return rc;
+        gz_first_ = false;
+        return fill_gz(p, cap);
     }
 
     // make sure cbuf_ holds file bytes [cpos_ + at, cpos_ + at + need) if the file has them
@@ -315,6 +376,9 @@ private:
     size_t cused_ = 0;           // bytes of cbuf_ already turned into output
     uint64_t delivered_ = 0;     // uncompressed bytes handed out so far
     std::vector<Block> blocks_;
+    // ordinary gzip, inflated in parallel
+    const uint8_t *map_ = nullptr;
+    std::unique_ptr<pgz::Reader> pgz_;
 };
 
 }  // namespace tdg

@@ -11,13 +11,13 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "native", "feed_check.cpp")
 _LIB = os.path.join(_HERE, "native", "libfeed_check.so")
-_DEP = os.path.join(os.path.dirname(_HERE), "tagdigger_b200", "csrc", "tdg_feed.h")
+_DEPS = [os.path.join(os.path.dirname(_HERE), "tagdigger_b200", "csrc", h) for h in ("tdg_feed.h", "tdg_pgz.h")]
 
 
 def build(force=False):
-    if not force and os.path.exists(_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(_LIB) for d in (_SRC, _DEP)):
+    if not force and os.path.exists(_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(_LIB) for d in [_SRC] + _DEPS):
         return _LIB
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", _LIB, _SRC, "-lz"])
+    subprocess.check_call(["g++", "-O3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", _LIB, _SRC, "-lz"])
     return _LIB
 
 
@@ -27,7 +27,7 @@ class FeedError(RuntimeError):
         self.code = code
 
 
-MODES = {0: "plain", 1: "plain_seq", 2: "bgzf", 3: "zlib"}
+MODES = {0: "plain", 1: "plain_seq", 2: "bgzf", 3: "zlib", 4: "pgzip"}
 
 
 def read_file(path, gz, chunk=1 << 20, cap=None):

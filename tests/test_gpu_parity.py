@@ -234,6 +234,45 @@ def test_files_plain_and_gzip(tmp_path):
         counting.find_tags_fastq(str(tmp_path / "missing.fq"), bcs, tags)
 
 
+def test_gzip_inflated_in_parallel(tmp_path, monkeypatch):
+    """Ordinary gzip files go through the speculative parallel inflater (csrc/tdg_pgz.h): same
+    counts as the oracle on the uncompressed bytes; damaged files raise what gzip.open raises."""
+    import zlib
+    monkeypatch.setenv("TDG_PGZ_MIN", "0")
+    monkeypatch.setenv("TDG_PGZ_CHUNK", "100000")
+    monkeypatch.setenv("TDG_IO_THREADS", "8")
+    rng = np.random.default_rng(31)
+    bcs = synth.make_barcodes(24, rng)
+    _, _, seqs = synth.make_marker_pairs(200, rng)
+    tags = [s for p in seqs for s in p]
+    fq, _ = synth.make_fastq(120000, bcs, tags, rng)
+    want, wtot, _ = _oracle(fq, bcs, tags)
+    cut = fq.index(b"\n", len(fq) // 3) + 1
+    blobs = {"l1.fq.gz": gzip.compress(fq, 1), "l9.fq.gz": gzip.compress(fq, 9),
+             "members.fq.gz": gzip.compress(fq[:cut], 6) + gzip.compress(b"") + gzip.compress(fq[cut:], 4) + b"\0" * 100}
+    for name, blob in blobs.items():
+        path = str(tmp_path / name)
+        with open(path, "wb") as fh:
+            fh.write(blob)
+        tot = []
+        assert counting.find_tags_fastq(path, bcs, tags, totals=tot) == want, name
+        assert tot == wtot
+        tot = []
+        assert counting.find_tags_fastq(path, bcs, tags, maxreads=50000, totals=tot) == _oracle(fq, bcs, tags, maxreads=50000)[0]
+    good = blobs["l9.fq.gz"]
+    bad = bytearray(good)
+    bad[len(bad) // 2] ^= 0x40
+    for name, blob, exc in (("trunc.gz", good[:len(good) // 2], EOFError), ("crc.gz", good[:-8] + b"\0" * 8, gzip.BadGzipFile),
+                            ("flip.gz", bytes(bad), (zlib.error, gzip.BadGzipFile))):
+        path = str(tmp_path / name)
+        with open(path, "wb") as fh:
+            fh.write(blob)
+        with pytest.raises(exc):
+            gzip.open(path, "rb").read()                  # the reference's reader
+        with pytest.raises(exc):
+            counting.find_tags_fastq(path, bcs, tags)
+
+
 def test_small_chunks_force_many_pieces():
     """A context with tiny chunk_bytes: every piece boundary lands mid-line."""
     rng = np.random.default_rng(8)
