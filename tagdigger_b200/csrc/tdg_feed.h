@@ -43,7 +43,7 @@ public:
     int open(const char *path, bool gz)
     {
         path_ = path;
-        threads_ = 8;
+        threads_ = 16;
         if (const char *e = getenv("TDG_IO_THREADS")) threads_ = std::max(1, atoi(e));
         unsigned hw = std::thread::hardware_concurrency();
         if (hw && threads_ > (int)hw) threads_ = (int)hw;
@@ -366,7 +366,7 @@ private:
 
     std::string path_, err_;
     Mode mode_ = PLAIN;
-    int fd_ = -1, threads_ = 8;
+    int fd_ = -1, threads_ = 16;
     uint64_t size_ = 0, pos_ = 0;
     gzFile zf_ = nullptr;
     bool gz_first_ = true;
