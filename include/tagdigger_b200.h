@@ -205,6 +205,41 @@ int         tdg_split_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off,
                             const uint32_t *bar_len, uint32_t nbar, uint32_t cutlen,
                             int32_t *bar_out, int32_t *slice2);
 
+/* Streaming barcode splitter: the loop of barcodeSplitter (tagdigger_fun.py:1327-1363) for one
+ * block of raw, uncompressed FASTQ bytes, entirely on the device -- universal-newline line
+ * ends, strip() of the four lines, barcode lookup (:1333), findAdapterSeq (:1337-1339), the
+ * Python slices sequence[slice1:slice2] / quality[slice1:slice2] (:1346,:1351), and the bytes
+ * each barcode's output file gains, in input order.
+ * tdg_split_begin: the barcode strings (appended to the first line, :1345) and the cut-site
+ * length; needs tdg_begin_file (barcode+cutsite table, rows = barcode indices) and
+ * tdg_set_trim.
+ * tdg_split_block: `bytes` (host, n <= 1 GiB) must start at a record boundary; final_block
+ * != 0 when the file ends with it (a last line without terminator is then a line).  At most
+ * max_records records are taken.  *n_records = complete records handled, *consumed = bytes
+ * they span (the caller carries the rest over to the front of its next block).
+ * *needs_host = 1: some record has a non-ASCII byte in its sequence or quality line
+ * (str.upper() and character indices are Python's then); nothing was produced and the
+ * caller handles bytes[0 .. consumed) itself.  Otherwise out[out_off[b] .. out_off[b+1]) are
+ * the bytes to append to barcode b's file and flags[r] = 1 (barcode and cut site found)
+ * | 2 (clipped on the 3' end) for every record; the three pointers are pinned host memory
+ * owned by the context, valid until the next call. */
+int         tdg_split_begin(tdg_ctx *ctx, const char *barcodes, const uint32_t *bar_off, uint32_t nbar,
+                            uint32_t cutlen);
+int         tdg_split_block(tdg_ctx *ctx, const uint8_t *bytes, size_t n, int final_block,
+                            uint64_t max_records, uint64_t *n_records, uint64_t *consumed,
+                            int *needs_host, const uint8_t **out, const uint64_t **out_off,
+                            const uint8_t **flags);
+
+/* The host feed by itself (what tdg_count_file reads through): the uncompressed bytes of a
+ * plain, gzip or BGZF file -- gzip.open(f, 'rt') / open(f, 'r') of tagdigger_fun.py:240-243
+ * and :1316-1319 -- with parallel pread / parallel inflate on host threads (TDG_IO_THREADS).
+ * No context; errors via tdg_last_error(NULL).  tdg_feed_read returns the bytes written to
+ * dst (0 = end of file) or a negative TDG_ERR_* code. */
+typedef struct tdg_feed tdg_feed;
+int         tdg_feed_open(tdg_feed **out, const char *path, int gz);
+long long   tdg_feed_read(tdg_feed *feed, void *dst, size_t cap);
+void        tdg_feed_close(tdg_feed *feed);
+
 /* Per-read results of the matcher for n sequence lines given as HOST buffers (stripped;
  * case is folded on the device): row_out[i] = the barcode row (sequence_index_lookup on
  * barcuttree, tagdigger_fun.py:257) or -1, col_out[i] = the tag column (:260-261) or -1.

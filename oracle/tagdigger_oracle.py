@@ -389,10 +389,11 @@ def find_adapter_seq(sequence, table, fullsite0, fullsite1, searchstart):
     return hit1 + len(fullsite1)
 
 
-def split_records(lines, barcodes, cutsite, adapter, maxreads=500000000):
+def split_records(lines, barcodes, cutsite, adapter, maxreads=500000000, every=False):
     """Loop of barcodeSplitter (tagdigger_fun.py:1328-1363) as a generator of
     (barcode index, 4 output lines, slice2 or 999) for every read that matches
-    a barcode; used to check trim decisions read by read."""
+    a barcode; used to check trim decisions read by read.  every=True: reads without
+    a barcode are reported too, as (-1, None, 999)."""
     if not set(cutsite) <= set(BASES):
         raise AssertionError("Only ACGT cut sites allowed.")
     pats = barcode_patterns(barcodes, cutsite)
@@ -422,5 +423,7 @@ def split_records(lines, barcodes, cutsite, adapter, maxreads=500000000):
                 head = c1 + barcodes[b]
                 yield b, [head, seq[s1:cut], "+" if c2 == "+" else head,
                           qual[s1:cut]], s2
+            elif every:
+                yield -1, None, 999
             if nreads >= maxreads:
                 break

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TDG_LIB") or os.path.join(_HERE, "libtagdigger_b200.so")   # TDG_LIB: tuning builds (scripts/sweep.py)
-_SOURCES = ["tdg_api.cu", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h", "tdg_trim.cuh", "tdg_feed.h", "tdg_pgz.h", "tdg_csv.h"]
+_SOURCES = ["tdg_api.cu", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h", "tdg_trim.cuh", "tdg_split.cuh", "tdg_feed.h", "tdg_pgz.h", "tdg_csv.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "20014,20011", "-shared"]
@@ -35,7 +35,7 @@ tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end
 tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
-tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch tdg_match_batch tdg_write_counts_csv tdg_write_geno_csv""".split()
+tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch tdg_split_begin tdg_split_block tdg_feed_open tdg_feed_read tdg_feed_close tdg_match_batch tdg_write_counts_csv tdg_write_geno_csv""".split()
 
 
 class TdgError(RuntimeError):
@@ -121,6 +121,12 @@ def lib():
         "tdg_set_trim": (i32, [vp, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, u32, vp, vp, vp, vp, vp, vp]),
         "tdg_trim_batch": (i32, [vp, vp, vp, vp, vp, u32, vp]),
         "tdg_split_batch": (i32, [vp, vp, vp, u32, vp, u32, u32, vp, vp]),
+        "tdg_split_begin": (i32, [vp, vp, vp, u32, u32]),
+        "tdg_split_block": (i32, [vp, vp, sz, i32, u64, ctypes.POINTER(u64), ctypes.POINTER(u64), ctypes.POINTER(i32),
+                                  ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]),
+        "tdg_feed_open": (i32, [ctypes.POINTER(vp), ctypes.c_char_p, i32]),
+        "tdg_feed_read": (ctypes.c_longlong, [vp, vp, sz]),
+        "tdg_feed_close": (None, [vp]),
         "tdg_match_batch": (i32, [vp, vp, vp, u32, vp, vp]),
         "tdg_write_counts_csv": (i32, [ctypes.c_char_p, vp, u32, u32, ctypes.c_char_p, sz, ctypes.c_char_p, vp, i32]),
         "tdg_write_geno_csv": (i32, [ctypes.c_char_p, vp, u32, u32, vp, vp, u32, ctypes.c_char_p, sz, ctypes.c_char_p, vp, i32]),
@@ -417,6 +423,33 @@ class Engine(object):
                                          cutlen, bar.ctypes.data, cut.ctypes.data))
         return bar, cut
 
+    def split_begin(self, barcodes, cutlen):
+        """Barcode strings and cut-site length for split_block (after begin_file and set_trim)."""
+        blob, off = _csr(list(barcodes), np.uint32)
+        self._ck(self._L.tdg_split_begin(self._h, blob, off.ctypes.data, len(barcodes), cutlen))
+        self._split_nbar = len(barcodes)
+
+    def split_block(self, ptr, n, final, max_records):
+        """One block of raw FASTQ bytes at host address ``ptr`` through the streaming splitter.
+        Returns (records, consumed bytes, needs_host, pieces, flags): pieces[b] is a uint8 array
+        (a view of pinned memory, valid until the next call) to append to barcode b's file,
+        flags a uint8 array per record (1 barcode found | 2 clipped); both None when needs_host."""
+        u64, vp = ctypes.c_uint64, ctypes.c_void_p
+        nrec, used, host = u64(0), u64(0), ctypes.c_int(0)
+        out, off, flags = vp(), vp(), vp()
+        self._ck(self._L.tdg_split_block(self._h, ptr, n, 1 if final else 0, min(int(max_records), (1 << 64) - 1),
+                                         ctypes.byref(nrec), ctypes.byref(used), ctypes.byref(host), ctypes.byref(out),
+                                         ctypes.byref(off), ctypes.byref(flags)))
+        if host.value or not out.value:
+            return nrec.value, used.value, bool(host.value), None, None
+        nbar = self._split_nbar
+        offs = np.ctypeslib.as_array(ctypes.cast(off, ctypes.POINTER(u64)), shape=(nbar + 1,))
+        total = int(offs[nbar])
+        data = np.ctypeslib.as_array(ctypes.cast(out, ctypes.POINTER(ctypes.c_uint8)), shape=(max(total, 1),))
+        pieces = [data[int(offs[b]):int(offs[b + 1])] for b in range(nbar)]
+        fl = np.ctypeslib.as_array(ctypes.cast(flags, ctypes.POINTER(ctypes.c_uint8)), shape=(max(nrec.value, 1),))[:nrec.value]
+        return nrec.value, used.value, False, pieces, fl
+
     def match_batch(self, seqs):
         """seqs: list of stripped sequence lines (bytes/str).  Returns (row, col) arrays, -1 = no match."""
         raw = [x.encode("utf-8") if isinstance(x, str) else bytes(x) for x in seqs]
@@ -428,3 +461,33 @@ class Engine(object):
         col = np.empty(len(raw), dtype=np.int32)
         self._ck(self._L.tdg_match_batch(self._h, blob, off.ctypes.data, len(raw), row.ctypes.data, col.ctypes.data))
         return row, col
+
+
+class Feed:
+    """The host feed on its own (csrc/tdg_feed.h): uncompressed bytes of a plain, gzip or BGZF
+    file, read / inflated by host threads straight into caller memory."""
+
+    def __init__(self, path, gz):
+        self._L = lib()
+        self._h = ctypes.c_void_p()
+        rc = self._L.tdg_feed_open(ctypes.byref(self._h), os.fsencode(path), 1 if gz else 0)
+        if rc != TDG_OK:
+            raise TdgError(rc, self._L.tdg_last_error(None).decode())
+
+    def read_into(self, ptr, cap):
+        """Up to ``cap`` bytes to host address ``ptr``; 0 at the end of the file."""
+        r = self._L.tdg_feed_read(self._h, ptr, cap)
+        if r < 0:
+            raise TdgError(int(r), self._L.tdg_last_error(None).decode())
+        return int(r)
+
+    def close(self):
+        if self._h.value:
+            self._L.tdg_feed_close(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

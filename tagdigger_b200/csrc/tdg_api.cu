@@ -20,6 +20,7 @@
 #include "tdg_feed.h"
 #include "tdg_tables.h"
 #include "tdg_trim.cuh"
+#include "tdg_split.cuh"
 
 static_assert(TDG_HALO_BYTES >= tdg::HALO, "the allocation slack promised by the header must cover the kernel halo");
 
@@ -93,6 +94,17 @@ struct tdg_ctx {
     tdg::TrimArgs trim;          // device pointers into d_trim
     uint32_t trim_nbar = 0;
     bool have_trim = false;
+
+    // streaming splitter (tdg_split_begin / tdg_split_block): growable device and pinned buffers
+    struct Grow {
+        void *p = nullptr;
+        size_t cap = 0;
+        bool host = false;
+    };
+    Grow sp_in, sp_tiles, sp_ends, sp_rec, sp_flags, sp_sums, sp_base, sp_out, sp_tabs;      // device
+    Grow sp_hout, sp_hflags, sp_hbase;                                                          // pinned host
+    uint32_t sp_nbar = 0, sp_cutlen = 0;
+    bool have_split = false;
 
     // pinned buffers of tdg_count_file (kept between files: pinning 192 MiB costs ~0.1 s)
     uint8_t *file_buf[3] = {nullptr, nullptr, nullptr};
@@ -524,6 +536,11 @@ void tdg_destroy(tdg_ctx *ctx)
         if (ctx->d_state) cudaFree(ctx->d_state);
         if (ctx->d_totals) cudaFree(ctx->d_totals);
         if (ctx->d_trim) cudaFree(ctx->d_trim);
+        for (tdg_ctx::Grow *g : {&ctx->sp_in, &ctx->sp_tiles, &ctx->sp_ends, &ctx->sp_rec, &ctx->sp_flags, &ctx->sp_sums,
+                                 &ctx->sp_base, &ctx->sp_out, &ctx->sp_tabs})
+            if (g->p) cudaFree(g->p);
+        for (tdg_ctx::Grow *g : {&ctx->sp_hout, &ctx->sp_hflags, &ctx->sp_hbase})
+            if (g->p) cudaFreeHost(g->p);
         if (ctx->d_replicas) cudaFree(ctx->d_replicas);
         for (int i = 0; i < 3; i++)
             if (ctx->file_buf[i]) cudaFreeHost(ctx->file_buf[i]);
@@ -1146,6 +1163,216 @@ int tdg_split_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, uint32_
     if (e2 != cudaSuccess) return fail(ctx, TDG_ERR_CUDA, std::string("tdg_split_batch: ") + cudaGetErrorString(e2));
     return TDG_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Streaming barcode splitter, csrc/tdg_split.cuh
+
+namespace {
+
+int grow(tdg_ctx *ctx, tdg_ctx::Grow &g, size_t need, bool host)
+{
+    if (need <= g.cap) return TDG_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (g.p) {
+        if (g.host) cudaFreeHost(g.p); else cudaFree(g.p);
+        g.p = nullptr;
+        g.cap = 0;
+    }
+    const size_t cap = need + need / 4 + 4096;
+    cudaError_t e = host ? cudaHostAlloc(&g.p, cap, cudaHostAllocDefault) : cudaMalloc(&g.p, cap);
+    if (e != cudaSuccess) {
+        g.p = nullptr;
+        return fail(ctx, TDG_ERR_NOMEM, std::string("splitter buffer of ") + std::to_string(cap) + " bytes: " + cudaGetErrorString(e));
+    }
+    g.cap = cap;
+    g.host = host;
+    return TDG_OK;
+}
+
+}  // namespace
+
+int tdg_split_begin(tdg_ctx *ctx, const char *barcodes, const uint32_t *bar_off, uint32_t nbar, uint32_t cutlen)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    ctx->have_split = false;
+    if (!ctx->have_trim) return fail(ctx, TDG_ERR_STATE, "tdg_set_trim has not been called");
+    if (!ctx->have_bar) return fail(ctx, TDG_ERR_STATE, "tdg_begin_file has not been called");
+    if (!bar_off || (!barcodes && nbar && bar_off[nbar] != bar_off[0])) return fail(ctx, TDG_ERR_ARG, "null argument");
+    if (nbar == 0 || nbar > 8192) return fail(ctx, TDG_ERR_ARG, "tdg_split_begin: between 1 and 8192 barcodes");
+    if (nbar != ctx->trim_nbar || ctx->max_row >= nbar)
+        return fail(ctx, TDG_ERR_ARG, "barcode table, trim tables and barcode list disagree on the number of barcodes");
+    for (uint32_t i = 0; i < nbar; i++)
+        if (bar_off[i + 1] < bar_off[i]) return fail(ctx, TDG_ERR_ARG, "offsets must be non-decreasing");
+    CK(cudaSetDevice(ctx->device));
+    // one blob: bar_off [nbar+1], bar_len [nbar], strings
+    const size_t o_len = (nbar + 1) * sizeof(uint32_t), o_str = o_len + nbar * sizeof(uint32_t);
+    const size_t nstr = bar_off[nbar] - bar_off[0];
+    std::vector<uint8_t> blob(o_str + nstr + 16);
+    uint32_t *po = (uint32_t *)blob.data(), *pl = (uint32_t *)(blob.data() + o_len);
+    for (uint32_t i = 0; i <= nbar; i++) po[i] = bar_off[i] - bar_off[0];
+    for (uint32_t i = 0; i < nbar; i++) pl[i] = bar_off[i + 1] - bar_off[i];
+    if (nstr) memcpy(blob.data() + o_str, barcodes + bar_off[0], nstr);
+    rc = grow(ctx, ctx->sp_tabs, blob.size(), false);
+    if (rc) return rc;
+    CK(cudaMemcpy(ctx->sp_tabs.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    ctx->sp_nbar = nbar;
+    ctx->sp_cutlen = cutlen;
+    ctx->have_split = true;
+    return TDG_OK;
+}
+
+int tdg_split_block(tdg_ctx *ctx, const uint8_t *bytes, size_t n, int final_block, uint64_t max_records,
+                    uint64_t *n_records, uint64_t *consumed, int *needs_host, const uint8_t **out,
+                    const uint64_t **out_off, const uint8_t **flags)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!ctx->have_split || !ctx->have_trim || !ctx->have_bar) return fail(ctx, TDG_ERR_STATE, "tdg_split_begin has not been called");
+    if (!n_records || !consumed || !needs_host || !out || !out_off || !flags || (!bytes && n)) return fail(ctx, TDG_ERR_ARG, "null argument");
+    if (n > ((size_t)1 << 30)) return fail(ctx, TDG_ERR_ARG, "tdg_split_block: at most 1 GiB per block");
+    *n_records = 0;
+    *consumed = 0;
+    *needs_host = 0;
+    *out = nullptr;
+    *out_off = nullptr;
+    *flags = nullptr;
+    if (n == 0 || max_records == 0) return TDG_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint32_t nbar = ctx->sp_nbar;
+
+    // ---- the block, and its line ends
+    const uint32_t n_tiles = (uint32_t)((n + tdg::SPLIT_TILE_BYTES - 1) / tdg::SPLIT_TILE_BYTES);
+    if ((rc = grow(ctx, ctx->sp_in, round_up(n, 16) + 16, false))) return rc;
+    if ((rc = grow(ctx, ctx->sp_tiles, (size_t)(n_tiles + 2) * sizeof(uint32_t), false))) return rc;
+    CK(cudaMemcpyAsync(ctx->sp_in.p, bytes, n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync((uint8_t *)ctx->sp_in.p + n, 0, round_up(n, 16) + 16 - n, st));
+    tdg::SplitWork w;
+    memset(&w, 0, sizeof w);
+    w.b.bytes = (const uint8_t *)ctx->sp_in.p;
+    w.b.n = (uint32_t)n;
+    w.b.final_block = final_block ? 1u : 0u;
+    w.b.n_tiles = n_tiles;
+    w.b.tile_count = (uint32_t *)ctx->sp_tiles.p;
+    w.b.ends = nullptr;
+    w.b.ends_cap = 0;
+    tdg::lineend_count<<<n_tiles, 256, 0, st>>>(w.b);
+    tdg::tile_scan<<<1, 1024, 0, st>>>(w.b.tile_count, n_tiles);
+    ctx->launches += 2;
+    uint32_t lines = 0;
+    CK(cudaMemcpyAsync(&lines, w.b.tile_count + n_tiles, sizeof lines, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // the text after the last line end is a line of its own when the file ends here
+    const uint8_t last = bytes[n - 1];
+    const bool open_tail = final_block && last != '\n' && last != '\r';
+    const uint64_t total_lines = (uint64_t)lines + (open_tail ? 1 : 0);
+    uint64_t nrec = total_lines / 4;
+    if (nrec > max_records) nrec = max_records;
+    if (nrec == 0) return TDG_OK;                    // the caller supplies more bytes (or stops at the end of the file)
+    if ((rc = grow(ctx, ctx->sp_ends, (size_t)(total_lines + 1) * sizeof(uint32_t), false))) return rc;
+    w.b.ends = (uint32_t *)ctx->sp_ends.p;
+    w.b.ends_cap = lines;
+    tdg::lineend_scatter<<<n_tiles, 256, 0, st>>>(w.b);
+    ctx->launches += 1;
+    if (open_tail) {
+        const uint32_t end = (uint32_t)n;
+        CK(cudaMemcpyAsync(w.b.ends + lines, &end, sizeof end, cudaMemcpyHostToDevice, st));
+    }
+    uint32_t last_end = 0;
+    CK(cudaMemcpyAsync(&last_end, w.b.ends + (4 * nrec - 1), sizeof last_end, cudaMemcpyDeviceToHost, st));
+
+    // ---- decisions
+    if ((rc = grow(ctx, ctx->sp_rec, (size_t)nrec * sizeof(tdg::SplitRec), false))) return rc;
+    if ((rc = grow(ctx, ctx->sp_flags, (size_t)nrec + 16, false))) return rc;
+    const uint32_t n_rtiles = (uint32_t)((nrec + tdg::SPLIT_REC_TILE - 1) / tdg::SPLIT_REC_TILE);
+    if ((rc = grow(ctx, ctx->sp_sums, (size_t)n_rtiles * nbar * sizeof(uint32_t), false))) return rc;
+    // bar_total [nbar], bar_base [nbar + 1], complex flag
+    if ((rc = grow(ctx, ctx->sp_base, (size_t)(2 * nbar + 2) * sizeof(unsigned long long), false))) return rc;
+    if ((rc = grow(ctx, ctx->sp_hbase, (size_t)(nbar + 2) * sizeof(unsigned long long), true))) return rc;
+    if ((rc = grow(ctx, ctx->sp_hflags, (size_t)nrec + 16, true))) return rc;
+    unsigned long long *bar_total = (unsigned long long *)ctx->sp_base.p;
+    w.n_rec = (uint32_t)nrec;
+    w.rec = (tdg::SplitRec *)ctx->sp_rec.p;
+    w.flags = (uint8_t *)ctx->sp_flags.p;
+    w.bar_base = bar_total + nbar;
+    w.complex_flag = (uint32_t *)(bar_total + 2 * nbar + 1);
+    w.s.t = ctx->trim;
+    w.s.bar = (const tdg::BarTable *)ctx->d_bar;
+    w.bar_off = (const uint32_t *)ctx->sp_tabs.p;
+    w.s.bar_len = w.bar_off + nbar + 1;
+    w.barcodes = (const uint8_t *)(w.s.bar_len + nbar);
+    w.s.cutlen = ctx->sp_cutlen;
+    w.nbar = nbar;
+    w.n_rtiles = n_rtiles;
+    w.tile_sums = (uint32_t *)ctx->sp_sums.p;
+    CK(cudaMemsetAsync(w.complex_flag, 0, sizeof(unsigned long long), st));
+    tdg::split_records<<<(unsigned)((nrec + 7) / 8), 256, 0, st>>>(w);
+    tdg::bar_tile_sums<<<n_rtiles, tdg::SPLIT_REC_TILE, nbar * sizeof(uint32_t), st>>>(w);
+    tdg::bar_tile_scan<<<(nbar + 255) / 256, 256, 0, st>>>(w, bar_total);
+    tdg::bar_bases<<<1, 32, 0, st>>>(bar_total, w.bar_base, nbar);
+    ctx->launches += 4;
+    unsigned long long *hbase = (unsigned long long *)ctx->sp_hbase.p;
+    CK(cudaMemcpyAsync(hbase, w.bar_base, (size_t)(nbar + 2) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    *n_records = nrec;
+    *consumed = last_end >= n ? n : (uint64_t)last_end + 1;
+    if ((uint32_t)hbase[nbar + 1] != 0) {            // the complex flag sits right behind bar_base[nbar]
+        *needs_host = 1;
+        return TDG_OK;
+    }
+
+    // ---- the bytes of every barcode's file
+    const size_t total_out = (size_t)hbase[nbar];
+    if ((rc = grow(ctx, ctx->sp_out, total_out + 16, false))) return rc;
+    if ((rc = grow(ctx, ctx->sp_hout, total_out + 16, true))) return rc;
+    w.out = (uint8_t *)ctx->sp_out.p;
+    tdg::split_write<<<n_rtiles, tdg::SPLIT_REC_TILE, nbar * sizeof(uint32_t), st>>>(w);
+    ctx->launches += 1;
+    if (total_out) CK(cudaMemcpyAsync(ctx->sp_hout.p, w.out, total_out, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->sp_hflags.p, w.flags, nrec, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    *out = (const uint8_t *)ctx->sp_hout.p;
+    *out_off = (const uint64_t *)hbase;
+    *flags = (const uint8_t *)ctx->sp_hflags.p;
+    return TDG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// The host feed on its own (tdg_feed.h): uncompressed bytes of a plain / gzip / BGZF file.
+
+struct tdg_feed {
+    tdg::Feeder f;
+};
+
+int tdg_feed_open(tdg_feed **out, const char *path, int gz)
+{
+    if (!out || !path) return fail(nullptr, TDG_ERR_ARG, "null argument");
+    *out = nullptr;
+    tdg_feed *h = new (std::nothrow) tdg_feed();
+    if (!h) return fail(nullptr, TDG_ERR_NOMEM, "out of memory");
+    int rc = h->f.open(path, gz != 0);
+    if (rc) {
+        fail(nullptr, rc, h->f.error());
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return TDG_OK;
+}
+
+long long tdg_feed_read(tdg_feed *h, void *dst, size_t cap)
+{
+    if (!h || (!dst && cap)) return fail(nullptr, TDG_ERR_ARG, "null argument");
+    if (cap == 0) return 0;
+    long long r = h->f.fill((uint8_t *)dst, cap);
+    if (r < 0) fail(nullptr, (int)r, h->f.error());
+    return r;
+}
+
+void tdg_feed_close(tdg_feed *h) { delete h; }
 
 int tdg_match_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, uint32_t n, int32_t *row_out, int32_t *col_out)
 {

@@ -121,6 +121,103 @@ def test_splitter_against_oracle(name, in_tmp, monkeypatch):
     assert open("md5.csv").read().splitlines()[0] == "File name,MD5 sum"
 
 
+def _check_against_oracle(splitter, text, barcodes, cutsite, adapter, maxreads=500000000, gz=False, label=""):
+    inp = "in.fq.gz" if gz else "in.fq"
+    data = text.encode("utf-8")
+    with open(inp, "wb") as fh:
+        fh.write(gzip.compress(data) if gz else data)
+    outs = ["o%d.fq" % i for i in range(len(barcodes))]
+    got_out, want_out = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(got_out):
+        splitter.barcodeSplitter(inp, barcodes, outs, cutsite=cutsite, adapter=adapter, maxreads=maxreads)
+    bufs = [io.StringIO() for _ in barcodes]
+    with contextlib.redirect_stdout(want_out):
+        for b, lines, _ in orc.split_records(io.StringIO(text, newline=None), barcodes, cutsite, adapter, maxreads):
+            bufs[b].write("".join(ln + "\n" for ln in lines))
+    for o, w in zip(outs, bufs):
+        with open(o, "rb") as fh:
+            assert fh.read() == w.getvalue().encode(), (label, o)
+    return got_out.getvalue()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("block_bytes", [1500, 40000, 64 << 20])
+def test_streaming_splitter_blocks_and_text_shapes(in_tmp, monkeypatch, block_bytes):
+    """The device path block by block: carries across block edges, every newline convention,
+    Unicode whitespace around lines, blank lines that shift the record phase, a last line
+    without terminator, a trailing partial record -- and blocks with non-ASCII sequence or
+    quality lines, which take the host path in the middle of the stream."""
+    from tagdigger_b200 import splitter
+    monkeypatch.setattr(splitter, "BLOCK_BYTES", block_bytes)
+    monkeypatch.setattr(splitter, "BLOCK_READS", 300)
+    rng = random.Random(block_bytes)
+    adapter = hostio.adapters["PstI-MspI-Hall"]
+    barcodes = ["ACGTA", "TTGCAC", "GGAT", "CATCGGA"]
+    base = _make_input(rng, barcodes, "TGCAG", adapter, 1200)
+    recs = base.split("\n")
+    recs = ["\n".join(recs[i:i + 4]) + "\n" for i in range(0, len(recs) - 1, 4)]
+    # Unicode whitespace around every kind of line
+    for i in range(0, len(recs), 7):
+        c1, s, c2, q = recs[i].split("\n")[:4]
+        pad = rng.choice(["\u00a0", "\u2003", "\x85", "\u3000 ", "\x1c\x0b", " \u2028"])
+        recs[i] = "\n".join([c1 + pad, pad + s + pad, c2 + pad if rng.random() < .5 else c2, q + pad + " "]) + "\n"
+    ascii_text = "".join(recs)
+    for name, text in (("lf", ascii_text), ("crlf", ascii_text.replace("\n", "\r\n")), ("cr", ascii_text.replace("\n", "\r")),
+                       ("no final newline", ascii_text[:-1]), ("partial record", ascii_text + "@x\nACGTATGCAGTT\n"),
+                       ("blank line shifts the phase", "".join(recs[:50]) + "\n" + "".join(recs[50:])),
+                       ("cr at the very end", ascii_text[:-1] + "\r"), ("empty", ""), ("one newline", "\n")):
+        _check_against_oracle(splitter, text, barcodes, "TGCAG", adapter, label=name)
+    _check_against_oracle(splitter, ascii_text, barcodes, "TGCAG", adapter, maxreads=777, label="maxreads")
+    _check_against_oracle(splitter, ascii_text.replace("\n", "\r\n"), barcodes, "TGCAG", adapter, gz=True, label="gz")
+    # non-ASCII inside sequence and quality lines: those blocks go to the host
+    for i in range(100, len(recs), 211):
+        c1, s, c2, q = recs[i].split("\n")[:4]
+        k = rng.randrange(4)
+        if k == 0:
+            s = s[:12] + "\u00e9" + s[12:]
+        elif k == 1:
+            q = "\u00df" + q
+        elif k == 2:
+            s = s + "\u00f1\u00f1"
+            q = q + "\u4e2d"
+        else:
+            s = "\u00e9" + s
+        recs[i] = "\n".join([c1, s, c2, q]) + "\n"
+    mixed = "".join(recs)
+    out = _check_against_oracle(splitter, mixed, barcodes, "TGCAG", adapter, label="non-ascii")
+    assert out.count("Reads: ") == 0                       # 1,200 reads: no progress line yet
+    _check_against_oracle(splitter, mixed, barcodes, "TGCAG", adapter, maxreads=450, label="non-ascii maxreads")
+
+
+@pytest.mark.gpu
+def test_streaming_splitter_progress_lines(in_tmp, monkeypatch):
+    """The 'Reads: ...' lines every 50,000 reads carry the running counts of the reference."""
+    from tagdigger_b200 import splitter
+    monkeypatch.setattr(splitter, "BLOCK_BYTES", 3 << 20)
+    rng = random.Random(77)
+    adapter = hostio.adapters["PstI-MspI-Clark"]
+    barcodes = ["ACGTA", "TTGCAC", "GGAT"]
+    text = _make_input(rng, barcodes, "TGCAG", adapter, 4000) * 30           # 120,000 reads
+    inp = "in.fq"
+    open(inp, "w").write(text)
+    outs = ["o%d.fq" % i for i in range(3)]
+    got = io.StringIO()
+    with contextlib.redirect_stdout(got):
+        splitter.barcodeSplitter(inp, barcodes, outs, adapter=adapter)
+    lines = [ln for ln in got.getvalue().splitlines() if ln.startswith("Reads: ")]
+    want = []
+    n = bar = clip = 0
+    with contextlib.redirect_stdout(io.StringIO()):
+        recs = list(orc.split_records(io.StringIO(text, newline=None), barcodes, "TGCAG", adapter, 500000000, every=True))
+    for b, _, s2 in recs:
+        n += 1
+        bar += b > -1
+        clip += b > -1 and s2 != 999
+        if n % 50000 == 0:
+            want.append("Reads: {0} With barcode and cut site: {1} Clipped on 3' end: {2}".format(n, bar, clip))
+    assert lines == want and len(want) == 2
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not have_reference(), reason="/root/reference not present")
 def test_splitter_stdout_matches_reference(in_tmp):
