@@ -47,7 +47,7 @@ def main():
     for bucket, per in sorted(groups.items(), key=lambda kv: -sum(kv[1].values())):
         total = sum(per.values())
         print("== %s: %.1f instr/tile" % (bucket, total))
-        for key, v in per.most_common(14):
+        for key, v in per.most_common(int(os.environ.get("TOPN","14"))):
             f, ln = key if key else ("?", 0)
             text = src[ln - 1].strip()[:80] if f == "tdg_kernel.cuh" and 0 < ln <= len(src) else ""
             print("   %6.1f  %s:%d  %s" % (v, f, ln, text))

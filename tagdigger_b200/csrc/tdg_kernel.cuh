@@ -223,34 +223,25 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         : "memory");
 }
 
-// 4 bytes -> 0x80 in every byte that is an ASCII control character (< 0x20).
-// Exact for all byte values: the low seven bits are tested without carries
-// between bytes, and bytes >= 0x80 are excluded by their own top bit.
+// 4 bytes -> 0x80 in every byte that MAY be an ASCII control character (< 0x20), in two
+// instructions.  The add carries between bytes, so the test is one-sided on purpose:
+//   * '\n' (0x0A) and '\r' (0x0D) are ALWAYS flagged: with or without a carry from the byte
+//     below, b + 0x60 (+1) stays under 0x80 for every b <= 0x1E;
+//   * a byte >= 0xA0 wraps around and is flagged although it is no control character, and
+//     0x1F right above such a byte is missed (it ends no line, so nothing is lost).
+// Every flagged byte is a CANDIDATE only: the candidate walk checks that it really is '\n'
+// and switches the warp to the exact classifier otherwise (see `classify`), so the line
+// ends found are exact for all byte values.
 __device__ __forceinline__ uint32_t ctl4(uint32_t w)
-{
-    uint32_t t = (w & 0x7F7F7F7Fu) + 0x60606060u;
-    return ~(t | w) & 0x80808080u;
-}
-// The same test in two instructions when every byte of the word is ASCII (< 0x80):
-// without the masking a byte >= 0xA0 would carry into its neighbour, so callers OR the
-// words they test into `seen` and fall back to ctl4 when a top bit shows up.
-__device__ __forceinline__ uint32_t ctl4_ascii(uint32_t w)
 {
     return ~(w + 0x60606060u) & 0x80808080u;
 }
-// 16 bytes -> 16-bit mask of control characters.  A byte-wise dot product with
-// the weights 1,2,4,..,128 gathers the 0x80 flags of two words into eight
-// adjacent bits (scaled by 128): one IDP.4A per word.
-template <bool ASCII>
-__device__ __forceinline__ uint32_t ctl_mask16(uint4 q, uint32_t &seen)
+// 16 bytes -> 16-bit candidate mask.  A byte-wise dot product with the weights 1,2,4,..,128
+// gathers the 0x80 flags of two words into eight adjacent bits (scaled by 128): one IDP.4A
+// per word.
+__device__ __forceinline__ uint32_t ctl_mask16(uint4 q)
 {
-    uint32_t fx, fy, fz, fw;
-    if (ASCII) {
-        fx = ctl4_ascii(q.x); fy = ctl4_ascii(q.y); fz = ctl4_ascii(q.z); fw = ctl4_ascii(q.w);
-        seen |= (q.x | q.y) | (q.z | q.w);
-    } else {
-        fx = ctl4(q.x); fy = ctl4(q.y); fz = ctl4(q.z); fw = ctl4(q.w);
-    }
+    const uint32_t fx = ctl4(q.x), fy = ctl4(q.y), fz = ctl4(q.z), fw = ctl4(q.w);
     uint32_t lo = __dp4a(fy, 0x80402010u, __dp4a(fx, 0x08040201u, 0u));   // flags of bytes 0-7, << 7
     uint32_t hi = __dp4a(fw, 0x80402010u, __dp4a(fz, 0x08040201u, 0u));   // flags of bytes 8-15, << 7
     return (hi * 256u + lo) >> 7;
@@ -952,22 +943,10 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         // lanes hit eight different bank groups, so every 128-bit load is conflict free)
         {
             const uint4 *src = (const uint4 *)(buf + lane * SPAN);
-            uint32_t seen = 0;
 #pragma unroll
             for (uint32_t i = 0; i < CHUNKS; i++) {
-                uint32_t m16 = ctl_mask16<true>(src[i], seen);
+                uint32_t m16 = ctl_mask16(src[i]);
                 if (i & 1u) mk[i >> 1] |= m16 << 16; else mk[i >> 1] = m16;
-            }
-            if (__any_sync(FULL, (seen & 0x80808080u) != 0)) {
-                // some byte of the tile is not ASCII: test again with the carry-safe form
-#pragma unroll 1
-                for (uint32_t i = 0; i < CHUNKS; i++) {
-                    uint32_t m16 = ctl_mask16<false>(src[i], seen);
-                    uint32_t word = i >> 1, sh16 = (i & 1u) * 16u;
-#pragma unroll
-                    for (uint32_t j = 0; j < MWORDS; j++)
-                        if (j == word) mk[j] = (mk[j] & ~(0xFFFFu << sh16)) | (m16 << sh16);
-                }
             }
         }
         if (last_tile) {
