@@ -12,13 +12,10 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(REPO, "gpurun_variants")
 VARIANTS = {
-    "w12_c11_h128": ["-DTDG_WARPS=12", "-DTDG_CHUNKS=11", "-DTDG_HALO=128"],
-    "w13_c9_h128": ["-DTDG_WARPS=13", "-DTDG_CHUNKS=9", "-DTDG_HALO=128"],
-    "w14_c9_h128": ["-DTDG_WARPS=14", "-DTDG_CHUNKS=9", "-DTDG_HALO=128", "-maxrregcount=144"],
-    "w16_c7_h128": ["-DTDG_WARPS=16", "-DTDG_CHUNKS=7", "-DTDG_HALO=128", "-maxrregcount=128"],
-    "w10_c13_h128": ["-DTDG_WARPS=10", "-DTDG_CHUNKS=13", "-DTDG_HALO=128"],
-    "w11_c11_h128": ["-DTDG_WARPS=11", "-DTDG_CHUNKS=11", "-DTDG_HALO=128"],
-    "w8_c17_h128": ["-DTDG_WARPS=8", "-DTDG_CHUNKS=17", "-DTDG_HALO=128"],
+    "w12_c11": ["-DTDG_WARPS=12", "-DTDG_CHUNKS=11"],
+    "w16_c7": ["-DTDG_WARPS=16", "-DTDG_CHUNKS=7"],
+    "w15_c9": ["-DTDG_WARPS=15", "-DTDG_CHUNKS=9"],
+    "w14_c9": ["-DTDG_WARPS=14", "-DTDG_CHUNKS=9"],
 }
 
 

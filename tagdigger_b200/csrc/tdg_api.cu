@@ -43,6 +43,7 @@ struct Slot {
 struct tdg_ctx {
     int device = 0;
     int sm_count = 0;
+    size_t smem_optin = 0;          // dynamic shared memory a block of the counting kernel may use
     std::string err;
     size_t chunk_bytes = 0;
 
@@ -177,6 +178,7 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
 
     size_t bar_smem = 0;
     if (MATCH && ctx->bar_blob.size() <= BAR_SMEM_MAX) bar_smem = round_up(ctx->bar_blob.size(), 16);
+    if (SMEM_FIXED + bar_smem > ctx->smem_optin) bar_smem = 0;      // no room: the kernel reads the table from global memory
     size_t smem = SMEM_FIXED + bar_smem;
     int &per_sm = MATCH ? ctx->occ_match : ctx->occ_lines;
     size_t &occ_smem = MATCH ? ctx->occ_match_smem : ctx->occ_lines_smem;
@@ -242,8 +244,22 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
             uint32_t h = (std::max(need, touch) + 15u) & ~15u;
             a.halo_bytes = std::min<uint32_t>(std::max<uint32_t>(h, 128u), HALO);
         }
+        {
+            // uniform matcher constants, computed once here instead of by every thread
+            const TagTable &tt = ctx->tags.t;
+            a.need = std::max<uint32_t>(hbar->max_tag_off + tt.max_len, hbar->max_len) + 36u;
+            a.tag_km = lowmask(tt.cls[0].K);
+            if (tt.min_len == tt.max_len && tt.max_len <= 64) {
+                a.ulen = tt.max_len;
+                for (uint32_t k = 0; k < 4; k++) {
+                    uint32_t nb = a.ulen > 16 * k ? a.ulen - 16 * k : 0;
+                    a.um[k] = nb >= 16 ? 0xFFFFFFFFu : ((1u << (2 * nb)) - 1u);
+                }
+            }
+        }
         a.bar = (const BarTable *)ctx->d_bar;
         a.bar_bytes = (uint32_t)ctx->bar_blob.size();
+        a.bar_in_smem = bar_smem != 0;
         a.cols = ctx->cols;
         a.tags = ctx->tags.t;
         a.tags.entries = ctx->d_entries;
@@ -494,6 +510,7 @@ int tdg_create(tdg_ctx **out, int device, size_t chunk_bytes)
     if (!c) return fail(nullptr, TDG_ERR_NOMEM, "out of memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin > 1024 ? prop.sharedMemPerBlockOptin - 1024 : 0;   // static part + reserve
     c->chunk_bytes = chunk_bytes ? chunk_bytes : ((size_t)64 << 20);
     if (const char *e = getenv("TDG_SEG_TILES")) c->force_seg_tiles = (uint32_t)atoi(e);
     if (const char *e = getenv("TDG_GENERAL")) c->force_general = atoi(e) != 0;

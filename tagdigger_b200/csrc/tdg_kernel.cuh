@@ -74,7 +74,8 @@ constexpr uint32_t QCAP = 128;                     // queue slots (power of two)
 constexpr uint32_t PUSH_CAP = QCAP - 32;           // starts pushed per emission round
 constexpr uint32_t BAR_SMEM_MAX = 10240;           // barcode tables up to this size (384-plex: 7.2 KB) are copied to smem
 constexpr uint32_t GUESS_LINES = 16;               // lines inspected for the FASTQ structure guess
-constexpr uint32_t FAST_WORDS_MAX = 24;            // 4-character words the fast matcher packs per read
+constexpr uint32_t FAST_WORDS_MAX = 24;
+constexpr uint32_t TIX_LAST = 0x80000000u;         // StageMeta: last tile of its segment            // 4-character words the fast matcher packs per read
 static_assert(CHUNKS % 2 == 1, "an odd chunk count keeps the 128-bit scan loads free of bank conflicts");
 static_assert(TILE % 16 == 0 && STAGE % 16 == 0, "tiles must keep the 16-byte alignment TMA needs");
 static_assert(RING < 65536, "queue entries are 16-bit offsets into a warp's ring");
@@ -121,6 +122,11 @@ struct ChunkArgs {
     uint32_t cols;
     uint32_t halo_bytes;            // bytes copied past each tile (multiple of 16, <= HALO)
     uint32_t fast_words;            // > 0: tables fit the fast matcher, which packs this many words
+    uint32_t need;                  // bytes a match may touch past the stripped line start
+    uint32_t ulen;                  // > 0: every tag has this length (<= 64), and
+    uint32_t um[4];                 //      these are its four 32-bit compare masks
+    uint32_t bar_in_smem;           // the barcode table is copied into shared memory
+    unsigned long long tag_km;      // mask of the first K bases of a key (class 0)
     TagTable tags;
     int32_t *matrix;
     int32_t *replicas;              // [n_replicas - 1][cells] extra copies of a SMALL matrix (or null)
@@ -160,13 +166,20 @@ inline uint32_t fast_words_for(const BarTable *bar, const TagTable &tt)
 
 #if defined(__CUDACC__)
 
-struct WarpShared {           // per-warp control block in shared memory
+struct alignas(16) WarpShared {   // per-warp control block in shared memory
     uint32_t mk[MWORDS][32];  // line-end masks of the tile being numbered: word j of lane l at [j][l]
     uint16_t q[QCAP];         // queued sequence-line starts: offsets into the warp's ring
-    uint32_t tile[STAGES];    // tile index (inside the chunk) of each stage
-    uint32_t spare[2 * STAGES];
+    // Warp-uniform state that is touched once per tile or less lives here, not in registers
+    // (a register holds 32 copies of it, and registers are what bounds the warps per SM).
+    long long reads;          // reads numbered by this warp (signed: the fix pass subtracts)
+    unsigned long long seg_first;   // fix pass: index of the segment's first line start
+    int32_t *matrix;          // the copy of the count matrix this warp updates
+    uint32_t tile[STAGES];    // per stage: tile index inside the chunk,
+    uint32_t item[STAGES];    //   work item (segment, or fix-list entry * 2 + pass); NONE = no more work,
+    uint32_t tix[STAGES];     //   index of the tile inside its segment | TIX_LAST
+    uint32_t p_item, p_seg, p_tix, p_ntiles;   // producer (lane 0): the next tile to request
+    uint32_t seg;             // segment being numbered
     uint16_t gs[GUESS_LINES + 8];   // first line starts of a segment
-    uint32_t pad[3];
 };
 static_assert(sizeof(WarpShared) % 16 == 0, "control blocks must keep the barcode table 16-byte aligned");
 
@@ -365,21 +378,12 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     uint8_t *const bar_smem = smem + SMEM_FIXED;
 
     // ---- chunk-level state -------------------------------------------------
-    unsigned long long line_base;
-    uint32_t prev_kind;
-    if (a.use_arg_state) {
-        line_base = a.line_base;
-        prev_kind = a.prev_kind;
-    } else {
-        line_base = a.state_in->next_line;
-        prev_kind = a.state_in->prev_kind;
-    }
-    const uint32_t n_items = a.mode == MODE_FIX ? 2u * *a.n_fix : a.num_segs;
-    if (n_items == 0) return;
+    const uint32_t prev_kind = a.use_arg_state ? a.prev_kind : a.state_in->prev_kind;
+    if ((a.mode == MODE_FIX ? *a.n_fix : a.num_segs) == 0) return;
 
     const BarTable *bar = a.bar;
     if (MATCH) {
-        if (a.bar_bytes <= BAR_SMEM_MAX) {
+        if (a.bar_in_smem) {
             const uint4 *src = (const uint4 *)a.bar;
             uint4 *dst = (uint4 *)bar_smem;
             for (uint32_t i = tid; i < (a.bar_bytes + 15u) / 16u; i += THREADS) dst[i] = src[i];
@@ -396,92 +400,77 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
 
     const uint32_t copy_bytes = TILE + a.halo_bytes;
 
-    // ---- producer: the next tile to request (state uniform across the warp) --------
-    // Stage metadata travels in registers (every lane holds the same values); only
-    // the tile index is also kept in shared memory, for the general matcher.
-    struct StageMeta { uint32_t item, tix, tile; };
-    uint32_t p_item = NONE, p_seg = 0, p_tix = 0, p_ntiles = 0;
-    bool p_done = false;
-    auto produce = [&](uint32_t s) -> StageMeta {
-        if (p_tix == p_ntiles && !p_done) {
-            unsigned long long t = 0;
-            if (lane == 0) t = atomicAdd(a.ticket, 1ull);
-            t = __shfl_sync(FULL, t, 0);
+    // ---- producer (lane 0): request the next tile into stage s ---------------------------
+    // Its state and the metadata of every stage live in the warp's control block; the other
+    // lanes read a stage's metadata when the tile is opened, two tiles later.
+    auto produce = [&](uint32_t s) {
+        uint32_t item = ws->p_item, tix = ws->p_tix, ntiles = ws->p_ntiles, pseg = ws->p_seg;
+        if (tix == ntiles) {                                   // draw the next segment
+            const uint32_t n_items = a.mode == MODE_FIX ? 2u * *a.n_fix : a.num_segs;
+            const unsigned long long t = atomicAdd(a.ticket, 1ull);
+            tix = 0;
             if (t < n_items) {
-                p_item = (uint32_t)t;
-                p_seg = a.mode == MODE_FIX ? a.fix[p_item >> 1].seg : p_item;
-                uint32_t first_tile = p_seg * a.seg_tiles;
-                uint32_t left = a.num_tiles - first_tile;
-                p_ntiles = left < a.seg_tiles ? left : a.seg_tiles;
-                p_tix = 0;
+                item = (uint32_t)t;
+                pseg = a.mode == MODE_FIX ? a.fix[item >> 1].seg : item;
+                const uint32_t left = a.num_tiles - pseg * a.seg_tiles;
+                ntiles = left < a.seg_tiles ? left : a.seg_tiles;
             } else {
-                p_item = NONE;
-                p_ntiles = 0;
-                p_tix = 0;
-                p_done = true;
+                item = NONE;
+                ntiles = NONE;                                 // never equal to tix again: no more tickets
             }
+            ws->p_item = item;
+            ws->p_seg = pseg;
+            ws->p_ntiles = ntiles;
         }
-        StageMeta m;
-        m.item = p_item;
-        m.tix = p_tix;
-        m.tile = p_seg * a.seg_tiles + p_tix;
-        if (p_item != NONE) {
-            if (lane == 0) {
-                ws->tile[s] = m.tile;
-                unsigned long long off = (unsigned long long)m.tile * TILE;
-                uint32_t bytes = copy_bytes;
-                if (m.tile + 2 >= a.num_tiles) {              // only the last tiles can run past the data
-                    unsigned long long left = a.n - off;
-                    if (left < bytes) bytes = ((uint32_t)left + 15u) & ~15u;
-                }
-                mbar_expect_tx(&full_bar[warp][s], bytes);
-                bulk_g2s(wbase + s * STAGE, a.bytes + off, bytes, &full_bar[warp][s]);
+        ws->item[s] = item;
+        if (item != NONE) {
+            const uint32_t tile = pseg * a.seg_tiles + tix;
+            ws->tile[s] = tile;
+            ws->tix[s] = tix + 1 == ntiles ? (tix | TIX_LAST) : tix;
+            const unsigned long long off = (unsigned long long)tile * TILE;
+            uint32_t bytes = copy_bytes;
+            if (tile + 2 >= a.num_tiles) {                     // only the last tiles can run past the data
+                const unsigned long long left = a.n - off;
+                if (left < bytes) bytes = ((uint32_t)left + 15u) & ~15u;
             }
-            p_tix++;
+            mbar_expect_tx(&full_bar[warp][s], bytes);
+            bulk_g2s(wbase + s * STAGE, a.bytes + off, bytes, &full_bar[warp][s]);
+            tix++;
         }
-        return m;
+        ws->p_tix = tix;
     };
-    StageMeta metaA = produce(0);          // the tile processed next
-    StageMeta metaB = produce(1);          // the one after it
+    if (lane == 0) {
+        ws->p_item = NONE;
+        ws->p_seg = 0;
+        ws->p_tix = 0;
+        ws->p_ntiles = 0;
+        ws->reads = 0;
+        produce(0);            // the tile processed next
+        produce(1);            // the one after it
+    }
 
-    // ---- matcher set-up (uniform) -----------------------------------------------------
+    // ---- matcher set-up: everything uniform comes straight from the kernel arguments ----
     const uint32_t nw = MATCH ? a.fast_words : 0;       // 0: general matcher only
-    uint32_t need = 0;                                  // bytes a match may touch past the stripped line start
-    uint32_t tagK = 0, tag_base = 0, tag_mask = 0;
-    uint32_t ulen = 0;                                  // > 0: every tag has this length
-    uint32_t UM0 = 0, UM1 = 0, UM2 = 0, UM3 = 0;        // and these are its compare masks
-    if (MATCH) {
-        need = bar->max_tag_off + a.tags.max_len + 36u;
-        if (bar->max_len + 36u > need) need = bar->max_len + 36u;
-        tagK = a.tags.cls[0].K;
-        tag_base = a.tags.cls[0].base;
-        tag_mask = a.tags.cls[0].mask;
-        if (a.tags.min_len == a.tags.max_len && a.tags.max_len <= 64) {
-            ulen = a.tags.max_len;
-            UM0 = lowmask32(ulen);
-            UM1 = lowmask32(ulen > 16 ? ulen - 16 : 0);
-            UM2 = lowmask32(ulen > 32 ? ulen - 32 : 0);
-            UM3 = lowmask32(ulen > 48 ? ulen - 48 : 0);
+    if (MATCH && lane == 0) {
+        // the copy of the count matrix this warp updates (copy 0 is the matrix itself)
+        int32_t *m = a.matrix;
+        if (a.n_replicas > 1) {
+            const uint32_t rep = (blockIdx.x * WARPS + warp) % a.n_replicas;
+            if (rep) m = a.replicas + (size_t)(rep - 1) * a.cells;
         }
+        ws->matrix = m;
     }
-    // the copy of the count matrix this warp updates (copy 0 is the matrix itself)
-    int32_t *my_matrix = a.matrix;
-    if (MATCH && a.n_replicas > 1) {
-        const uint32_t rep = (blockIdx.x * WARPS + warp) % a.n_replicas;
-        if (rep) my_matrix = a.replicas + (size_t)(rep - 1) * a.cells;
-    }
-    const uint64_t tag_km = lowmask(tagK);
+    __syncwarp();
     const uint4 *tag_entries = (const uint4 *)a.tags.entries;
-    long long my_reads = 0;
     int32_t my_bar = 0, my_tag = 0;
 
     // ---- queue of sequence-line starts (uniform bookkeeping, contents in ws->q) ------------
     uint32_t q_head = 0, q_len = 0, q_old = 0;
 
     // ---- per-segment state (uniform across the warp) -----------------------------------------
-    uint32_t seg = 0, seg_ntiles = 0, seg_lines = 0, guess = 0;
-    unsigned long long seg_first = 0;     // (assumed) index of the segment's first line start
-    unsigned long long limit = ~0ull;
+    uint32_t seg_lines = 0;               // line starts numbered so far
+    uint32_t phase = 0;                   // (assumed) index of the segment's first line start, mod 4
+    bool has_limit = false;               // fix pass, true numbering: a.reads_limit applies
     int32_t weight = 1;
     bool need_guess = false;
     bool classify_first = !MATCH;         // sticky: this input has control characters other than '\n'
@@ -489,7 +478,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
 
     // 128-bit compare of a table entry with the read's key over the entry's length
     auto tag_differs = [&](const uint4 &k, uint32_t L, uint32_t T0, uint32_t T1, uint32_t T2, uint32_t T3) -> uint32_t {
-        if (ulen) return ((k.x ^ T0) & UM0) | ((k.y ^ T1) & UM1) | ((k.z ^ T2) & UM2) | ((k.w ^ T3) & UM3);
+        if (a.ulen) return ((k.x ^ T0) & a.um[0]) | ((k.y ^ T1) & a.um[1]) | ((k.z ^ T2) & a.um[2]) | ((k.w ^ T3) & a.um[3]);
         return ((k.x ^ T0) & lowmask32(L)) | ((k.y ^ T1) & lowmask32(L > 16 ? L - 16 : 0)) |
                ((k.z ^ T2) & lowmask32(L > 32 ? L - 32 : 0)) | ((k.w ^ T3) & lowmask32(L > 48 ? L - 48 : 0));
     };
@@ -504,7 +493,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     int32_t pb_row = -1, pb_col = -1;     // per lane
     bool pb_probe = false;                // per lane: slots loaded, compare still to do
     uint32_t pb_T0 = 0, pb_T1 = 0, pb_T2 = 0, pb_T3 = 0, pb_h = 0, pb_V = 0xFFFFFFFFu, pb_end = 0;
-    uint4 pb_k0 = make_uint4(0, 0, 0, 0), pb_m0 = pb_k0, pb_k1 = pb_k0, pb_m1 = pb_k0;
+    uint4 pb_k0 = make_uint4(0, 0, 0, 0), pb_k1 = pb_k0;
+    uint2 pb_m0 = make_uint2(0, 0), pb_m1 = pb_m0;      // len | flags, column (the first half of an entry's second 16 bytes)
 
     auto batch_front = [&](uint32_t nb) {
         uint32_t off = 0;
@@ -579,17 +569,17 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 pb_T0 = __funnelshift_r(Q0, Q1, bit);
                 pb_T1 = __funnelshift_r(Q1, Q2, bit);
             }
-            const uint64_t pre = (((uint64_t)pb_T1 << 32) | pb_T0) & tag_km;
-            pb_h = tag_slot(pre, tag_mask);            // even: both slots share a 64-byte line
+            const uint64_t pre = (((uint64_t)pb_T1 << 32) | pb_T0) & a.tag_km;
+            pb_h = tag_slot(pre, a.tags.cls[0].mask);            // even: both slots share a 64-byte line
             const bool want = have & !slow & (row >= 0);
             {
                 // unconditional (lanes that do not probe read slot 0): a predicated load would be
                 // staged through temporaries and copied, and the copy waits for the data at once
-                const uint4 *e0 = tag_entries + 2 * (size_t)(tag_base + (want ? pb_h : 0u));
+                const uint4 *e0 = tag_entries + 2 * (size_t)(a.tags.cls[0].base + (want ? pb_h : 0u));
                 pb_k0 = __ldg(e0);
-                pb_m0 = __ldg(e0 + 1);
+                pb_m0 = __ldg((const uint2 *)(e0 + 1));
                 pb_k1 = __ldg(e0 + 2);
-                pb_m1 = __ldg(e0 + 3);
+                pb_m1 = __ldg((const uint2 *)(e0 + 3));
             }
             // ---- the rest of the tag (bases 32..63) while the loads are in flight
 #pragma unroll
@@ -630,7 +620,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             const unsigned long long tile_off = (unsigned long long)tile * TILE;
             const unsigned long long avail = a.n - tile_off;
             const uint32_t staged = avail < copy_bytes ? (uint32_t)avail : copy_bytes;
-            MatchResult mr = match_general(wbase + se * STAGE, p, staged, a.bytes + tile_off, avail, need, bar, bent, &a.tags);
+            MatchResult mr = match_general(wbase + se * STAGE, p, staged, a.bytes + tile_off, avail, a.need, bar, bent, &a.tags);
             pb_row = mr.row;
             pb_col = mr.col;
         }
@@ -641,7 +631,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         if (pb_probe) {
             uint32_t tlen = 0;
             uint32_t h = pb_h;
-            uint4 k0 = pb_k0, m0 = pb_m0, k1 = pb_k1, m1 = pb_m1;
+            uint4 k0 = pb_k0, k1 = pb_k1;
+            uint2 m0 = pb_m0, m1 = pb_m1;
             for (;;) {
                 if (m0.x == TDG_EMPTY_LEN) break;
                 const uint32_t L0 = m0.x & TDG_LEN_MASK;
@@ -650,12 +641,12 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 if (tag_differs(k1, m1.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { pb_col = (int32_t)m1.y; tlen = m1.x; break; }
                 if (!(m0.x & TDG_LEN_MORE)) break;        // nothing was ever stored past this pair
                 // rare: the sequence goes on; slots come in even-aligned pairs
-                h = (h + 2) & tag_mask;
-                const uint4 *e0 = tag_entries + 2 * (size_t)(tag_base + h);
+                h = (h + 2) & a.tags.cls[0].mask;
+                const uint4 *e0 = tag_entries + 2 * (size_t)(a.tags.cls[0].base + h);
                 k0 = __ldg(e0);
-                m0 = __ldg(e0 + 1);
+                m0 = __ldg((const uint2 *)(e0 + 1));
                 k1 = __ldg(e0 + 2);
-                m1 = __ldg(e0 + 3);
+                m1 = __ldg((const uint2 *)(e0 + 3));
             }
             if (pb_col >= 0 && pb_end + tlen > pb_V) pb_col = -1;     // the tag runs into a non-base
         }
@@ -668,7 +659,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             cell = (uint32_t)pb_row * a.cols + (uint32_t)pb_col;
         }
         const uint32_t peers = __match_any_sync(FULL, cell);
-        if (cell != NONE && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&my_matrix[cell], weight * (int32_t)__popc(peers));
+        if (cell != NONE && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&ws->matrix[cell], weight * (int32_t)__popc(peers));
         pb_pending = false;
     };
 
@@ -677,24 +668,16 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     // (ranks, emission, batch_front) and then OPENS the next one (wait for its bytes, scan).
     // batch_back sits after the scan, so that the probe loads issued by batch_front are
     // consumed a whole scan later with only straight-line code in between.
-    uint32_t tix = 0, t = 0, extra = 0, sbase = 0;
-    bool seg_end = false, last_tile = false, opened = false;
+    uint32_t extra = 0, sbase = 0;
+    bool seg_end = false, opened = false;
     const uint8_t *buf = wbase;
-    unsigned long long avail = 0;
-    uint32_t mk[MWORDS];
-#pragma unroll
-    for (uint32_t j = 0; j < MWORDS; j++) mk[j] = 0;
+    uint32_t avail = 0;                   // bytes from the tile start to the end of the chunk, saturated
+    uint32_t scan_cnt = 0, scan_nz = 0;
     for (;;) {
         if (opened) {
             // the candidate loops below walk the masks through shared memory (one loop
             // over all candidates of a lane instead of one loop per mask word)
-            uint32_t cnt = 0, nz = 0;
-#pragma unroll
-            for (uint32_t j = 0; j < MWORDS; j++) {
-                ws->mk[j][lane] = mk[j];
-                cnt += __popc(mk[j]);
-                if (mk[j]) nz |= 1u << j;
-            }
+            uint32_t cnt = scan_cnt, nz = scan_nz;
 
             // exact line ends: '\n' ends a line; '\r' ends one unless a '\n' follows
             // (Python universal newlines); every other control character is content.
@@ -764,21 +747,20 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                         hit = buf[p0] == '@' && buf[p2] == '+' && p2 - p1 == p4 - p3;
                     }
                     const uint32_t hits = __ballot_sync(FULL, hit);
-                    guess = hits ? ((4u - ((uint32_t)(__ffs(hits) - 1) & 3u)) & 3u) : 0u;   // that line has index 0 mod 4
-                    seg_first = guess;
+                    phase = hits ? ((4u - ((uint32_t)(__ffs(hits) - 1) & 3u)) & 3u) : 0u;   // that line has index 0 mod 4
                     need_guess = false;
                 }
 
                 // ---- emission: queue the starts of sequence lines (index % 4 == 1) -----------
-                const unsigned long long F = seg_first + seg_lines;        // index of rank 0 of this tile
-                const uint32_t a4 = (1u - (uint32_t)F) & 3u;                 // first rank that is a sequence line
+                // rank 0 of this tile has index F = (first index of the segment) + seg_lines
+                const uint32_t a4 = (1u - (phase + seg_lines)) & 3u;         // first rank that is a sequence line
                 const uint32_t nq = total > a4 ? (total - a4 + 3u) >> 2 : 0u;
                 uint32_t nlive = nq;                                         // those below the read limit (a prefix)
-                if (limit != ~0ull) {                                        // only the fix pass applies a limit
-                    const unsigned long long first_idx = (F + a4) >> 2;
+                if (has_limit) {                                             // only the fix pass applies a limit
+                    const unsigned long long first_idx = (ws->seg_first + seg_lines + a4) >> 2;
                     nlive = 0;
-                    if (nq && first_idx < limit) {
-                        unsigned long long room = limit - first_idx;
+                    if (nq && first_idx < a.reads_limit) {
+                        unsigned long long room = a.reads_limit - first_idx;
                         nlive = nq < room ? nq : (uint32_t)room;
                     }
                 }
@@ -873,7 +855,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     continue;
                 }
                 // reads numbered in this tile (those below the limit)
-                my_reads += weight * (long long)nlive;
+                if (lane == 0) ws->reads += weight * (long long)nlive;
                 break;
             }
             seg_lines += total;
@@ -882,54 +864,57 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             if (lane == 0 && a.mode == MODE_MAIN && seg_end) {
                 SegInfo si;
                 si.lines = seg_lines;
-                si.guess = guess;
-                a.seginfo[seg] = si;
+                si.guess = phase;
+                a.seginfo[ws->seg] = si;
             }
 
             // ---- refill the stage of the previous tile (nothing points into it any more) ---
             __syncwarp();
-            if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            metaA = metaB;
-            metaB = produce(s == 0 ? STAGES - 1 : s - 1);
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                produce(s == 0 ? STAGES - 1 : s - 1);
+            }
             if (++s == STAGES) { s = 0; parity ^= 1u; }
         }
 
         // ---- open the next tile ------------------------------------------------------
-        const uint32_t item = metaA.item;
+        __syncwarp();                                 // lane 0's metadata of stage s (written two tiles ago at the latest)
+        const uint32_t item = ws->item[s];
         if (item == NONE) break;
-        tix = metaA.tix;
-        t = metaA.tile;                               // tile index in the chunk
+        const uint32_t tixf = ws->tix[s];
+        const uint32_t t = ws->tile[s];               // tile index in the chunk
         cur_tile = t;
         if (!mbar_test(&full_bar[warp][s], parity)) mbar_wait(&full_bar[warp][s], parity);   // usually there already
 
-        if (tix == 0) {                    // a new segment starts
+        if ((tixf & ~TIX_LAST) == 0) {     // a new segment starts
             seg_lines = 0;
-            limit = ~0ull;
+            has_limit = false;
             weight = 1;
             need_guess = false;
+            uint32_t seg = item;
             if (a.mode == MODE_FIX) {
-                FixEntry fe = a.fix[item >> 1];
+                const FixEntry fe = a.fix[item >> 1];
                 seg = fe.seg;
-                if (item & 1u) { seg_first = fe.true_first; limit = a.reads_limit; }
-                else           { seg_first = fe.guess; weight = -1; }
+                if (item & 1u) { phase = (uint32_t)fe.true_first & 3u; has_limit = true; if (lane == 0) ws->seg_first = fe.true_first; }
+                else           { phase = fe.guess & 3u; weight = -1; }
+            } else if (seg == 0) {
+                // known exactly
+                phase = (uint32_t)(a.use_arg_state ? a.line_base : a.state_in->next_line) & 3u;
             } else {
-                seg = item;
-                if (seg == 0) seg_first = line_base;       // known exactly
-                else { seg_first = 0; need_guess = MATCH; }
+                phase = 0;
+                need_guess = MATCH;
             }
-            guess = (uint32_t)(seg_first & 3ull);
-            uint32_t first_tile = seg * a.seg_tiles;
-            uint32_t left = a.num_tiles - first_tile;
-            seg_ntiles = left < a.seg_tiles ? left : a.seg_tiles;
+            if (lane == 0) ws->seg = seg;
         }
-        seg_end = tix == seg_ntiles - 1;
-        last_tile = t == a.num_tiles - 1;
+        seg_end = (tixf & TIX_LAST) != 0;
+        const bool last_tile = t == a.num_tiles - 1;
 
         buf = wbase + s * STAGE;
         sbase = s * STAGE;
         const unsigned long long tile_off = (unsigned long long)t * TILE;
-        avail = a.n - tile_off;                                     // bytes from tile start to chunk end
-        const uint32_t valid = avail < TILE ? (uint32_t)avail : TILE;
+        const unsigned long long avail64 = a.n - tile_off;          // bytes from tile start to chunk end
+        avail = avail64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)avail64;
+        const uint32_t valid = avail < TILE ? avail : TILE;
 
         // An implicit line end just before byte 0 of the chunk?
         extra = 0;
@@ -941,6 +926,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         // ---- scan: control-character mask of my SPAN bytes ----------------------
         // (lane l reads 16-byte units CHUNKS*l + i: with CHUNKS odd, eight consecutive
         // lanes hit eight different bank groups, so every 128-bit load is conflict free)
+        uint32_t mk[MWORDS];
         {
             const uint4 *src = (const uint4 *)(buf + lane * SPAN);
 #pragma unroll
@@ -966,6 +952,16 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 *a.last_kind = c == '\n' ? PREV_LF : (c == '\r' ? PREV_CR : PREV_OTHER);
             }
         }
+        // the masks go to shared memory right away (only their count and the set of non-empty
+        // words stay in registers while batch_back runs)
+        scan_cnt = 0;
+        scan_nz = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < MWORDS; j++) {
+            ws->mk[j][lane] = mk[j];
+            scan_cnt += __popc(mk[j]);
+            if (mk[j]) scan_nz |= 1u << j;
+        }
         opened = true;
         if (MATCH && pb_pending) batch_back();       // its probe loads went out before the refill and this scan
     }
@@ -978,6 +974,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             my_tag += __shfl_xor_sync(FULL, my_tag, o);
         }
         if (lane == 0) {
+            const long long my_reads = ws->reads;
             if (my_reads) atomicAdd(&a.totals[0], (unsigned long long)my_reads);
             if (my_bar) atomicAdd(&a.totals[1], (unsigned long long)(long long)my_bar);
             if (my_tag) atomicAdd(&a.totals[2], (unsigned long long)(long long)my_tag);
