@@ -12,10 +12,8 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(REPO, "gpurun_variants")
 VARIANTS = {
-    "w12_c11": ["-DTDG_WARPS=12", "-DTDG_CHUNKS=11"],
-    "w16_c7": ["-DTDG_WARPS=16", "-DTDG_CHUNKS=7"],
     "w15_c9": ["-DTDG_WARPS=15", "-DTDG_CHUNKS=9"],
-    "w14_c9": ["-DTDG_WARPS=14", "-DTDG_CHUNKS=9"],
+    "w15_c9_oldscan": ["-DTDG_WARPS=15", "-DTDG_CHUNKS=9", "-DTDG_OLD_SCAN"],
 }
 
 

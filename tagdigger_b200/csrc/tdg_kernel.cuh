@@ -51,10 +51,10 @@
 namespace tdg {
 
 #ifndef TDG_WARPS
-#define TDG_WARPS 12
+#define TDG_WARPS 15
 #endif
 #ifndef TDG_CHUNKS
-#define TDG_CHUNKS 11
+#define TDG_CHUNKS 9
 #endif
 #ifndef TDG_HALO
 #define TDG_HALO 128
@@ -76,6 +76,7 @@ constexpr uint32_t BAR_SMEM_MAX = 10240;           // barcode tables up to this 
 constexpr uint32_t GUESS_LINES = 16;               // lines inspected for the FASTQ structure guess
 constexpr uint32_t FAST_WORDS_MAX = 24;
 constexpr uint32_t TIX_LAST = 0x80000000u;         // StageMeta: last tile of its segment            // 4-character words the fast matcher packs per read
+static_assert(FAST_WORDS_MAX == 24, "the fast matcher's group flags are written out for six groups");
 static_assert(CHUNKS % 2 == 1, "an odd chunk count keeps the 128-bit scan loads free of bank conflicts");
 static_assert(TILE % 16 == 0 && STAGE % 16 == 0, "tiles must keep the 16-byte alignment TMA needs");
 static_assert(RING < 65536, "queue entries are 16-bit offsets into a warp's ring");
@@ -236,28 +237,36 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         : "memory");
 }
 
-// 4 bytes -> 0x80 in every byte that MAY be an ASCII control character (< 0x20), in two
-// instructions.  The add carries between bytes, so the test is one-sided on purpose:
-//   * '\n' (0x0A) and '\r' (0x0D) are ALWAYS flagged: with or without a carry from the byte
-//     below, b + 0x60 (+1) stays under 0x80 for every b <= 0x1E;
-//   * a byte >= 0xA0 wraps around and is flagged although it is no control character, and
-//     0x1F right above such a byte is missed (it ends no line, so nothing is lost).
-// Every flagged byte is a CANDIDATE only: the candidate walk checks that it really is '\n'
-// and switches the warp to the exact classifier otherwise (see `classify`), so the line
-// ends found are exact for all byte values.
-__device__ __forceinline__ uint32_t ctl4(uint32_t w)
+// Line-end candidates, 16 bytes at a time.  b + 0x60 has its top bit set for every byte in
+// 0x20..0x9F, i.e. "certainly no control character"; PRMT's sign replication turns that bit
+// into 0xFF / 0x00 bytes, and a signed-by-unsigned byte dot product with the weights
+// 1,2,4,..,128, started at 255, leaves the 8-bit mask of the CANDIDATES of eight bytes:
+// three instructions per four bytes (IADD, PRMT, IDP.4A).
+// The add carries between bytes, so the test is one-sided on purpose:
+//   * '\n' (0x0A) and '\r' (0x0D) are ALWAYS candidates: with or without a carry from the
+//     byte below, b + 0x60 (+1) stays under 0x80 for every b <= 0x1E;
+//   * a byte >= 0xA0 wraps around and becomes a candidate although it is no control
+//     character, and 0x1F right above such a byte is missed (it ends no line: nothing lost).
+// The candidate walk checks that every candidate really is '\n' and switches the warp to the
+// exact classifier otherwise (see `classify`), so the line ends found are exact for all
+// byte values.
+__device__ __forceinline__ uint32_t notctl4(uint32_t w)
 {
-    return ~(w + 0x60606060u) & 0x80808080u;
+    uint32_t r;                                              // 0xFF where bit 7 of the sum is set
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w + 0x60606060u), "r"(0u), "r"(0xBA98u));
+    return r;
 }
-// 16 bytes -> 16-bit candidate mask.  A byte-wise dot product with the weights 1,2,4,..,128
-// gathers the 0x80 flags of two words into eight adjacent bits (scaled by 128): one IDP.4A
-// per word.
+__device__ __forceinline__ int32_t dp4a_su(uint32_t a_signed_bytes, uint32_t b_unsigned_bytes, int32_t c)
+{
+    int32_t d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_signed_bytes), "r"(b_unsigned_bytes), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint32_t ctl_mask16(uint4 q)
 {
-    const uint32_t fx = ctl4(q.x), fy = ctl4(q.y), fz = ctl4(q.z), fw = ctl4(q.w);
-    uint32_t lo = __dp4a(fy, 0x80402010u, __dp4a(fx, 0x08040201u, 0u));   // flags of bytes 0-7, << 7
-    uint32_t hi = __dp4a(fw, 0x80402010u, __dp4a(fz, 0x08040201u, 0u));   // flags of bytes 8-15, << 7
-    return (hi * 256u + lo) >> 7;
+    const int32_t lo = dp4a_su(notctl4(q.y), 0x80402010u, dp4a_su(notctl4(q.x), 0x08040201u, 255));   // bytes 0-7
+    const int32_t hi = dp4a_su(notctl4(q.w), 0x80402010u, dp4a_su(notctl4(q.z), 0x08040201u, 255));   // bytes 8-15
+    return (uint32_t)hi * 256u + (uint32_t)lo;
 }
 
 // Unaligned 32-character window out of a shared-memory stage buffer.
@@ -469,6 +478,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
 
     // ---- per-segment state (uniform across the warp) -----------------------------------------
     uint32_t seg_lines = 0;               // line starts numbered so far
+    uint32_t seg_reads = 0;               // reads numbered so far (those below the limit)
     uint32_t phase = 0;                   // (assumed) index of the segment's first line start, mod 4
     bool has_limit = false;               // fix pass, true numbering: a.reads_limit applies
     int32_t weight = 1;
@@ -520,7 +530,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             const uint32_t sh = off & 3u;
             const uint32_t *wp = (const uint32_t *)(wbase + (off & ~3u));
             uint32_t P[FAST_WORDS_MAX / 4];
-            uint32_t gbm = 0;         // bit g: words 4g..4g+3 hold a character outside ACGTacgt
+            uint32_t GB[FAST_WORDS_MAX / 4];  // non-zero: words 4g..4g+3 hold a character outside ACGTacgt
             auto pack_group = [&](uint32_t g) {
                 uint32_t x[4], gbad = 0;
 #pragma unroll
@@ -530,13 +540,13 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     if (g == 0 && k == 0) bad &= 0xFFFFFFFFu << (8u * sh);   // bytes before the line start
                     gbad |= bad;          // words past nw may flag too: V below ignores them
                 }
-                if (gbad) gbm |= 1u << g;
+                GB[g] = gbad;
                 P[g] = __byte_perm(__byte_perm(x[0], x[1], 0x0073), __byte_perm(x[2], x[3], 0x0073), 0x5410);
             };
             // groups 0..3 (64 characters) hold the barcode, the cut site and the first 32 bases
             // of the tag, which is all the hash needs: the probe loads go out before the rest
 #pragma unroll
-            for (uint32_t g = 0; g < FAST_WORDS_MAX / 4; g++) P[g] = 0;
+            for (uint32_t g = 0; g < FAST_WORDS_MAX / 4; g++) { P[g] = 0; GB[g] = 0; }
 #pragma unroll
             for (uint32_t g = 0; g < 4; g++)
                 if (4 * g < nw) pack_group(g);
@@ -592,9 +602,12 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             }
             // some character is not a base: matches stand only if they end before it
             uint32_t V = 0xFFFFFFFFu;                  // valid bases from the line start
-            if (gbm != 0) {
+            if (((GB[0] | GB[1] | GB[2]) | (GB[3] | GB[4] | GB[5])) != 0) {
                 // first character that is not a base, inside the first flagged group of four words
-                const uint32_t i0 = 4u * (__ffs(gbm) - 1u);
+                uint32_t i0 = 0;
+#pragma unroll
+                for (int g = FAST_WORDS_MAX / 4 - 1; g >= 0; g--)
+                    if (GB[g] != 0) i0 = 4u * g;
                 uint32_t firstbad = 0, at = 0;
 #pragma unroll
                 for (int k = 3; k >= 0; k--) {
@@ -817,7 +830,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                             }
                         }
                     }
-                    if (lane == 0 && extra && a4 == 0 && w0 == 0 && room > 0) ws->q[qbase & (QCAP - 1)] = (uint16_t)sbase;
+                    if (extra != 0)           // uniform; only a chunk's first tile can have it
+                        if (lane == 0 && a4 == 0 && w0 == 0 && room > 0) ws->q[qbase & (QCAP - 1)] = (uint16_t)sbase;
                     if (!verified) {
                         if (__any_sync(FULL, dev != 0)) { redo = true; break; }
                         verified = true;
@@ -855,17 +869,23 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     continue;
                 }
                 // reads numbered in this tile (those below the limit)
-                if (lane == 0) ws->reads += weight * (long long)nlive;
+                seg_reads += nlive;
                 break;
             }
             seg_lines += total;
 
             q_old = q_len;
-            if (lane == 0 && a.mode == MODE_MAIN && seg_end) {
-                SegInfo si;
-                si.lines = seg_lines;
-                si.guess = phase;
-                a.seginfo[ws->seg] = si;
+            if (seg_end) {                   // uniform, once per segment
+                if (lane == 0) {
+                    ws->reads += weight * (long long)seg_reads;
+                    if (a.mode == MODE_MAIN) {
+                        SegInfo si;
+                        si.lines = seg_lines;
+                        si.guess = phase;
+                        a.seginfo[ws->seg] = si;
+                    }
+                }
+                seg_reads = 0;
             }
 
             // ---- refill the stage of the previous tile (nothing points into it any more) ---
@@ -907,16 +927,20 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             if (lane == 0) ws->seg = seg;
         }
         seg_end = (tixf & TIX_LAST) != 0;
-        const bool last_tile = t == a.num_tiles - 1;
 
         buf = wbase + s * STAGE;
         sbase = s * STAGE;
-        const unsigned long long tile_off = (unsigned long long)t * TILE;
-        const unsigned long long avail64 = a.n - tile_off;          // bytes from tile start to chunk end
-        avail = avail64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)avail64;
-        const uint32_t valid = avail < TILE ? avail : TILE;
-
-        // An implicit line end just before byte 0 of the chunk?
+        // Only a chunk's last tiles can be cut by the end of the data, only its first tile can
+        // follow an implicit line end: everything in between takes neither branch.
+        avail = 0xFFFFFFFFu;
+        uint32_t valid = TILE;
+        bool last_tile = false;
+        if (t + 2 >= a.num_tiles) {
+            const unsigned long long avail64 = a.n - (unsigned long long)t * TILE;     // bytes from tile start to chunk end
+            avail = avail64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)avail64;
+            valid = avail < TILE ? avail : TILE;
+            last_tile = t == a.num_tiles - 1;
+        }
         extra = 0;
         if (t == 0) {
             if (prev_kind == PREV_NONE || prev_kind == PREV_LF) extra = 1;

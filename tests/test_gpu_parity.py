@@ -117,10 +117,10 @@ def test_unicode_whitespace_and_non_ascii():
     assert want == [[5, 1]]
 
 
-KERNEL_TILE = 7680      # csrc/tdg_kernel.cuh: bytes per warp tile
+KERNEL_TILES = [4608, 5632]      # csrc/tdg_kernel.cuh: bytes per warp tile (15 warps x 9 units; 12 warps x 11 units)
 
 
-@pytest.mark.parametrize("tile", [KERNEL_TILE, _native.TDG_TILE_BYTES])
+@pytest.mark.parametrize("tile", KERNEL_TILES + [_native.TDG_TILE_BYTES])
 @pytest.mark.parametrize("delta", [-3, -2, -1, 0, 1, 2, 3, 17])
 def test_device_chunk_sizes_around_tile_edges(eng, delta, tile):
     """tdg_count_device with n just below / at / above multiples of the tile
@@ -492,7 +492,8 @@ def test_fuzz_byte_soup(seed):
                                                           b"\x00", b"\x0b", "é".encode(), b"I", b"#"]
     hits = [(r.choice(barcodes) + t).encode() for t in tags]
     for _ in range(25):
-        n = r.choice([0, 1, 5, 127, 128, 129, 175, 176, 177, 5631, 5632, 5633, 5760, 11264, 17000, 40000]) + r.randint(0, 3)
+        n = r.choice([0, 1, 5, 127, 128, 129, 143, 144, 145, 175, 176, 177, 4607, 4608, 4609, 4736, 5631, 5632, 5633, 5760,
+                      9216, 11264, 17000, 40000]) + r.randint(0, 3)
         parts = []
         size = 0
         while size < n:
