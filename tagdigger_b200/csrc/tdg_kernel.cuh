@@ -640,39 +640,54 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         pb_pending = true;
     };
 
+    // The count update of a batch is retired one batch later: MATCH.ANY takes a while, and this
+    // way nothing waits for it.  (A segment's last update is retired before its weight changes.)
+    uint32_t pr_cell = NONE, pr_peers = 0;
+    auto red_retire = [&]() {
+        // warp-aggregated: one red per distinct cell
+        if (pr_cell != NONE && lane == (uint32_t)(__ffs(pr_peers) - 1))
+            atomicAdd(&ws->matrix[pr_cell], weight * (int32_t)__popc(pr_peers));
+        pr_cell = NONE;
+    };
+
     auto batch_back = [&]() {
-        if (pb_probe) {
-            uint32_t tlen = 0;
-            uint32_t h = pb_h;
-            uint4 k0 = pb_k0, k1 = pb_k1;
-            uint2 m0 = pb_m0, m1 = pb_m1;
-            for (;;) {
-                if (m0.x == TDG_EMPTY_LEN) break;
-                const uint32_t L0 = m0.x & TDG_LEN_MASK;
-                if (tag_differs(k0, L0, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { pb_col = (int32_t)m0.y; tlen = L0; break; }
-                if (m1.x == TDG_EMPTY_LEN) break;
-                if (tag_differs(k1, m1.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { pb_col = (int32_t)m1.y; tlen = m1.x; break; }
-                if (!(m0.x & TDG_LEN_MORE)) break;        // nothing was ever stored past this pair
-                // rare: the sequence goes on; slots come in even-aligned pairs
-                h = (h + 2) & a.tags.cls[0].mask;
-                const uint4 *e0 = tag_entries + 2 * (size_t)(a.tags.cls[0].base + h);
-                k0 = __ldg(e0);
-                m0 = __ldg((const uint2 *)(e0 + 1));
-                k1 = __ldg(e0 + 2);
-                m1 = __ldg((const uint2 *)(e0 + 3));
+        red_retire();
+        {
+            // the first slot pair of the probe sequence, without branches (every lane computes,
+            // probing lanes use the result)
+            const bool e0 = pb_m0.x == TDG_EMPTY_LEN, e1 = pb_m1.x == TDG_EMPTY_LEN;
+            const uint32_t L0 = pb_m0.x & TDG_LEN_MASK;
+            const bool hit0 = !e0 & (tag_differs(pb_k0, L0, pb_T0, pb_T1, pb_T2, pb_T3) == 0);
+            const bool hit1 = !e0 & !e1 & !hit0 & (tag_differs(pb_k1, pb_m1.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0);
+            int32_t col = hit0 ? (int32_t)pb_m0.y : (hit1 ? (int32_t)pb_m1.y : -1);
+            uint32_t tlen = hit0 ? L0 : pb_m1.x;
+            // rare: both slots taken by other keys and something was stored beyond this pair
+            if (pb_probe & !e0 & !e1 & !hit0 & !hit1 & ((pb_m0.x & TDG_LEN_MORE) != 0)) {
+                uint32_t h = pb_h;
+                for (;;) {
+                    h = (h + 2) & a.tags.cls[0].mask;                 // slots come in even-aligned pairs
+                    const uint4 *e = tag_entries + 2 * (size_t)(a.tags.cls[0].base + h);
+                    const uint4 k0 = __ldg(e), k1 = __ldg(e + 2);
+                    const uint2 m0 = __ldg((const uint2 *)(e + 1)), m1 = __ldg((const uint2 *)(e + 3));
+                    if (m0.x == TDG_EMPTY_LEN) break;
+                    const uint32_t l0 = m0.x & TDG_LEN_MASK;
+                    if (tag_differs(k0, l0, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { col = (int32_t)m0.y; tlen = l0; break; }
+                    if (m1.x == TDG_EMPTY_LEN) break;
+                    if (tag_differs(k1, m1.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { col = (int32_t)m1.y; tlen = m1.x; break; }
+                    if (!(m0.x & TDG_LEN_MORE)) break;
+                }
             }
-            if (pb_col >= 0 && pb_end + tlen > pb_V) pb_col = -1;     // the tag runs into a non-base
+            __syncwarp();
+            if (pb_probe) pb_col = (col >= 0 && pb_end + tlen > pb_V) ? -1 : col;     // -1: the tag runs into a non-base
         }
-        __syncwarp();
         if (pb_row >= 0) my_bar += weight;
-        // warp-aggregated count update: one red per distinct cell
         uint32_t cell = NONE;
         if (pb_col >= 0) {
             my_tag += weight;
             cell = (uint32_t)pb_row * a.cols + (uint32_t)pb_col;
         }
-        const uint32_t peers = __match_any_sync(FULL, cell);
-        if (cell != NONE && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&ws->matrix[cell], weight * (int32_t)__popc(peers));
+        pr_cell = cell;
+        pr_peers = __match_any_sync(FULL, cell);
         pb_pending = false;
     };
 
@@ -718,7 +733,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 }
             };
             bool verified = false;
-            if (classify_first || need_guess) { classify(); verified = true; }
+            if (classify_first) { classify(); verified = true; }
 
             uint32_t incl, total;
             for (;;) {
@@ -876,6 +891,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
 
             q_old = q_len;
             if (seg_end) {                   // uniform, once per segment
+                red_retire();
                 if (lane == 0) {
                     ws->reads += weight * (long long)seg_reads;
                     if (a.mode == MODE_MAIN) {
