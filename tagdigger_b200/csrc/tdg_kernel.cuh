@@ -555,17 +555,27 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             uint32_t tag_off = 0, blen = 0;
             int32_t row = -1;
             {
-                uint32_t b = key0 & 0xFFu;
-                uint32_t lo = bar->bucket[b], hi = bar->bucket[b + 1];
-                for (uint32_t e = lo; e < hi; e++) {
-                    uint4 be = *(const uint4 *)(bent + e);       // key lo, key hi, row, len | tag_off << 16
-                    uint32_t len = be.w & 0xFFFFu;
-                    if (((key0 ^ be.x) & lowmask32(len)) == 0) {
-                        row = (int32_t)be.z;
-                        blen = len;
-                        tag_off = be.w >> 16;
-                        break;
+                // entry: key (low half), compare mask (tdg_tables.h puts it in the key's unused high
+                // half), row, len | tag_off << 16.  A bucket rarely holds more than two patterns:
+                // its first two entries are compared without a loop (the table ends in two zero
+                // entries, so these loads never leave it), the rest in a rare divergent loop.
+                const uint32_t b = key0 & 0xFFu;
+                const uint32_t lo = bar->bucket[b], hi = bar->bucket[b + 1];
+                const uint4 be0 = *(const uint4 *)(bent + lo), be1 = *(const uint4 *)(bent + lo + 1);
+                const bool h0 = (lo < hi) & (((key0 ^ be0.x) & be0.y) == 0);
+                const bool h1 = (lo + 1 < hi) & (((key0 ^ be1.x) & be1.y) == 0);
+                uint32_t rz = h0 ? be0.z : be1.z, rw = h0 ? be0.w : be1.w;
+                bool hit = h0 | h1;
+                if (!hit & (lo + 2 < hi)) {
+                    for (uint32_t e = lo + 2; e < hi; e++) {
+                        const uint4 be = *(const uint4 *)(bent + e);
+                        if (((key0 ^ be.x) & be.y) == 0) { rz = be.z; rw = be.w; hit = true; break; }
                     }
+                }
+                if (hit) {
+                    row = (int32_t)rz;
+                    blen = rw & 0xFFFFu;
+                    tag_off = rw >> 16;
                 }
             }
             __syncwarp();             // the bucket walks have different lengths: reconverge here
@@ -807,7 +817,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     if (simple) {
                         // one walk over my candidates: check them, remember the (at most two)
                         // that start a sequence line
-                        uint32_t o = 0, qp0 = 0, qp1 = 0;
+                        // (a candidate's byte is looked at one iteration after its load was issued)
+                        uint32_t o = 0, qp0 = 0, qp1 = 0, byte = 0x0Au;
                         while ((cur | nzl) != 0) {
                             if (cur == 0) {
                                 const uint32_t j = __ffs(nzl) - 1u;
@@ -817,11 +828,13 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                             }
                             const uint32_t p = pbase + __ffs(cur) - 1u;
                             cur &= cur - 1u;
-                            dev |= (uint32_t)buf[p] ^ 0x0Au;
+                            dev |= byte ^ 0x0Au;
+                            byte = buf[p];
                             if (o == skip0) qp0 = p;
                             if (o == skip0 + 4u) qp1 = p;
                             o++;
                         }
+                        dev |= byte ^ 0x0Au;
                         if (cnt > skip0) ws->q[(qbase + jj0) & (QCAP - 1)] = (uint16_t)(sbase + qp0 + 1);
                         if (cnt > skip0 + 4u) ws->q[(qbase + jj0 + 1) & (QCAP - 1)] = (uint16_t)(sbase + qp1 + 1);
                     } else {

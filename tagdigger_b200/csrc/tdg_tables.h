@@ -200,7 +200,15 @@ inline std::string build_bar_table(const char *bases, const uint32_t *off, const
         }
         hdr.bucket[256] = (uint32_t)ents.size();
         hdr.n_entries = (uint32_t)ents.size();
+        // Patterns of at most 16 bases leave the upper half of `key` free: it carries the 32-bit
+        // compare mask for the kernel's fast matcher (every other reader masks the key to the
+        // pattern's length, so the extra bits are invisible there).
+        if (hdr.max_len <= 16)
+            for (BarEntry &e : ents) e.key |= (uint64_t)(uint32_t)lowmask(e.len) << 32;
     }
+    // two zero entries behind the last one: the fast matcher loads a bucket's first two entries
+    // without looking at the bucket's size first
+    ents.resize(ents.size() + 2, BarEntry{0, 0, 0, 0});
     blob.resize(sizeof(BarTable) + ents.size() * sizeof(BarEntry));
     memcpy(blob.data(), &hdr, sizeof(hdr));
     if (!ents.empty()) memcpy(blob.data() + sizeof(hdr), ents.data(), ents.size() * sizeof(BarEntry));
