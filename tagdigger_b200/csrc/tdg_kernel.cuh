@@ -262,10 +262,15 @@ __device__ __forceinline__ int32_t dp4a_su(uint32_t a_signed_bytes, uint32_t b_u
     asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_signed_bytes), "r"(b_unsigned_bytes), "r"(c));
     return d;
 }
-__device__ __forceinline__ uint32_t ctl_mask16(uint4 q)
+// `dev` collects (candidate byte) ^ '\n' over all candidates: it stays zero exactly when every
+// candidate is a line feed, which is all the common path needs to know about them.
+__device__ __forceinline__ uint32_t ctl_mask16(uint4 q, uint32_t &dev)
 {
-    const int32_t lo = dp4a_su(notctl4(q.y), 0x80402010u, dp4a_su(notctl4(q.x), 0x08040201u, 255));   // bytes 0-7
-    const int32_t hi = dp4a_su(notctl4(q.w), 0x80402010u, dp4a_su(notctl4(q.z), 0x08040201u, 255));   // bytes 8-15
+    const uint32_t nx = notctl4(q.x), ny = notctl4(q.y), nz = notctl4(q.z), nw = notctl4(q.w);
+    const int32_t lo = dp4a_su(ny, 0x80402010u, dp4a_su(nx, 0x08040201u, 255));   // bytes 0-7
+    const int32_t hi = dp4a_su(nw, 0x80402010u, dp4a_su(nz, 0x08040201u, 255));   // bytes 8-15
+    dev |= ((q.x ^ 0x0A0A0A0Au) & ~nx) | ((q.y ^ 0x0A0A0A0Au) & ~ny);
+    dev |= ((q.z ^ 0x0A0A0A0Au) & ~nz) | ((q.w ^ 0x0A0A0A0Au) & ~nw);
     return (uint32_t)hi * 256u + (uint32_t)lo;
 }
 
@@ -710,7 +715,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     bool seg_end = false, opened = false;
     const uint8_t *buf = wbase;
     uint32_t avail = 0;                   // bytes from the tile start to the end of the chunk, saturated
-    uint32_t scan_cnt = 0, scan_nz = 0;
+    uint32_t scan_cnt = 0, scan_nz = 0, scan_dev = 0;
     for (;;) {
         if (opened) {
             // the candidate loops below walk the masks through shared memory (one loop
@@ -806,8 +811,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 const uint32_t skip0 = (a4 - rho0) & 3u;
                 const uint32_t jj0 = (rho0 + skip0 - a4) >> 2;
                 // Common case: everything fits one round, the read limit does not fall inside
-                // the tile and no lane holds more than two sequence-line starts.
-                const bool simple = nlive == nq && nq <= PUSH_CAP && !__any_sync(FULL, cnt > skip0 + 8u);
+                // the tile and no lane holds more than one sequence-line start.
+                const bool simple = nlive == nq && nq <= PUSH_CAP && !__any_sync(FULL, cnt > skip0 + 4u);
                 bool redo = false;
                 for (uint32_t w0 = 0;;) {
                     const uint32_t room = nlive - w0 < PUSH_CAP ? nlive - w0 : PUSH_CAP;
@@ -815,28 +820,23 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     uint32_t dev = 0;                                     // non-zero: a candidate is not '\n'
                     uint32_t nzl = nz, cur = 0, pbase = 0;
                     if (simple) {
-                        // one walk over my candidates: check them, remember the (at most two)
-                        // that start a sequence line
-                        // (a candidate's byte is looked at one iteration after its load was issued)
-                        uint32_t o = 0, qp0 = 0, qp1 = 0, byte = 0x0Au;
-                        while ((cur | nzl) != 0) {
-                            if (cur == 0) {
-                                const uint32_t j = __ffs(nzl) - 1u;
-                                nzl &= nzl - 1u;
-                                cur = ws->mk[j][lane];
-                                pbase = lane * SPAN + 32 * j;
-                            }
-                            const uint32_t p = pbase + __ffs(cur) - 1u;
-                            cur &= cur - 1u;
-                            dev |= byte ^ 0x0Au;
-                            byte = buf[p];
-                            if (o == skip0) qp0 = p;
-                            if (o == skip0 + 4u) qp1 = p;
-                            o++;
+                        // No walk: the scan has already compared every candidate with '\n' (scan_dev;
+                        // after a redo the masks are the classifier's and need no check), and the
+                        // one sequence-line start a lane can hold is its candidate number skip0 --
+                        // found by counting through the mask words.
+                        uint32_t m = 0, pb = 0, r = skip0, seen = 0;
+#pragma unroll
+                        for (uint32_t j = 0; j < MWORDS; j++) {
+                            const uint32_t w = ws->mk[j][lane];
+                            if (skip0 >= seen) { m = w; pb = 32u * j; r = skip0 - seen; }
+                            seen += __popc(w);
                         }
-                        dev |= byte ^ 0x0Au;
-                        if (cnt > skip0) ws->q[(qbase + jj0) & (QCAP - 1)] = (uint16_t)(sbase + qp0 + 1);
-                        if (cnt > skip0 + 4u) ws->q[(qbase + jj0 + 1) & (QCAP - 1)] = (uint16_t)(sbase + qp1 + 1);
+                        if (r >= 1u) m &= m - 1u;
+                        if (r >= 2u) m &= m - 1u;
+                        if (r >= 3u) m &= m - 1u;
+                        if (cnt > skip0)
+                            ws->q[(qbase + jj0) & (QCAP - 1)] = (uint16_t)(sbase + lane * SPAN + pb + __ffs(m));
+                        if (!verified) dev = scan_dev;
                     } else {
                         uint32_t skip = skip0, jj = jj0;
                         while ((cur | nzl) != 0) {
@@ -983,8 +983,9 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         {
             const uint4 *src = (const uint4 *)(buf + lane * SPAN);
 #pragma unroll
+            scan_dev = 0;
             for (uint32_t i = 0; i < CHUNKS; i++) {
-                uint32_t m16 = ctl_mask16(src[i]);
+                uint32_t m16 = ctl_mask16(src[i], scan_dev);
                 if (i & 1u) mk[i >> 1] |= m16 << 16; else mk[i >> 1] = m16;
             }
         }
