@@ -521,7 +521,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         pb_row = -1;
         pb_col = -1;
         pb_probe = false;
-        const uint32_t c0 = wbase[off];
+        // first character of the line, out of the aligned word the pack starts with
+        const uint32_t c0 = (*(const uint32_t *)(wbase + (off & ~3u)) >> (8u * (off & 3u))) & 0xFFu;
         // the general matcher takes: table shapes outside the fast envelope, the last tiles of a
         // chunk (lines may be cut by the end of the data), leading whitespace, non-ASCII
         // (evaluated without short-circuit branches: the warp must stay converged for the pack)
@@ -552,9 +553,9 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             // of the tag, which is all the hash needs: the probe loads go out before the rest
 #pragma unroll
             for (uint32_t g = 0; g < FAST_WORDS_MAX / 4; g++) { P[g] = 0; GB[g] = 0; }
+            // (always four groups: the halo covers them whatever the table shape)
 #pragma unroll
-            for (uint32_t g = 0; g < 4; g++)
-                if (4 * g < nw) pack_group(g);
+            for (uint32_t g = 0; g < 4; g++) pack_group(g);
             // ---- barcode + cut site: first 16 bases, bucket = first 4
             const uint32_t key0 = __funnelshift_r(P[0], P[1], 2u * sh);
             uint32_t tag_off = 0, blen = 0;
@@ -607,9 +608,10 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 pb_m1 = __ldg((const uint2 *)(e0 + 3));
             }
             // ---- the rest of the tag (bases 32..63) while the loads are in flight
-#pragma unroll
-            for (uint32_t g = 4; g < FAST_WORDS_MAX / 4; g++)
-                if (4 * g < nw) pack_group(g);
+            if (nw > 16) {
+                pack_group(4);
+                if (nw > 20) pack_group(5);
+            }
             {
                 const uint32_t Q2 = up ? P[3] : P[2], Q3 = up ? P[4] : P[3], Q4 = up ? P[5] : P[4];
                 pb_T2 = __funnelshift_r(Q2, Q3, bit);
@@ -752,13 +754,23 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
 
             uint32_t incl, total;
             for (;;) {
-                incl = cnt;
+                // inclusive prefix sum of cnt over the lanes.  Counts are small: one ballot per bit of
+                // the count (independent of each other) instead of five dependent shuffles.
+                if (!__any_sync(FULL, cnt >= 8u)) {
+                    const uint32_t upto = 0xFFFFFFFFu >> (31u - lane);          // lanes 0..lane
+                    const uint32_t b0 = __ballot_sync(FULL, (cnt & 1u) != 0), b1 = __ballot_sync(FULL, (cnt & 2u) != 0),
+                                   b2 = __ballot_sync(FULL, (cnt & 4u) != 0);
+                    incl = __popc(b0 & upto) + 2u * __popc(b1 & upto) + 4u * __popc(b2 & upto);
+                    total = extra + __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+                } else {
+                    incl = cnt;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    uint32_t o = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= (uint32_t)d) incl += o;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        uint32_t o = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= (uint32_t)d) incl += o;
+                    }
+                    total = extra + __shfl_sync(FULL, incl, 31);
                 }
-                total = extra + __shfl_sync(FULL, incl, 31);
                 if (!MATCH) break;
                 const uint32_t rho0 = extra + incl - cnt;       // rank of the line start after my first line end
 
