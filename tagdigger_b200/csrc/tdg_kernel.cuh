@@ -749,11 +749,11 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     if (keepm) nz |= 1u << j;
                 }
             };
-            bool verified = false;
-            if (classify_first) { classify(); verified = true; }
+            bool verified = false, do_classify = classify_first;
 
             uint32_t incl, total;
             for (;;) {
+                if (do_classify) { classify(); verified = true; do_classify = false; }
                 // inclusive prefix sum of cnt over the lanes.  Counts are small: one ballot per bit of
                 // the count (independent of each other) instead of five dependent shuffles.
                 if (!__any_sync(FULL, cnt >= 8u)) {
@@ -830,7 +830,6 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     const uint32_t room = nlive - w0 < PUSH_CAP ? nlive - w0 : PUSH_CAP;
                     const uint32_t qbase = q_head + q_len - w0;           // slot of ordinal 0
                     uint32_t dev = 0;                                     // non-zero: a candidate is not '\n'
-                    uint32_t nzl = nz, cur = 0, pbase = 0;
                     if (simple) {
                         // No walk: the scan has already compared every candidate with '\n' (scan_dev;
                         // after a redo the masks are the classifier's and need no check), and the
@@ -848,8 +847,9 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                         if (r >= 3u) m &= m - 1u;
                         if (cnt > skip0)
                             ws->q[(qbase + jj0) & (QCAP - 1)] = (uint16_t)(sbase + lane * SPAN + pb + __ffs(m));
-                        if (!verified) dev = scan_dev;
+                        dev = scan_dev;
                     } else {
+                        uint32_t nzl = nz, cur = 0, pbase = 0;
                         uint32_t skip = skip0, jj = jj0;
                         while ((cur | nzl) != 0) {
                             if (cur == 0) {
@@ -880,31 +880,33 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     q_len += room;
                     w0 += room;
                     // Match full warps.  After the tile's last round also drain what must not
-                    // wait: entries that point into the previous tile's stage have to go
-                    // before that stage is refilled, a segment's entries before its state
-                    // (weight, limit) changes.
-                    for (;;) {
-                        const bool last_round = w0 >= nlive;
-                        uint32_t nb = 0;
-                        if (q_len >= 32) nb = 32;
-                        else if (last_round && (seg_end || q_old > 0)) nb = q_len;
-                        // the segment ends: nothing may stay in flight
-                        const bool finish = pb_pending && last_round && seg_end;
-                        if (nb == 0 && !finish) break;
-                        if (pb_pending) batch_back();      // rare here: a second batch from one tile, or a flush
-                        if (nb == 0) break;
-                        batch_front(nb);
-                        // Common case: nothing more to do for this tile.  Leave through a forward
-                        // branch -- ptxas waits for outstanding loads at loop headers, and the
-                        // probe loads just issued must stay in flight until batch_back.
-                        const bool again = q_len >= 32 || (last_round && (seg_end || (q_old > 0 && q_len > 0)));
-                        if (!again) break;
+                    // wait: entries that point into the previous tile's stage have to go before
+                    // that stage is refilled, a segment's entries before its state (weight,
+                    // limit) changes.
+                    const bool last_round = w0 >= nlive;
+                    const bool flush = last_round && (seg_end || q_old > 0);
+                    if (q_len >= 32 || flush) {            // (most tiles that end without a full batch skip this)
+                        for (;;) {
+                            uint32_t nb = 0;
+                            if (q_len >= 32) nb = 32;
+                            else if (flush) nb = q_len;
+                            // the segment ends: nothing may stay in flight
+                            const bool finish = pb_pending && last_round && seg_end;
+                            if (nb == 0 && !finish) break;
+                            if (pb_pending) batch_back();      // rare here: a second batch from one tile, or a flush
+                            if (nb == 0) break;
+                            batch_front(nb);
+                            // Common case: nothing more to do for this tile.  Leave through a forward
+                            // branch -- ptxas waits for outstanding loads at loop headers, and the
+                            // probe loads just issued must stay in flight until batch_back.
+                            const bool again = q_len >= 32 || (last_round && (seg_end || (q_old > 0 && q_len > 0)));
+                            if (!again) break;
+                        }
                     }
-                    if (w0 >= nlive) break;
+                    if (last_round) break;
                 }
                 if (redo) {
-                    classify();
-                    verified = true;
+                    do_classify = true;
                     classify_first = true;
                     continue;
                 }
