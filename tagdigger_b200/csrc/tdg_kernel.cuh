@@ -947,6 +947,10 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         const uint32_t tixf = ws->tix[s];
         const uint32_t t = ws->tile[s];               // tile index in the chunk
         cur_tile = t;
+        // the probe loads of the pending batch went out before the refill: by now they are back, and
+        // the MATCH.ANY issued at the end of batch_back has the whole scan to finish before the
+        // loop header (where ptxas waits for everything outstanding)
+        if (MATCH && pb_pending) batch_back();
         if (!mbar_test(&full_bar[warp][s], parity)) mbar_wait(&full_bar[warp][s], parity);   // usually there already
 
         if ((tixf & ~TIX_LAST) == 0) {     // a new segment starts
@@ -1031,7 +1035,6 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             if (mk[j]) scan_nz |= 1u << j;
         }
         opened = true;
-        if (MATCH && pb_pending) batch_back();       // its probe loads went out before the refill and this scan
     }
 
     if (MATCH) {
