@@ -717,16 +717,26 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     bool seg_end = false, opened = false;
     const uint8_t *buf = wbase;
     uint32_t avail = 0;                   // bytes from the tile start to the end of the chunk, saturated
-    uint32_t scan_cnt = 0, scan_nz = 0, scan_dev = 0;
+    uint32_t scan_cnt = 0, scan_dev = 0;
     for (;;) {
         if (opened) {
             // the candidate loops below walk the masks through shared memory (one loop
             // over all candidates of a lane instead of one loop per mask word)
-            uint32_t cnt = scan_cnt, nz = scan_nz;
+            uint32_t cnt = scan_cnt;
+            uint32_t nz = 0;                 // bit j: my mask word j is not empty (only the rare paths ask)
+            bool nz_known = false;
+            auto need_nz = [&]() {
+                if (nz_known) return;
+#pragma unroll
+                for (uint32_t j = 0; j < MWORDS; j++)
+                    if (ws->mk[j][lane]) nz |= 1u << j;
+                nz_known = true;
+            };
 
             // exact line ends: '\n' ends a line; '\r' ends one unless a '\n' follows
             // (Python universal newlines); every other control character is content.
             auto classify = [&]() {
+                need_nz();
                 uint32_t nzl = nz;
                 cnt = 0;
                 nz = 0;
@@ -780,6 +790,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     // sequence and quality lines of equal length).  Any answer is acceptable --
                     // a wrong one is found and repaired by verify_kernel + the fix pass.
                     {
+                        need_nz();
                         uint32_t r = rho0, nzl = nz;
                         while (nzl && r < GUESS_LINES + 5) {
                             const uint32_t j = __ffs(nzl) - 1u;
@@ -824,7 +835,10 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 const uint32_t jj0 = (rho0 + skip0 - a4) >> 2;
                 // Common case: everything fits one round, the read limit does not fall inside
                 // the tile and no lane holds more than one sequence-line start.
-                const bool simple = nlive == nq && nq <= PUSH_CAP && !__any_sync(FULL, cnt > skip0 + 4u);
+                // (one vote: a lane with a candidate that is not '\n' sends the tile to the walk as well,
+                // which checks every candidate itself)
+                const bool simple = nlive == nq && nq <= PUSH_CAP &&
+                                    !__any_sync(FULL, (cnt > skip0 + 4u) | (!verified & (scan_dev != 0)));
                 bool redo = false;
                 for (uint32_t w0 = 0;;) {
                     const uint32_t room = nlive - w0 < PUSH_CAP ? nlive - w0 : PUSH_CAP;
@@ -847,8 +861,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                         if (r >= 3u) m &= m - 1u;
                         if (cnt > skip0)
                             ws->q[(qbase + jj0) & (QCAP - 1)] = (uint16_t)(sbase + lane * SPAN + pb + __ffs(m));
-                        dev = scan_dev;
                     } else {
+                        need_nz();
                         uint32_t nzl = nz, cur = 0, pbase = 0;
                         uint32_t skip = skip0, jj = jj0;
                         while ((cur | nzl) != 0) {
@@ -1024,15 +1038,12 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 *a.last_kind = c == '\n' ? PREV_LF : (c == '\r' ? PREV_CR : PREV_OTHER);
             }
         }
-        // the masks go to shared memory right away (only their count and the set of non-empty
-        // words stay in registers while batch_back runs)
+        // the masks go to shared memory right away (only their count stays in a register)
         scan_cnt = 0;
-        scan_nz = 0;
 #pragma unroll
         for (uint32_t j = 0; j < MWORDS; j++) {
             ws->mk[j][lane] = mk[j];
             scan_cnt += __popc(mk[j]);
-            if (mk[j]) scan_nz |= 1u << j;
         }
         opened = true;
     }
