@@ -13,6 +13,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(REPO, "gpurun_variants")
 VARIANTS = {
     "w15_c9": ["-DTDG_WARPS=15", "-DTDG_CHUNKS=9"],
+    "w15_c9_el": ["-DTDG_WARPS=15", "-DTDG_CHUNKS=9", "-DTDG_EVICT_LAST"],
 }
 
 

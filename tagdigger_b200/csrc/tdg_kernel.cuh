@@ -230,10 +230,14 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
 // TMA bulk copy global -> shared, completion signalled on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
+    // the FASTQ bytes are read once: let them leave L2 first, so that the tag table and the count
+    // matrix (probed at random) stay resident
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
             smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
 

@@ -80,6 +80,26 @@ def test_synthetic_against_c_oracle(cutsite, newline, lengths):
     assert (np.asarray(got) >= truth["expected"]).all()
 
 
+@pytest.mark.parametrize("nbar,newline", [(384, b"\n"), (384, b"\r\n"), (200, b"\n")])
+def test_many_barcodes(nbar, newline):
+    """384-plex: the barcode table does not fit beside the kernel's rings (it is read through L1
+    instead of shared memory) and many of its 256 buckets hold more than two patterns (the
+    matcher's loop behind the two unrolled compares)."""
+    rng = np.random.default_rng(384 + nbar + len(newline))
+    site = orc.expand_cut_site("TGCAG")[0]
+    bcs = synth.make_barcodes(nbar, rng, cutsite=site)
+    _, _, seqs = synth.make_marker_pairs(200, rng, cutsite=site)
+    tags = [s for p in seqs for s in p]
+    fq, truth = synth.make_fastq(50000, bcs, tags, rng, cutsite=site, newline=newline, readlen=100)
+    want, wtot, wlines = _oracle(fq, bcs, tags, "TGCAG")
+    tot = []
+    got = counting.find_tags_bytes(fq, bcs, tags, "TGCAG", totals=tot)
+    assert got == want
+    assert tot[:3] == wtot and tot[3] == wlines
+    assert (np.asarray(got) >= truth["expected"]).all()
+    assert sum(map(sum, got)) > 20000
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_line_soup(seed):
     """Arbitrary text: mixed line ends, blank lines, whitespace, truncated
