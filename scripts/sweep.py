@@ -12,8 +12,10 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(REPO, "gpurun_variants")
 VARIANTS = {
-    "w15_c9": ["-DTDG_WARPS=15", "-DTDG_CHUNKS=9"],
-    "w15_c9_el": ["-DTDG_WARPS=15", "-DTDG_CHUNKS=9", "-DTDG_EVICT_LAST"],
+    "w15_c9": ["-DTDG_WARPS=15", "-DTDG_CHUNKS=9"],        # the library's geometry
+    "w16_c7": ["-DTDG_WARPS=16", "-DTDG_CHUNKS=7"],
+    "w14_c9": ["-DTDG_WARPS=14", "-DTDG_CHUNKS=9"],
+    "w12_c11": ["-DTDG_WARPS=12", "-DTDG_CHUNKS=11"],
 }
 
 
