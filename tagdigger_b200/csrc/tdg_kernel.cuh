@@ -624,20 +624,32 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             // some character is not a base: matches stand only if they end before it
             uint32_t V = 0xFFFFFFFFu;                  // valid bases from the line start
             if (((GB[0] | GB[1] | GB[2]) | (GB[3] | GB[4] | GB[5])) != 0) {
-                // first character that is not a base, inside the first flagged group of four words
+                // The first flagged group of four words brackets the first such character:
+                // [Vmin, Vmax].  Mostly that decides already -- everything a match needs lies
+                // before the group, or some of it surely lies behind -- and V = Vmin gives the
+                // right answer; only a lane whose match could end INSIDE the group looks for the
+                // exact position.
                 uint32_t i0 = 0;
 #pragma unroll
                 for (int g = FAST_WORDS_MAX / 4 - 1; g >= 0; g--)
                     if (GB[g] != 0) i0 = 4u * g;
-                uint32_t firstbad = 0, at = 0;
+                const uint32_t Vmin = i0 ? 4u * i0 - sh : 0u, Vmax = 4u * i0 + 15u - sh;
+                const uint32_t end_max = tag_off + a.tags.max_len, end_min = tag_off + a.tags.min_len;
+                // (the barcode+cutsite decision feeds a total of its own, so it is bracketed by itself)
+                const bool bar_amb = (blen > Vmin) & (blen <= Vmax);
+                const bool tag_amb = (blen <= Vmin) & (end_max > Vmin) & (end_min <= Vmax);
+                V = Vmin;
+                if (want & (bar_amb | tag_amb)) {
+                    uint32_t firstbad = 0, at = 0;
 #pragma unroll
-                for (int k = 3; k >= 0; k--) {
-                    uint32_t bad;
-                    (void)pack_word(wp[i0 + k], bad);
-                    if (i0 + k == 0) bad &= 0xFFFFFFFFu << (8u * sh);
-                    if (bad != 0 && i0 + k < nw) { firstbad = bad; at = i0 + k; }
+                    for (int k = 3; k >= 0; k--) {
+                        uint32_t bad;
+                        (void)pack_word(wp[i0 + k], bad);
+                        if (i0 + k == 0) bad &= 0xFFFFFFFFu << (8u * sh);
+                        if (bad != 0 && i0 + k < nw) { firstbad = bad; at = i0 + k; }
+                    }
+                    V = firstbad ? 4u * at + ((uint32_t)(__ffs(firstbad) - 1) >> 3) - sh : 0xFFFFFFFFu;
                 }
-                if (firstbad) V = 4u * at + ((uint32_t)(__ffs(firstbad) - 1) >> 3) - sh;
             }
             __syncwarp();
             pb_probe = want & (blen <= V);
