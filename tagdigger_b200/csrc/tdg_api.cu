@@ -506,11 +506,14 @@ int tdg_create(tdg_ctx **out, int device, size_t chunk_bytes)
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
         return fail(nullptr, TDG_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 class; this library is built for sm_100a only");
+    // dynamic shared memory a block may ask for: the opt-in limit minus the kernel's static part
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, tdg::count_kernel<true>));
     tdg_ctx *c = new (std::nothrow) tdg_ctx();
     if (!c) return fail(nullptr, TDG_ERR_NOMEM, "out of memory");
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    c->smem_optin = prop.sharedMemPerBlockOptin > 1024 ? prop.sharedMemPerBlockOptin - 1024 : 0;   // static part + reserve
+    c->smem_optin = prop.sharedMemPerBlockOptin > fa.sharedSizeBytes ? prop.sharedMemPerBlockOptin - fa.sharedSizeBytes : 0;
     c->chunk_bytes = chunk_bytes ? chunk_bytes : ((size_t)64 << 20);
     if (const char *e = getenv("TDG_SEG_TILES")) c->force_seg_tiles = (uint32_t)atoi(e);
     if (const char *e = getenv("TDG_GENERAL")) c->force_general = atoi(e) != 0;

@@ -46,6 +46,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 #include "tdg_match.h"
 
 namespace tdg {
@@ -172,16 +173,17 @@ struct alignas(16) WarpShared {   // per-warp control block in shared memory
     uint16_t q[QCAP];         // queued sequence-line starts: offsets into the warp's ring
     // Warp-uniform state that is touched once per tile or less lives here, not in registers
     // (a register holds 32 copies of it, and registers are what bounds the warps per SM).
+    uint4 meta[STAGES];       // per stage: x tile index inside the chunk, y work item (segment, or fix-list
+                              //   entry * 2 + pass; NONE = no more work), z index of the tile inside its
+                              //   segment | TIX_LAST
+    uint32_t p_item, p_seg, p_tix, p_ntiles;   // producer (lane 0): the next tile to request
     long long reads;          // reads numbered by this warp (signed: the fix pass subtracts)
     unsigned long long seg_first;   // fix pass: index of the segment's first line start
     int32_t *matrix;          // the copy of the count matrix this warp updates
-    uint32_t tile[STAGES];    // per stage: tile index inside the chunk,
-    uint32_t item[STAGES];    //   work item (segment, or fix-list entry * 2 + pass); NONE = no more work,
-    uint32_t tix[STAGES];     //   index of the tile inside its segment | TIX_LAST
-    uint32_t p_item, p_seg, p_tix, p_ntiles;   // producer (lane 0): the next tile to request
     uint32_t seg;             // segment being numbered
     uint16_t gs[GUESS_LINES + 8];   // first line starts of a segment
 };
+static_assert(offsetof(WarpShared, meta) % 16 == 0 && offsetof(WarpShared, p_item) % 16 == 0, "16-byte records");
 static_assert(sizeof(WarpShared) % 16 == 0, "control blocks must keep the barcode table 16-byte aligned");
 
 constexpr size_t SMEM_FIXED = (size_t)WARPS * RING + (size_t)WARPS * sizeof(WarpShared);
@@ -440,14 +442,12 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             ws->p_seg = pseg;
             ws->p_ntiles = ntiles;
         }
-        ws->item[s] = item;
+        const uint32_t tile = pseg * a.seg_tiles + tix;
+        ws->meta[s] = make_uint4(tile, item, tix + 1 == ntiles ? (tix | TIX_LAST) : tix, 0u);
         if (item != NONE) {
-            const uint32_t tile = pseg * a.seg_tiles + tix;
-            ws->tile[s] = tile;
-            ws->tix[s] = tix + 1 == ntiles ? (tix | TIX_LAST) : tix;
             const unsigned long long off = (unsigned long long)tile * TILE;
             uint32_t bytes = copy_bytes;
-            if (tile + 2 >= a.num_tiles) {                     // only the last tiles can run past the data
+            if (__builtin_expect(tile + 2 >= a.num_tiles, 0)) {    // only the last tiles can run past the data
                 const unsigned long long left = a.n - off;
                 if (left < bytes) bytes = ((uint32_t)left + 15u) & ~15u;
             }
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
         if (slow) {
             const uint32_t se = off >= 2 * STAGE ? 2u : (off >= STAGE ? 1u : 0u);
             const uint32_t p = off - se * STAGE;
-            const uint32_t tile = ws->tile[se];
+            const uint32_t tile = ws->meta[se].x;
             const unsigned long long tile_off = (unsigned long long)tile * TILE;
             const unsigned long long avail = a.n - tile_off;
             const uint32_t staged = avail < copy_bytes ? (uint32_t)avail : copy_bytes;
@@ -972,10 +972,11 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
 
         // ---- open the next tile ------------------------------------------------------
         __syncwarp();                                 // lane 0's metadata of stage s (written two tiles ago at the latest)
-        const uint32_t item = ws->item[s];
+        const uint4 meta = ws->meta[s];
+        const uint32_t item = meta.y;
         if (item == NONE) break;
-        const uint32_t tixf = ws->tix[s];
-        const uint32_t t = ws->tile[s];               // tile index in the chunk
+        const uint32_t tixf = meta.z;
+        const uint32_t t = meta.x;                    // tile index in the chunk
         cur_tile = t;
         // the probe loads of the pending batch went out before the refill: by now they are back, and
         // the MATCH.ANY issued at the end of batch_back has the whole scan to finish before the
