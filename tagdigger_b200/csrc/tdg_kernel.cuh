@@ -1096,46 +1096,76 @@ __global__ void __launch_bounds__(256) fold_kernel(int32_t *matrix, int32_t *rep
 
 // One CTA: prefix sum over the per-segment line counts, next chunk's state,
 // and the list of segments the fix pass must redo.
+// Every warp takes a contiguous run of segments and walks it 32 entries at a time (coalesced
+// loads): first the run's total, then -- once the totals of the warps before it are known -- the
+// true first line index of every segment, by a warp scan per round.
 constexpr int VERIFY_THREADS = 1024;
 __global__ void __launch_bounds__(VERIFY_THREADS) verify_kernel(const VerifyArgs v)
 {
-    __shared__ unsigned long long s_sum[VERIFY_THREADS];
-    const uint32_t tid = threadIdx.x;
-    unsigned long long line_base;
-    if (v.use_arg_state) line_base = v.line_base; else line_base = v.state_in->next_line;
-    uint32_t per = (v.num_segs + VERIFY_THREADS - 1) / VERIFY_THREADS;
-    uint32_t lo = tid * per, hi = lo + per < v.num_segs ? lo + per : v.num_segs;
+    constexpr uint32_t NW = VERIFY_THREADS / 32;
+    __shared__ unsigned long long s_total[NW];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const unsigned long long line_base = v.use_arg_state ? v.line_base : v.state_in->next_line;
+    const uint32_t per = ((v.num_segs + NW - 1) / NW + 31u) & ~31u;          // segments per warp: whole rounds
+    const uint32_t lo = warp * per < v.num_segs ? warp * per : v.num_segs;
+    const uint32_t hi = lo + per < v.num_segs ? lo + per : v.num_segs;
+
     unsigned long long sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += v.seginfo[i].lines;
-    s_sum[tid] = sum;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partial sums
-    for (int d = 1; d < VERIFY_THREADS; d <<= 1) {
-        unsigned long long x = tid >= (uint32_t)d ? s_sum[tid - d] : 0;
-        __syncthreads();
-        s_sum[tid] += x;
-        __syncthreads();
+    for (uint32_t i = lo + lane; i < hi; i += 128) {
+        uint32_t part[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) part[k] = i + 32 * k < hi ? __ldg(&v.seginfo[i + 32 * k].lines) : 0u;
+        sum += (unsigned long long)part[0] + part[1] + part[2] + part[3];
     }
-    unsigned long long first = line_base + s_sum[tid] - sum;       // true first index of segment lo
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) s_total[warp] = sum;
+    __syncthreads();
+    unsigned long long before = 0, total = 0;                      // lines in the runs of the warps before mine / in all
+    for (uint32_t w = 0; w < NW; w++) {
+        const unsigned long long t = s_total[w];
+        if (w < warp) before += t;
+        total += t;
+    }
+
     if (v.make_fixes) {
-        for (uint32_t i = lo; i < hi; i++) {
-            SegInfo si = v.seginfo[i];
-            bool wrong = ((first ^ si.guess) & 3ull) != 0;
-            // could any read of this segment reach the limit?
-            bool past = si.lines && ((first + si.lines - 1) >> 2) >= v.reads_limit;
-            if (si.lines && (wrong || past)) {
-                uint32_t k = atomicAdd(v.n_fix, 1u);
-                FixEntry fe;
-                fe.seg = i;
-                fe.guess = si.guess;
-                fe.true_first = first;
-                v.fix[k] = fe;
+        unsigned long long first = line_base + before;             // true first index of the round's first segment
+        for (uint32_t i0 = lo; i0 < hi; i0 += 128) {
+            // four rounds' loads go out together (a round's scan must not wait a memory latency)
+            uint2 part[4];
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t i = i0 + 32 * k + lane;
+                part[k] = i < hi ? __ldg((const uint2 *)&v.seginfo[i]) : make_uint2(0u, 0u);
             }
-            first += si.lines;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++) {
+                const uint32_t i = i0 + 32 * k + lane;
+                const uint32_t lines = part[k].x, guess = part[k].y;
+                uint32_t incl = lines;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= (uint32_t)d) incl += o;
+                }
+                const unsigned long long mine = first + (incl - lines);
+                const bool wrong = ((mine ^ guess) & 3ull) != 0;
+                // could any read of this segment reach the limit?
+                const bool past = lines && ((mine + lines - 1) >> 2) >= v.reads_limit;
+                if (lines && (wrong || past)) {
+                    const uint32_t slot = atomicAdd(v.n_fix, 1u);
+                    FixEntry fe;
+                    fe.seg = i;
+                    fe.guess = guess;
+                    fe.true_first = mine;
+                    v.fix[slot] = fe;
+                }
+                first += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
         }
     }
-    if (tid == VERIFY_THREADS - 1) {
-        v.state_out->next_line = line_base + s_sum[tid];
+    if (tid == 0) {
+        v.state_out->next_line = line_base + total;
         v.state_out->prev_kind = *v.last_kind;
         v.state_out->pad = 0;
     }
