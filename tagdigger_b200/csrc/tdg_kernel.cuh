@@ -558,8 +558,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
 #pragma unroll
             for (uint32_t g = 0; g < FAST_WORDS_MAX / 4; g++) { P[g] = 0; GB[g] = 0; }
             // (always four groups: the halo covers them whatever the table shape)
-#pragma unroll
-            for (uint32_t g = 0; g < 4; g++) pack_group(g);
+            pack_group(0);
+            pack_group(1);
             // ---- barcode + cut site: first 16 bases, bucket = first 4
             const uint32_t key0 = __funnelshift_r(P[0], P[1], 2u * sh);
             uint32_t tag_off = 0, blen = 0;
@@ -589,6 +589,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 }
             }
             __syncwarp();             // the bucket walks have different lengths: reconverge here
+            pack_group(2);            // (the bucket's shared-memory loads overlap this packing)
+            pack_group(3);
             // ---- tag key at tag_off: the first 32 bases give the slot; fetch the first two
             // slots of the probe sequence right away (speculatively: validity is checked below)
             const uint32_t toff = sh + tag_off;
