@@ -15,18 +15,22 @@
 // (cp.async.bulk + mbarrier complete_tx).  There is no CTA-wide barrier after the
 // prologue, and every byte of the stream is read from HBM exactly once.
 //
-// Per tile (7,680 bytes + halo) a warp
-//   1. scans: each lane tests its 240 contiguous bytes for control characters,
-//      15 x 128-bit shared loads (240 = 15 x 16: consecutive lanes start in
-//      consecutive 16-byte bank groups, so the loads are conflict free);
-//   2. ranks the line ends with one warp prefix sum, which gives every line start
-//      its index in the file, and pushes the starts of SEQUENCE lines onto a small
-//      per-warp queue (positions inside the ring);
-//   3. whenever 32 starts are queued, matches them one per lane: pack 2 bits per
-//      base, barcode bucket lookup in shared memory, 128-bit key, one hash probe
-//      of the L2-resident tag table, warp-aggregated count update.
-// The queue decouples "lines per tile" from "lanes per warp": matching always runs
-// with full warps whatever the record length.
+// Per tile (4,608 bytes + 128 of halo) a warp
+//   1. scans: each lane looks at its 144 contiguous bytes, 9 x 128-bit shared loads
+//      (144 = 9 x 16: consecutive lanes start in consecutive 16-byte bank groups, so
+//      the loads are conflict free); per 4 bytes an add, a PRMT with sign replication
+//      and a byte dot product leave the mask of the line-end CANDIDATES, and 1.5 LOP3
+//      check that every candidate is a line feed (otherwise the exact classifier runs);
+//   2. ranks the line ends with three ballots, which gives every line start its index
+//      in the file, and pushes the starts of SEQUENCE lines (at most one per lane in
+//      ordinary FASTQ, selected without a loop) onto a small per-warp queue;
+//   3. whenever 32 starts are queued, matches them one per lane in two halves: pack 2
+//      bits per base, barcode bucket lookup in shared memory, 128-bit key, the loads of
+//      one hash probe of the L2-resident tag table (batch_front); compare and warp-
+//      aggregated count update once the next tile's bytes have arrived (batch_back).
+// The queue decouples "lines per tile" from "lanes per warp": matching runs with full
+// warps whatever the record length.  Warp-uniform state lives in the warp's control
+// block in shared memory (WarpShared), not in registers: 124 registers, 15 warps per SM.
 //
 // Line numbering.  Which lines are sequence lines is decided by the GLOBAL line
 // index (lineindex % 4 == 1 counted from the start of the file), which a warp that
@@ -64,9 +68,9 @@ namespace tdg {
 constexpr int      WARPS = TDG_WARPS;              // independent pipelines per CTA (one CTA per SM)
 constexpr int      THREADS = WARPS * 32;
 constexpr uint32_t CHUNKS = TDG_CHUNKS;            // 16-byte pieces per lane per tile; odd: see scan
-constexpr uint32_t SPAN = CHUNKS * 16;             // 176 bytes per lane
+constexpr uint32_t SPAN = CHUNKS * 16;             // 144 bytes per lane
 constexpr uint32_t MWORDS = (SPAN + 31) / 32;      // 32-bit mask words per lane
-constexpr uint32_t TILE = 32 * SPAN;               // 5,632 bytes per warp tile
+constexpr uint32_t TILE = 32 * SPAN;               // 4,608 bytes per warp tile
 constexpr uint32_t HALO = TDG_HALO;                // bytes staged past a tile (<= TDG_HALO_BYTES)
 constexpr uint32_t STAGE = TILE + HALO;            // one ring stage
 constexpr int      STAGES = 3;
