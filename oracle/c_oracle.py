@@ -128,3 +128,57 @@ def find_tags_bytes(data, barcodes, tags, cutsite="TGCAG", maxreads=5e9):
 def count_lines(data):
     arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
     return int(lib().orc_count_lines(arr.ctypes.data, arr.size))
+
+
+# ---- sharded counting of large images (parity checks at 10^7 reads and more) ----------------------
+
+_SHARD = {}
+
+
+def _lines_worker(span):
+    a, b = span
+    return count_lines(_SHARD["img"][a:b])
+
+
+def _count_worker(job):
+    a, b, first_line = job
+    # sequence lines (index % 4 == 1) that precede line `first_line`
+    m, tot = _SHARD["counter"].count(_SHARD["img"][a:b], first_line=first_line, reads_before=(first_line + 2) // 4)
+    nz = np.flatnonzero(m)                      # sparse: a 384 x 500,000 matrix is 1.5 GB, its non-zeros are few
+    return m.shape, nz, m.ravel()[nz], tot
+
+
+def count_sharded(img, counter, procs=None):
+    """Exact counts of a FASTQ image (uint8 ndarray whose lines end in '\\n') with ``counter``,
+    sharded over forked host processes: the image is cut after line feeds, the lines before every
+    cut are counted first (orc_count_lines), and every shard is then counted with its true first
+    line index -- the same result as one sequential pass.  Returns (int64 matrix, totals)."""
+    import multiprocessing as mp
+    import os
+    procs = procs or os.cpu_count() or 1
+    n = img.size
+    cuts = [0]
+    for i in range(1, procs):
+        pos = max(cuts[-1], n * i // procs)
+        nl = np.flatnonzero(img[pos:pos + (1 << 20)] == 10)
+        cuts.append(pos + int(nl[0]) + 1 if nl.size else n)
+    cuts.append(n)
+    spans = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    if len(spans) <= 1:
+        return counter.count(img)
+    lib()
+    _SHARD["img"] = img
+    _SHARD["counter"] = counter
+    try:
+        with mp.get_context("fork").Pool(len(spans)) as pool:
+            nlines = pool.map(_lines_worker, spans, chunksize=1)
+            firsts = np.concatenate([[0], np.cumsum(nlines)[:-1]]).tolist()
+            res = pool.map(_count_worker, [(a, b, int(f)) for (a, b), f in zip(spans, firsts)], chunksize=1)
+    finally:
+        _SHARD.clear()
+    total = np.zeros(res[0][0], dtype=np.int64)
+    tot = [0, 0, 0]
+    for _shape, nz, vals, t in res:
+        total.ravel()[nz] += vals
+        tot = [x + y for x, y in zip(tot, t)]
+    return total, tot

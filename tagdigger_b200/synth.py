@@ -215,3 +215,44 @@ def make_fastq(nreads, barcodes, tags, rng, cutsite="TGCAG", readlen=100,
     truth = dict(kind=kind, barcode=bidx, tag=tidx, mutated=mutated,
                  expected=expected, nreads=nreads)
     return out.tobytes(), truth
+
+
+# ---- the table shapes of BASELINE.json's configs (bench + parity tests) --------------------------
+
+SHAPES = {
+    # name: barcodes, marker pairs, read length, tag lengths incl. cut site (None = 64), blank barcode,
+    #       cut site as given to the counter, concrete site written into tags/reads, read-mix overrides
+    "C2": dict(nbar=96, npairs=20000, readlen=100),
+    "C3": dict(nbar=1, npairs=20000, readlen=100, blank=True, mix=dict(p_nobar=0.05, p_unknown=0.30)),
+    "C4": dict(nbar=384, npairs=250000, readlen=100, lengths=(20, 64)),
+    "C4-150": dict(nbar=384, npairs=250000, readlen=150, lengths=(20, 64)),
+    "C4-stacks": dict(nbar=384, npairs=250000, readlen=150, lengths=(80, 140)),
+    "C5": dict(nbar=96, npairs=20000, readlen=100, lengths=(30, 64)),
+    "ApeKI": dict(nbar=96, npairs=20000, readlen=100, cutsite="CWGC", site="CAGC"),
+    "short": dict(nbar=96, npairs=20000, readlen=50, lengths=(30, 30)),
+}
+
+
+def shape_tables(name, seed=7, npairs=None):
+    """Barcodes and tags of a named shape: ``(barcodes, tags, cutsite, site, readlen, mix)``.
+    Variable-length random tags overlap now and then; those markers are dropped the way
+    ``tagdigger_script`` would (``sanitizeTags``), so the tag set is one the reference accepts."""
+    import contextlib
+    import io
+    from . import hostio
+    sh = SHAPES[name]
+    rng = np.random.default_rng(seed)
+    cutsite = sh.get("cutsite", "TGCAG")
+    site = sh.get("site", cutsite)
+    bcs = [""] if sh.get("blank") else make_barcodes(sh["nbar"], rng, cutsite=site)
+    n = npairs or sh["npairs"]
+    lens = None
+    if sh.get("lengths"):
+        lens = rng.integers(sh["lengths"][0], sh["lengths"][1] + 1, size=n)
+    mnames, _, seqs = make_marker_pairs(n, rng, cutsite=site, lengths=lens)
+    tags = [s for p in seqs for s in p]
+    if sh.get("lengths") and sh["lengths"][0] != sh["lengths"][1]:
+        names = ["%s_%d" % (m, k) for m in mnames for k in (0, 1)]
+        with contextlib.redirect_stdout(io.StringIO()):
+            tags = hostio.sanitizeTags([names, tags])[1]
+    return bcs, tags, cutsite, site, sh["readlen"], dict(sh.get("mix", {}))
