@@ -86,12 +86,18 @@ public:
     }
 
     Mode mode() const { return mode_; }
+    int threads() const { return threads_; }
     const std::string &error() const { return err_; }
 
     // Next chunk: up to cap bytes into p.  Returns the number of bytes (0 = end of file) or a
     // negative code with error() set.
     long long fill(uint8_t *p, size_t cap)
     {
+        if (deferred_) {                  // the bytes before the defect went out with the previous call
+            int code = deferred_;
+            deferred_ = 0;
+            return code;
+        }
         switch (mode_) {
         case PLAIN: return fill_plain(p, cap);
         case PLAIN_SEQ: return fill_seq(p, cap);
@@ -123,6 +129,17 @@ private:
     {
         err_ = msg;
         return code;
+    }
+
+    // A defect `got` bytes into a chunk: hand out the good bytes first and report the error with
+    // the next call, as a reader that walks the stream line by line would meet them (a caller
+    // that stops inside those bytes -- maxreads -- never sees the error, like the reference).
+    long long fail_after(size_t got, int code, const std::string &msg)
+    {
+        err_ = msg;
+        if (got == 0) return code;
+        deferred_ = code;
+        return (long long)got;
     }
 
     // Is this the header of a BGZF member?  csize = size of the whole member, hlen = header bytes.
@@ -220,14 +237,15 @@ private:
             if (r < 0) {
                 int en = 0;
                 const char *m = gzerror(zf_, &en);
-                return fail(-6, "gzip error in " + path_ + ": " + (m ? m : "?"));
+                return fail_after(got, -6, "gzip error in " + path_ + ": " + (m ? m : "?"));
             }
             if (r == 0) {
                 // a stream that stops before its end-of-stream marker or inside its trailer: gzread
                 // hands out what it has and only notes Z_BUF_ERROR; Python's gzip raises EOFError
                 int en = 0;
                 const char *m = gzerror(zf_, &en);
-                if (en == Z_BUF_ERROR) return fail(-6, "gzip error in " + path_ + ": " + (m && *m ? m : "unexpected end of file"));
+                if (en == Z_BUF_ERROR)
+                    return fail_after(got, -6, "gzip error in " + path_ + ": " + (m && *m ? m : "unexpected end of file"));
                 break;
             }
             got += (size_t)r;
@@ -367,6 +385,7 @@ private:
     std::string path_, err_;
     Mode mode_ = PLAIN;
     int fd_ = -1, threads_ = 16;
+    int deferred_ = 0;
     uint64_t size_ = 0, pos_ = 0;
     gzFile zf_ = nullptr;
     bool gz_first_ = true;

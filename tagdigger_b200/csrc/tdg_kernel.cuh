@@ -56,10 +56,10 @@
 namespace tdg {
 
 #ifndef TDG_WARPS
-#define TDG_WARPS 15
+#define TDG_WARPS 14
 #endif
 #ifndef TDG_CHUNKS
-#define TDG_CHUNKS 9
+#define TDG_CHUNKS 15
 #endif
 #ifndef TDG_HALO
 #define TDG_HALO 128
@@ -68,23 +68,24 @@ namespace tdg {
 constexpr int      WARPS = TDG_WARPS;              // independent pipelines per CTA (one CTA per SM)
 constexpr int      THREADS = WARPS * 32;
 constexpr uint32_t CHUNKS = TDG_CHUNKS;            // 16-byte pieces per lane per tile; odd: see scan
-constexpr uint32_t SPAN = CHUNKS * 16;             // 144 bytes per lane
+constexpr uint32_t SPAN = CHUNKS * 16;             // 240 bytes per lane
 constexpr uint32_t MWORDS = (SPAN + 31) / 32;      // 32-bit mask words per lane
-constexpr uint32_t TILE = 32 * SPAN;               // 4,608 bytes per warp tile
+constexpr uint32_t HALF_WORDS = MWORDS / 2;        // a lane's span is handled as two halves (<= 128 bytes each)
+constexpr uint32_t TILE = 32 * SPAN;               // 7,680 bytes per warp tile: about one batch of 32 reads
 constexpr uint32_t HALO = TDG_HALO;                // bytes staged past a tile (<= TDG_HALO_BYTES)
 constexpr uint32_t STAGE = TILE + HALO;            // one ring stage
-constexpr int      STAGES = 3;
+constexpr int      STAGES = 2;                     // the tile being processed + the one in flight
 constexpr uint32_t RING = STAGES * STAGE;          // bytes of shared memory per warp
-constexpr uint32_t QCAP = 128;                     // queue slots (power of two)
-constexpr uint32_t PUSH_CAP = QCAP - 32;           // starts pushed per emission round
+constexpr uint32_t QCAP = 64;                      // sequence-line starts a tile can queue on the common path
 constexpr uint32_t BAR_SMEM_MAX = 10240;           // barcode tables up to this size (384-plex: 7.2 KB) are copied to smem
 constexpr uint32_t GUESS_LINES = 16;               // lines inspected for the FASTQ structure guess
-constexpr uint32_t FAST_WORDS_MAX = 24;
-constexpr uint32_t TIX_LAST = 0x80000000u;         // StageMeta: last tile of its segment            // 4-character words the fast matcher packs per read
+constexpr uint32_t FAST_WORDS_MAX = 24;            // 4-character words the fast matcher packs per read
+constexpr uint32_t TIX_LAST = 0x80000000u;         // tile metadata: last tile of its segment
 static_assert(FAST_WORDS_MAX == 24, "the fast matcher's group flags are written out for six groups");
 static_assert(CHUNKS % 2 == 1, "an odd chunk count keeps the 128-bit scan loads free of bank conflicts");
 static_assert(TILE % 16 == 0 && STAGE % 16 == 0, "tiles must keep the 16-byte alignment TMA needs");
 static_assert(RING < 65536, "queue entries are 16-bit offsets into a warp's ring");
+static_assert((MWORDS - HALF_WORDS) * 32 <= 128 && HALF_WORDS * 32 <= 128, "a half must not exceed 128 bytes");
 
 enum { PREV_NONE = 0, PREV_LF = 1, PREV_CR = 2, PREV_OTHER = 3 };
 enum { MODE_MAIN = 0, MODE_FIX = 1 };
@@ -172,22 +173,10 @@ inline uint32_t fast_words_for(const BarTable *bar, const TagTable &tt)
 
 #if defined(__CUDACC__)
 
-struct alignas(16) WarpShared {   // per-warp control block in shared memory
-    uint32_t mk[MWORDS][32];  // line-end masks of the tile being numbered: word j of lane l at [j][l]
-    uint16_t q[QCAP];         // queued sequence-line starts: offsets into the warp's ring
-    // Warp-uniform state that is touched once per tile or less lives here, not in registers
-    // (a register holds 32 copies of it, and registers are what bounds the warps per SM).
-    uint4 meta[STAGES];       // per stage: x tile index inside the chunk, y work item (segment, or fix-list
-                              //   entry * 2 + pass; NONE = no more work), z index of the tile inside its
-                              //   segment | TIX_LAST
-    uint32_t p_item, p_seg, p_tix, p_ntiles;   // producer (lane 0): the next tile to request
-    long long reads;          // reads numbered by this warp (signed: the fix pass subtracts)
-    unsigned long long seg_first;   // fix pass: index of the segment's first line start
-    int32_t *matrix;          // the copy of the count matrix this warp updates
-    uint32_t seg;             // segment being numbered
-    uint16_t gs[GUESS_LINES + 8];   // first line starts of a segment
+struct alignas(16) WarpShared {   // per-warp scratch in shared memory
+    uint16_t q[QCAP];                // sequence-line starts of the current tile: offsets into the warp's ring
+    uint16_t gs[GUESS_LINES + 8];    // first line starts of a segment (structure guess)
 };
-static_assert(offsetof(WarpShared, meta) % 16 == 0 && offsetof(WarpShared, p_item) % 16 == 0, "16-byte records");
 static_assert(sizeof(WarpShared) % 16 == 0, "control blocks must keep the barcode table 16-byte aligned");
 
 constexpr size_t SMEM_FIXED = (size_t)WARPS * RING + (size_t)WARPS * sizeof(WarpShared);
@@ -424,80 +413,69 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
 
     const uint32_t copy_bytes = TILE + a.halo_bytes;
 
-    // ---- producer (lane 0): request the next tile into stage s ---------------------------
-    // Its state and the metadata of every stage live in the warp's control block; the other
-    // lanes read a stage's metadata when the tile is opened, two tiles later.
-    auto produce = [&](uint32_t s) {
-        uint32_t item = ws->p_item, tix = ws->p_tix, ntiles = ws->p_ntiles, pseg = ws->p_seg;
-        if (tix == ntiles) {                                   // draw the next segment
+    // ---- producer: request the next tile into stage st -----------------------------------------
+    // All of its state is warp-uniform and lives in registers; every lane runs the (uniform)
+    // arithmetic, lane 0 alone draws the ticket and issues the copy.
+    uint32_t p_item = NONE, p_seg = 0, p_tix = 0, p_ntiles = 0;
+    auto produce = [&](uint32_t st, uint32_t &m_tile, uint32_t &m_item, uint32_t &m_tixf) {
+        if (p_tix == p_ntiles) {                                   // draw the next segment
             const uint32_t n_items = a.mode == MODE_FIX ? 2u * *a.n_fix : a.num_segs;
-            const unsigned long long t = atomicAdd(a.ticket, 1ull);
-            tix = 0;
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd((unsigned int *)a.ticket, 1u);
+            t = __shfl_sync(FULL, t, 0);
+            p_tix = 0;
             if (t < n_items) {
-                item = (uint32_t)t;
-                pseg = a.mode == MODE_FIX ? a.fix[item >> 1].seg : item;
-                const uint32_t left = a.num_tiles - pseg * a.seg_tiles;
-                ntiles = left < a.seg_tiles ? left : a.seg_tiles;
+                p_item = t;
+                p_seg = a.mode == MODE_FIX ? a.fix[t >> 1].seg : t;
+                const uint32_t left = a.num_tiles - p_seg * a.seg_tiles;
+                p_ntiles = left < a.seg_tiles ? left : a.seg_tiles;
             } else {
-                item = NONE;
-                ntiles = NONE;                                 // never equal to tix again: no more tickets
+                p_item = NONE;
+                p_ntiles = NONE;                                   // never equal to p_tix again: no more tickets
             }
-            ws->p_item = item;
-            ws->p_seg = pseg;
-            ws->p_ntiles = ntiles;
         }
-        const uint32_t tile = pseg * a.seg_tiles + tix;
-        ws->meta[s] = make_uint4(tile, item, tix + 1 == ntiles ? (tix | TIX_LAST) : tix, 0u);
-        if (item != NONE) {
-            const unsigned long long off = (unsigned long long)tile * TILE;
-            uint32_t bytes = copy_bytes;
-            if (__builtin_expect(tile + 2 >= a.num_tiles, 0)) {    // only the last tiles can run past the data
-                const unsigned long long left = a.n - off;
-                if (left < bytes) bytes = ((uint32_t)left + 15u) & ~15u;
+        m_tile = p_seg * a.seg_tiles + p_tix;
+        m_item = p_item;
+        m_tixf = p_tix + 1 == p_ntiles ? (p_tix | TIX_LAST) : p_tix;
+        if (p_item != NONE) {
+            if (lane == 0) {
+                const unsigned long long off = (unsigned long long)m_tile * TILE;
+                uint32_t bytes = copy_bytes;
+                if (__builtin_expect(m_tile + 2 >= a.num_tiles, 0)) {    // only the last tiles can run past the data
+                    const unsigned long long left = a.n - off;
+                    if (left < bytes) bytes = ((uint32_t)left + 15u) & ~15u;
+                }
+                mbar_expect_tx(&full_bar[warp][st], bytes);
+                bulk_g2s(wbase + st * STAGE, a.bytes + off, bytes, &full_bar[warp][st]);
             }
-            mbar_expect_tx(&full_bar[warp][s], bytes);
-            bulk_g2s(wbase + s * STAGE, a.bytes + off, bytes, &full_bar[warp][s]);
-            tix++;
+            p_tix++;
         }
-        ws->p_tix = tix;
     };
-    if (lane == 0) {
-        ws->p_item = NONE;
-        ws->p_seg = 0;
-        ws->p_tix = 0;
-        ws->p_ntiles = 0;
-        ws->reads = 0;
-        produce(0);            // the tile processed next
-        produce(1);            // the one after it
-    }
 
     // ---- matcher set-up: everything uniform comes straight from the kernel arguments ----
     const uint32_t nw = MATCH ? a.fast_words : 0;       // 0: general matcher only
-    if (MATCH && lane == 0) {
-        // the copy of the count matrix this warp updates (copy 0 is the matrix itself)
-        int32_t *m = a.matrix;
-        if (a.n_replicas > 1) {
-            const uint32_t rep = (blockIdx.x * WARPS + warp) % a.n_replicas;
-            if (rep) m = a.replicas + (size_t)(rep - 1) * a.cells;
-        }
-        ws->matrix = m;
+    int32_t *wmatrix = a.matrix;                        // the copy of the count matrix this warp updates
+    if (MATCH && a.n_replicas > 1) {
+        const uint32_t rep = (blockIdx.x * WARPS + warp) % a.n_replicas;
+        if (rep) wmatrix = a.replicas + (size_t)(rep - 1) * a.cells;
     }
-    __syncwarp();
     const uint4 *tag_entries = (const uint4 *)a.tags.entries;
     int32_t my_bar = 0, my_tag = 0;
-
-    // ---- queue of sequence-line starts (uniform bookkeeping, contents in ws->q) ------------
-    uint32_t q_head = 0, q_len = 0, q_old = 0;
+    long long my_reads = 0;               // uniform: reads numbered by this warp (signed: the fix pass subtracts)
 
     // ---- per-segment state (uniform across the warp) -----------------------------------------
     uint32_t seg_lines = 0;               // line starts numbered so far
     uint32_t seg_reads = 0;               // reads numbered so far (those below the limit)
+    uint32_t seg_id = 0;
+    unsigned long long seg_first = 0;     // fix pass: index of the segment's first line start
     uint32_t phase = 0;                   // (assumed) index of the segment's first line start, mod 4
     bool has_limit = false;               // fix pass, true numbering: a.reads_limit applies
     int32_t weight = 1;
     bool need_guess = false;
-    bool classify_first = !MATCH;         // sticky: this input has control characters other than '\n'
-    uint32_t cur_tile = 0;
+    bool classify_first = false;          // sticky: this input has control characters other than '\n'
+
+    // metadata of the tile being processed (cur) and of the one in flight (nxt)
+    uint32_t cur_tile = 0, cur_item = NONE, cur_tixf = 0, nxt_tile = 0, nxt_item = NONE, nxt_tixf = 0;
 
     // 128-bit compare of a table entry with the read's key over the entry's length
     auto tag_differs = [&](const uint4 &k, uint32_t L, uint32_t T0, uint32_t T1, uint32_t T2, uint32_t T3) -> uint32_t {
@@ -507,11 +485,11 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     };
 
     // ---- matching, software-pipelined ------------------------------------------------
-    // batch_front takes up to 32 queued line starts, one per lane: pack, barcode
-    // lookup, tag key, hash -- and ISSUES the loads of the first two table slots.
-    // batch_back, called just before the next front (i.e. after the next tile's
-    // scan), compares, finishes rare longer probe sequences and counts.  The L2
-    // round trip of the probe is hidden behind the scan instead of stalling the warp.
+    // batch_front takes up to 32 queued line starts of the CURRENT tile, one per lane: pack,
+    // barcode lookup, tag key, hash -- and ISSUES the loads of the first two table slots.
+    // batch_back, called when the next tile is opened, compares, finishes rare longer probe
+    // sequences and votes (MATCH.ANY); red_retire, after that tile's scan, issues the reds.
+    // The L2 round trip of the probe hides behind the refill, the MATCH behind the scan.
     bool pb_pending = false;              // uniform: a batch is between front and back
     int32_t pb_row = -1, pb_col = -1;     // per lane
     bool pb_probe = false;                // per lane: slots loaded, compare still to do
@@ -519,13 +497,10 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     uint4 pb_k0 = make_uint4(0, 0, 0, 0), pb_k1 = pb_k0;
     uint2 pb_m0 = make_uint2(0, 0), pb_m1 = pb_m0;      // len | flags, column (the first half of an entry's second 16 bytes)
 
-    auto batch_front = [&](uint32_t nb) {
-        uint32_t off = 0;
+    auto batch_front = [&](uint32_t qoff, uint32_t nb, uint32_t st) {
+        uint32_t off = st * STAGE;
         const bool have = lane < nb;
-        if (have) off = ws->q[(q_head + lane) & (QCAP - 1)];      // lanes without a read work on offset 0, results dropped
-        q_head += nb;
-        q_len -= nb;
-        q_old = q_old > nb ? q_old - nb : 0;
+        if (have) off = ws->q[qoff + lane];                       // lanes without a read work on the stage start, results dropped
         pb_row = -1;
         pb_col = -1;
         pb_probe = false;
@@ -666,26 +641,26 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             }
         }
         if (slow) {
-            const uint32_t se = off >= 2 * STAGE ? 2u : (off >= STAGE ? 1u : 0u);
-            const uint32_t p = off - se * STAGE;
-            const uint32_t tile = ws->meta[se].x;
-            const unsigned long long tile_off = (unsigned long long)tile * TILE;
+            const uint32_t p = off - st * STAGE;
+            const unsigned long long tile_off = (unsigned long long)cur_tile * TILE;
             const unsigned long long avail = a.n - tile_off;
             const uint32_t staged = avail < copy_bytes ? (uint32_t)avail : copy_bytes;
-            MatchResult mr = match_general(wbase + se * STAGE, p, staged, a.bytes + tile_off, avail, a.need, bar, bent, &a.tags);
+            MatchResult mr = match_general(wbase + st * STAGE, p, staged, a.bytes + tile_off, avail, a.need, bar, bent, &a.tags);
             pb_row = mr.row;
             pb_col = mr.col;
         }
+        __syncwarp();
         pb_pending = true;
     };
 
-    // The count update of a batch is retired one batch later: MATCH.ANY takes a while, and this
-    // way nothing waits for it.  (A segment's last update is retired before its weight changes.)
+    // The count update of a batch is issued a scan later than its vote: MATCH.ANY takes a while,
+    // and this way nothing waits for it.
     uint32_t pr_cell = NONE, pr_peers = 0;
+    int32_t pr_w = 1;
     auto red_retire = [&]() {
         // warp-aggregated: one red per distinct cell
         if (pr_cell != NONE && lane == (uint32_t)(__ffs(pr_peers) - 1))
-            atomicAdd(&ws->matrix[pr_cell], weight * (int32_t)__popc(pr_peers));
+            atomicAdd(&wmatrix[pr_cell], pr_w * (int32_t)__popc(pr_peers));
         pr_cell = NONE;
     };
 
@@ -726,46 +701,52 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             cell = (uint32_t)pb_row * a.cols + (uint32_t)pb_col;
         }
         pr_cell = cell;
+        pr_w = weight;
         pr_peers = __match_any_sync(FULL, cell);
         pb_pending = false;
     };
 
+    // ---- the tile loop ------------------------------------------------------------------------
+    // Rotated: an iteration FINISHES the tile that the previous iteration opened (ranks, emission,
+    // batch_front), refills its stage, and then OPENS the next one (batch_back, wait for its bytes,
+    // scan, red_retire).  Only straight-line code sits between batch_front's probe loads and
+    // batch_back, and between the vote and the reds: ptxas waits for everything outstanding at
+    // loop headers.
     uint32_t s = 0, parity = 0;
-    // The loop is rotated: an iteration FINISHES the tile that the previous iteration opened
-    // (ranks, emission, batch_front) and then OPENS the next one (wait for its bytes, scan).
-    // batch_back sits after the scan, so that the probe loads issued by batch_front are
-    // consumed a whole scan later with only straight-line code in between.
-    uint32_t extra = 0, sbase = 0;
-    bool seg_end = false, opened = false;
-    const uint8_t *buf = wbase;
-    uint32_t avail = 0;                   // bytes from the tile start to the end of the chunk, saturated
-    uint32_t scan_cnt = 0, scan_dev = 0;
+    uint32_t mk[MWORDS];                  // line-end (candidate) masks of my SPAN bytes of the open tile
+#pragma unroll
+    for (uint32_t j = 0; j < MWORDS; j++) mk[j] = 0;
+    uint32_t scan_dev = 0;
+    bool opened = false;
+
+    produce(0, cur_tile, cur_item, cur_tixf);
+    produce(1, nxt_tile, nxt_item, nxt_tixf);
+
     for (;;) {
         if (opened) {
-            // the candidate loops below walk the masks through shared memory (one loop
-            // over all candidates of a lane instead of one loop per mask word)
-            uint32_t cnt = scan_cnt;
-            uint32_t nz = 0;                 // bit j: my mask word j is not empty (only the rare paths ask)
-            bool nz_known = false;
-            auto need_nz = [&]() {
-                if (nz_known) return;
-#pragma unroll
-                for (uint32_t j = 0; j < MWORDS; j++)
-                    if (ws->mk[j][lane]) nz |= 1u << j;
-                nz_known = true;
-            };
+            const uint8_t *const buf = wbase + s * STAGE;
+            const uint32_t sbase = s * STAGE;
+            const uint32_t t = cur_tile;
+            const bool seg_end = (cur_tixf & TIX_LAST) != 0;
+            // Only a chunk's last tiles can be cut by the end of the data, only its first tile can
+            // follow an implicit line end: everything in between takes neither branch.
+            const bool edge = (t == 0) | (t + 2 >= a.num_tiles);
 
-            // exact line ends: '\n' ends a line; '\r' ends one unless a '\n' follows
-            // (Python universal newlines); every other control character is content.
-            auto classify = [&]() {
-                need_nz();
-                uint32_t nzl = nz;
-                cnt = 0;
-                nz = 0;
-                while (nzl) {
-                    const uint32_t j = __ffs(nzl) - 1u;
-                    nzl &= nzl - 1u;
-                    uint32_t m = ws->mk[j][lane], keepm = m;
+            uint32_t avail = 0xFFFFFFFFu;         // bytes from the tile start to the end of the chunk, saturated
+            if (t + 2 >= a.num_tiles) {
+                const unsigned long long avail64 = a.n - (unsigned long long)t * TILE;
+                avail = avail64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)avail64;
+            }
+            // Exact line ends: '\n' ends a line; '\r' ends one unless a '\n' follows (Python
+            // universal newlines); every other control character is content.  The scan's masks
+            // hold CANDIDATES; they are exact as long as every candidate is a line feed.  The
+            // first tile that has another one (a '\r', a tab, a byte >= 0xA0 ...) switches the warp
+            // to checking every candidate (sticky: such files have them everywhere).
+            if (classify_first | __any_sync(FULL, scan_dev != 0)) {
+                classify_first = true;
+#pragma unroll
+                for (uint32_t j = 0; j < MWORDS; j++) {
+                    uint32_t m = mk[j], keepm = m;
                     while (m) {
                         const uint32_t b = __ffs(m) - 1u;
                         m &= m - 1u;
@@ -776,48 +757,42 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                         if (c == '\r') end = (p + 1 < avail) && buf[p + 1] != '\n';
                         if (!end) keepm &= ~(1u << b);
                     }
-                    ws->mk[j][lane] = keepm;
-                    cnt += __popc(keepm);
-                    if (keepm) nz |= 1u << j;
+                    mk[j] = keepm;
                 }
-            };
-            bool verified = false, do_classify = classify_first;
-
-            uint32_t incl, total;
-            for (;;) {
-                if (do_classify) { classify(); verified = true; do_classify = false; }
-                // inclusive prefix sum of cnt over the lanes.  Counts are small: one ballot per bit of
-                // the count (independent of each other) instead of five dependent shuffles.
-                if (!__any_sync(FULL, cnt >= 8u)) {
-                    const uint32_t upto = 0xFFFFFFFFu >> (31u - lane);          // lanes 0..lane
-                    const uint32_t b0 = __ballot_sync(FULL, (cnt & 1u) != 0), b1 = __ballot_sync(FULL, (cnt & 2u) != 0),
-                                   b2 = __ballot_sync(FULL, (cnt & 4u) != 0);
-                    incl = __popc(b0 & upto) + 2u * __popc(b1 & upto) + 4u * __popc(b2 & upto);
-                    total = extra + __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
-                } else {
-                    incl = cnt;
+                __syncwarp();
+            }
+            uint32_t cntA = 0, cntB = 0;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        uint32_t o = __shfl_up_sync(FULL, incl, d);
-                        if (lane >= (uint32_t)d) incl += o;
-                    }
-                    total = extra + __shfl_sync(FULL, incl, 31);
-                }
-                if (!MATCH) break;
-                const uint32_t rho0 = extra + incl - cnt;       // rank of the line start after my first line end
+            for (uint32_t j = 0; j < MWORDS; j++) {
+                if (j < HALF_WORDS) cntA += __popc(mk[j]); else cntB += __popc(mk[j]);
+            }
+            uint32_t cnt = cntA + cntB;
+            uint32_t total = 0, nlive = 0;
 
+            // ---- the common tile: FASTQ text in the middle of a chunk ----------------------------
+            bool general = edge | has_limit | __any_sync(FULL, cnt >= 8u);
+            uint32_t incl = 0;
+            if (!general) {
+                // inclusive prefix sum of cnt over the lanes.  Counts are small: one ballot per bit
+                // of the count (independent of each other) instead of five dependent shuffles.
+                const uint32_t upto = 0xFFFFFFFFu >> (31u - lane);          // lanes 0..lane
+                const uint32_t b0 = __ballot_sync(FULL, (cnt & 1u) != 0), b1 = __ballot_sync(FULL, (cnt & 2u) != 0),
+                               b2 = __ballot_sync(FULL, (cnt & 4u) != 0);
+                incl = __popc(b0 & upto) + 2u * __popc(b1 & upto) + 4u * __popc(b2 & upto);
+                total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+            }
+            if (MATCH && !general) {
+                const uint32_t rhoA = incl - cnt;               // rank of the line start after my first line end
                 if (need_guess) {
                     // First lines of a segment whose position in the file is not known yet:
                     // find a line that looks like a FASTQ header ('@', then '+' two lines on,
                     // sequence and quality lines of equal length).  Any answer is acceptable --
                     // a wrong one is found and repaired by verify_kernel + the fix pass.
-                    {
-                        need_nz();
-                        uint32_t r = rho0, nzl = nz;
-                        while (nzl && r < GUESS_LINES + 5) {
-                            const uint32_t j = __ffs(nzl) - 1u;
-                            nzl &= nzl - 1u;
-                            uint32_t m = ws->mk[j][lane];
+                    if (rhoA < GUESS_LINES + 5) {
+                        uint32_t r = rhoA;
+#pragma unroll
+                        for (uint32_t j = 0; j < MWORDS; j++) {
+                            uint32_t m = mk[j];
                             while (m && r < GUESS_LINES + 5) {
                                 const uint32_t b = __ffs(m) - 1u;
                                 m &= m - 1u;
@@ -838,216 +813,213 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     phase = hits ? ((4u - ((uint32_t)(__ffs(hits) - 1) & 3u)) & 3u) : 0u;   // that line has index 0 mod 4
                     need_guess = false;
                 }
-
-                // ---- emission: queue the starts of sequence lines (index % 4 == 1) -----------
+                // ---- emission: the starts of sequence lines (index % 4 == 1) ----------------------
                 // rank 0 of this tile has index F = (first index of the segment) + seg_lines
                 const uint32_t a4 = (1u - (phase + seg_lines)) & 3u;         // first rank that is a sequence line
                 const uint32_t nq = total > a4 ? (total - a4 + 3u) >> 2 : 0u;
-                uint32_t nlive = nq;                                         // those below the read limit (a prefix)
-                if (has_limit) {                                             // only the fix pass applies a limit
-                    const unsigned long long first_idx = (ws->seg_first + seg_lines + a4) >> 2;
-                    nlive = 0;
-                    if (nq && first_idx < a.reads_limit) {
-                        unsigned long long room = a.reads_limit - first_idx;
-                        nlive = nq < room ? nq : (uint32_t)room;
+                // Each half of my span (HALF_WORDS mask words, then the rest) holds at most one
+                // such start in ordinary FASTQ: candidate number `skip` of the half.
+                const uint32_t rhoB = rhoA + cntA;
+                const uint32_t skipA = (a4 - rhoA) & 3u, skipB = (a4 - rhoB) & 3u;
+                if (__any_sync(FULL, (cntA > skipA + 4u) | (cntB > skipB + 4u)) | (nq > QCAP)) {
+                    general = true;                  // very short lines: the walk below handles any shape
+                } else {
+                    // candidate number `skip` of a half, found by counting through its mask words
+                    uint32_t mA = 0, pA = 0, rA = skipA, seen = 0;
+#pragma unroll
+                    for (uint32_t j = 0; j < HALF_WORDS; j++) {
+                        const uint32_t w = mk[j];
+                        if (skipA >= seen) { mA = w; pA = 32u * j; rA = skipA - seen; }
+                        seen += __popc(w);
+                    }
+                    uint32_t mB = 0, pB = 0, rB = skipB;
+                    seen = 0;
+#pragma unroll
+                    for (uint32_t j = HALF_WORDS; j < MWORDS; j++) {
+                        const uint32_t w = mk[j];
+                        if (skipB >= seen) { mB = w; pB = 32u * j; rB = skipB - seen; }
+                        seen += __popc(w);
+                    }
+                    if (rA >= 1u) mA &= mA - 1u;
+                    if (rA >= 2u) mA &= mA - 1u;
+                    if (rA >= 3u) mA &= mA - 1u;
+                    if (rB >= 1u) mB &= mB - 1u;
+                    if (rB >= 2u) mB &= mB - 1u;
+                    if (rB >= 3u) mB &= mB - 1u;
+                    const uint32_t mine = sbase + lane * SPAN;
+                    if (cntA > skipA) ws->q[(rhoA + skipA - a4) >> 2] = (uint16_t)(mine + pA + __ffs(mA));
+                    if (cntB > skipB) ws->q[(rhoB + skipB - a4) >> 2] = (uint16_t)(mine + pB + __ffs(mB));
+                    __syncwarp();
+                    nlive = nq;
+                    if (nq != 0) {
+                        batch_front(0, nq < 32u ? nq : 32u, s);
+                        if (nq > 32u) {              // short records: a second batch from the same tile
+                            batch_back();
+                            batch_front(32, nq - 32u, s);
+                        }
                     }
                 }
-                // my first sequence line: `skip0` candidates on, ordinal `jj0` among the tile's
-                const uint32_t skip0 = (a4 - rho0) & 3u;
-                const uint32_t jj0 = (rho0 + skip0 - a4) >> 2;
-                // Common case: everything fits one round, the read limit does not fall inside
-                // the tile and no lane holds more than one sequence-line start.
-                // (one vote: a lane with a candidate that is not '\n' sends the tile to the walk as well,
-                // which checks every candidate itself)
-                const bool simple = nlive == nq && nq <= PUSH_CAP &&
-                                    !__any_sync(FULL, (cnt > skip0 + 4u) | (!verified & (scan_dev != 0)));
-                bool redo = false;
-                for (uint32_t w0 = 0;;) {
-                    const uint32_t room = nlive - w0 < PUSH_CAP ? nlive - w0 : PUSH_CAP;
-                    const uint32_t qbase = q_head + q_len - w0;           // slot of ordinal 0
-                    uint32_t dev = 0;                                     // non-zero: a candidate is not '\n'
-                    if (simple) {
-                        // No walk: the scan has already compared every candidate with '\n' (scan_dev;
-                        // after a redo the masks are the classifier's and need no check), and the
-                        // one sequence-line start a lane can hold is its candidate number skip0 --
-                        // found by counting through the mask words.
-                        uint32_t m = 0, pb = 0, r = skip0, seen = 0;
+            }
+
+            // ---- every other tile: chunk edges, very short lines, the read limit of the fix pass ------
+            if (general) {
+                uint32_t extra = 0;                   // 1: the tile's first byte starts a line (chunk start)
+                if (t == 0) {
+                    if (prev_kind == PREV_NONE || prev_kind == PREV_LF) extra = 1;
+                    else if (prev_kind == PREV_CR && buf[0] != '\n') extra = 1;
+                }
+                incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t o = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= (uint32_t)d) incl += o;
+                }
+                total = extra + __shfl_sync(FULL, incl, 31);
+                if (MATCH) {
+                    const uint32_t rho0 = extra + incl - cnt;
+                    if (need_guess) {
+                        if (rho0 < GUESS_LINES + 5) {
+                            uint32_t r = rho0;
+#pragma unroll
+                            for (uint32_t j = 0; j < MWORDS; j++) {
+                                uint32_t m = mk[j];
+                                while (m && r < GUESS_LINES + 5) {
+                                    const uint32_t b = __ffs(m) - 1u;
+                                    m &= m - 1u;
+                                    ws->gs[r] = (uint16_t)(lane * SPAN + 32 * j + b + 1);
+                                    r++;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        const uint32_t have = total < GUESS_LINES + 5 ? total : GUESS_LINES + 5;
+                        bool hit = false;
+                        if (lane < GUESS_LINES && lane + 4 < have) {
+                            uint32_t p0 = ws->gs[lane], p1 = ws->gs[lane + 1], p2 = ws->gs[lane + 2], p3 = ws->gs[lane + 3],
+                                     p4 = ws->gs[lane + 4];
+                            hit = buf[p0] == '@' && buf[p2] == '+' && p2 - p1 == p4 - p3;
+                        }
+                        const uint32_t hits = __ballot_sync(FULL, hit);
+                        phase = hits ? ((4u - ((uint32_t)(__ffs(hits) - 1) & 3u)) & 3u) : 0u;
+                        need_guess = false;
+                    }
+                    const uint32_t a4 = (1u - (phase + seg_lines)) & 3u;
+                    const uint32_t nq = total > a4 ? (total - a4 + 3u) >> 2 : 0u;
+                    nlive = nq;                                                  // those below the read limit (a prefix)
+                    if (has_limit) {                                             // only the fix pass applies a limit
+                        const unsigned long long first_idx = (seg_first + seg_lines + a4) >> 2;
+                        nlive = 0;
+                        if (nq && first_idx < a.reads_limit) {
+                            unsigned long long room = a.reads_limit - first_idx;
+                            nlive = nq < room ? nq : (uint32_t)room;
+                        }
+                    }
+                    // my first sequence line: `skip0` candidates on, ordinal `jj0` among the tile's
+                    const uint32_t skip0 = (a4 - rho0) & 3u;
+                    const uint32_t jj0 = (rho0 + skip0 - a4) >> 2;
+                    // rounds of up to 32 starts, matched at once (no pipelining here)
+                    for (uint32_t w0 = 0; w0 < nlive; w0 += 32u) {
+                        const uint32_t room = nlive - w0 < 32u ? nlive - w0 : 32u;
+                        uint32_t skip = skip0, jj = jj0;
 #pragma unroll
                         for (uint32_t j = 0; j < MWORDS; j++) {
-                            const uint32_t w = ws->mk[j][lane];
-                            if (skip0 >= seen) { m = w; pb = 32u * j; r = skip0 - seen; }
-                            seen += __popc(w);
-                        }
-                        if (r >= 1u) m &= m - 1u;
-                        if (r >= 2u) m &= m - 1u;
-                        if (r >= 3u) m &= m - 1u;
-                        if (cnt > skip0)
-                            ws->q[(qbase + jj0) & (QCAP - 1)] = (uint16_t)(sbase + lane * SPAN + pb + __ffs(m));
-                    } else {
-                        need_nz();
-                        uint32_t nzl = nz, cur = 0, pbase = 0;
-                        uint32_t skip = skip0, jj = jj0;
-                        while ((cur | nzl) != 0) {
-                            if (cur == 0) {
-                                const uint32_t j = __ffs(nzl) - 1u;
-                                nzl &= nzl - 1u;
-                                cur = ws->mk[j][lane];
-                                pbase = lane * SPAN + 32 * j;
-                            }
-                            const uint32_t p = pbase + __ffs(cur) - 1u;
-                            cur &= cur - 1u;
-                            dev |= (uint32_t)buf[p] ^ 0x0Au;
-                            if (skip == 0) {
-                                if (jj - w0 < room) ws->q[(qbase + jj) & (QCAP - 1)] = (uint16_t)(sbase + p + 1);
-                                jj++;
-                                skip = 3;
-                            } else {
-                                skip--;
+                            uint32_t m = mk[j];
+                            while (m) {
+                                const uint32_t b = __ffs(m) - 1u;
+                                m &= m - 1u;
+                                if (skip == 0) {
+                                    if (jj - w0 < room) ws->q[jj - w0] = (uint16_t)(sbase + lane * SPAN + 32 * j + b + 1);
+                                    jj++;
+                                    skip = 3;
+                                } else {
+                                    skip--;
+                                }
                             }
                         }
+                        // the line that starts with the chunk's first byte
+                        if (extra != 0 && lane == 0 && a4 == 0 && w0 == 0) ws->q[0] = (uint16_t)sbase;
+                        __syncwarp();
+                        if (pb_pending) batch_back();
+                        batch_front(0, room, s);
+                        batch_back();
+                        __syncwarp();
                     }
-                    if (extra != 0)           // uniform; only a chunk's first tile can have it
-                        if (lane == 0 && a4 == 0 && w0 == 0 && room > 0) ws->q[qbase & (QCAP - 1)] = (uint16_t)sbase;
-                    if (!verified) {
-                        if (__any_sync(FULL, dev != 0)) { redo = true; break; }
-                        verified = true;
-                    }
-                    __syncwarp();
-                    q_len += room;
-                    w0 += room;
-                    // Match full warps.  After the tile's last round also drain what must not
-                    // wait: entries that point into the previous tile's stage have to go before
-                    // that stage is refilled, a segment's entries before its state (weight,
-                    // limit) changes.
-                    const bool last_round = w0 >= nlive;
-                    const bool flush = last_round && (seg_end || q_old > 0);
-                    if (q_len >= 32 || flush) {            // (most tiles that end without a full batch skip this)
-                        for (;;) {
-                            uint32_t nb = 0;
-                            if (q_len >= 32) nb = 32;
-                            else if (flush) nb = q_len;
-                            // the segment ends: nothing may stay in flight
-                            const bool finish = pb_pending && last_round && seg_end;
-                            if (nb == 0 && !finish) break;
-                            if (pb_pending) batch_back();      // rare here: a second batch from one tile, or a flush
-                            if (nb == 0) break;
-                            batch_front(nb);
-                            // Common case: nothing more to do for this tile.  Leave through a forward
-                            // branch -- ptxas waits for outstanding loads at loop headers, and the
-                            // probe loads just issued must stay in flight until batch_back.
-                            const bool again = q_len >= 32 || (last_round && (seg_end || (q_old > 0 && q_len > 0)));
-                            if (!again) break;
-                        }
-                    }
-                    if (last_round) break;
                 }
-                if (redo) {
-                    do_classify = true;
-                    classify_first = true;
-                    continue;
-                }
-                // reads numbered in this tile (those below the limit)
-                seg_reads += nlive;
-                break;
             }
             seg_lines += total;
+            seg_reads += nlive;
 
-            q_old = q_len;
-            if (seg_end) {                   // uniform, once per segment
-                red_retire();
-                if (lane == 0) {
-                    ws->reads += weight * (long long)seg_reads;
-                    if (a.mode == MODE_MAIN) {
-                        SegInfo si;
-                        si.lines = seg_lines;
-                        si.guess = phase;
-                        a.seginfo[ws->seg] = si;
-                    }
+            if (seg_end) {                   // uniform, once per segment: nothing may stay in flight
+                if (MATCH) {
+                    if (pb_pending) batch_back();
+                    red_retire();
+                }
+                my_reads += weight * (long long)seg_reads;
+                if (lane == 0 && a.mode == MODE_MAIN) {
+                    SegInfo si;
+                    si.lines = seg_lines;
+                    si.guess = phase;
+                    a.seginfo[seg_id] = si;
                 }
                 seg_reads = 0;
             }
 
-            // ---- refill the stage of the previous tile (nothing points into it any more) ---
+            // ---- refill this tile's stage (nothing points into it any more) --------------------
             __syncwarp();
-            if (lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                produce(s == 0 ? STAGES - 1 : s - 1);
-            }
-            if (++s == STAGES) { s = 0; parity ^= 1u; }
+            if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            cur_tile = nxt_tile;
+            cur_item = nxt_item;
+            cur_tixf = nxt_tixf;
+            produce(s, nxt_tile, nxt_item, nxt_tixf);
+            s ^= 1u;
+            if (s == 0) parity ^= 1u;
         }
 
         // ---- open the next tile ------------------------------------------------------
-        __syncwarp();                                 // lane 0's metadata of stage s (written two tiles ago at the latest)
-        const uint4 meta = ws->meta[s];
-        const uint32_t item = meta.y;
-        if (item == NONE) break;
-        const uint32_t tixf = meta.z;
-        const uint32_t t = meta.x;                    // tile index in the chunk
-        cur_tile = t;
+        if (cur_item == NONE) break;
         // the probe loads of the pending batch went out before the refill: by now they are back, and
-        // the MATCH.ANY issued at the end of batch_back has the whole scan to finish before the
-        // loop header (where ptxas waits for everything outstanding)
+        // the MATCH.ANY issued at the end of batch_back has the whole scan to finish
         if (MATCH && pb_pending) batch_back();
         if (!mbar_test(&full_bar[warp][s], parity)) mbar_wait(&full_bar[warp][s], parity);   // usually there already
 
-        if ((tixf & ~TIX_LAST) == 0) {     // a new segment starts
+        if ((cur_tixf & ~TIX_LAST) == 0) {     // a new segment starts
             seg_lines = 0;
             has_limit = false;
             weight = 1;
             need_guess = false;
-            uint32_t seg = item;
+            seg_id = cur_item;
             if (a.mode == MODE_FIX) {
-                const FixEntry fe = a.fix[item >> 1];
-                seg = fe.seg;
-                if (item & 1u) { phase = (uint32_t)fe.true_first & 3u; has_limit = true; if (lane == 0) ws->seg_first = fe.true_first; }
-                else           { phase = fe.guess & 3u; weight = -1; }
-            } else if (seg == 0) {
+                const FixEntry fe = a.fix[cur_item >> 1];
+                seg_id = fe.seg;
+                if (cur_item & 1u) { phase = (uint32_t)fe.true_first & 3u; has_limit = true; seg_first = fe.true_first; }
+                else               { phase = fe.guess & 3u; weight = -1; }
+            } else if (seg_id == 0) {
                 // known exactly
                 phase = (uint32_t)(a.use_arg_state ? a.line_base : a.state_in->next_line) & 3u;
             } else {
                 phase = 0;
                 need_guess = MATCH;
             }
-            if (lane == 0) ws->seg = seg;
-        }
-        seg_end = (tixf & TIX_LAST) != 0;
-
-        buf = wbase + s * STAGE;
-        sbase = s * STAGE;
-        // Only a chunk's last tiles can be cut by the end of the data, only its first tile can
-        // follow an implicit line end: everything in between takes neither branch.
-        avail = 0xFFFFFFFFu;
-        uint32_t valid = TILE;
-        bool last_tile = false;
-        if (t + 2 >= a.num_tiles) {
-            const unsigned long long avail64 = a.n - (unsigned long long)t * TILE;     // bytes from tile start to chunk end
-            avail = avail64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)avail64;
-            valid = avail < TILE ? avail : TILE;
-            last_tile = t == a.num_tiles - 1;
-        }
-        extra = 0;
-        if (t == 0) {
-            if (prev_kind == PREV_NONE || prev_kind == PREV_LF) extra = 1;
-            else if (prev_kind == PREV_CR && buf[0] != '\n') extra = 1;
         }
 
         // ---- scan: control-character mask of my SPAN bytes ----------------------
         // (lane l reads 16-byte units CHUNKS*l + i: with CHUNKS odd, eight consecutive
         // lanes hit eight different bank groups, so every 128-bit load is conflict free)
-        uint32_t mk[MWORDS];
         {
-            const uint4 *src = (const uint4 *)(buf + lane * SPAN);
-#pragma unroll
+            const uint4 *src = (const uint4 *)(wbase + s * STAGE + lane * SPAN);
             scan_dev = 0;
+#pragma unroll
             for (uint32_t i = 0; i < CHUNKS; i++) {
                 uint32_t m16 = ctl_mask16(src[i], scan_dev);
                 if (i & 1u) mk[i >> 1] |= m16 << 16; else mk[i >> 1] = m16;
             }
         }
-        if (last_tile) {
+        if (cur_tile == a.num_tiles - 1) {
             // The line that would start right after the last byte of the chunk is
             // numbered by the NEXT chunk (PREV_LF), and bytes at and after n do not
             // exist: keep line ends at p < valid - 1 only.
+            const unsigned long long avail64 = a.n - (unsigned long long)cur_tile * TILE;
+            const uint32_t valid = avail64 < TILE ? (uint32_t)avail64 : TILE;
             const uint32_t lim = valid - 1;
             const uint32_t first = lane * SPAN;
             const uint32_t keep = lim > first ? lim - first : 0;
@@ -1057,29 +1029,24 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 if (nb < 32) mk[j] &= (1u << nb) - 1u;
             }
             if (lane == 0) {
-                uint32_t c = buf[valid - 1];
+                uint32_t c = (wbase + s * STAGE)[valid - 1];
                 *a.last_kind = c == '\n' ? PREV_LF : (c == '\r' ? PREV_CR : PREV_OTHER);
             }
         }
-        // the masks go to shared memory right away (only their count stays in a register)
-        scan_cnt = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < MWORDS; j++) {
-            ws->mk[j][lane] = mk[j];
-            scan_cnt += __popc(mk[j]);
-        }
+        if (MATCH) red_retire();
         opened = true;
     }
 
+    // totals: one set of atomics per warp
     if (MATCH) {
-        // totals: one set of atomics per warp
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             my_bar += __shfl_xor_sync(FULL, my_bar, o);
             my_tag += __shfl_xor_sync(FULL, my_tag, o);
         }
-        if (lane == 0) {
-            const long long my_reads = ws->reads;
+    }
+    if (lane == 0) {
+        if (MATCH) {
             if (my_reads) atomicAdd(&a.totals[0], (unsigned long long)my_reads);
             if (my_bar) atomicAdd(&a.totals[1], (unsigned long long)(long long)my_bar);
             if (my_tag) atomicAdd(&a.totals[2], (unsigned long long)(long long)my_tag);
