@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define TDG_ABI_VERSION 1
+#define TDG_ABI_VERSION 2
 
 #define TDG_OK            0
 #define TDG_ERR_CUDA     -1   /* a CUDA runtime call failed (message has the CUDA error string) */
@@ -41,6 +41,7 @@ extern "C" {
 #define TDG_ERR_STATE    -4   /* call made out of order (e.g. submit before begin_file) */
 #define TDG_ERR_NOMEM    -5
 #define TDG_ERR_GZIP     -6   /* not a gzip stream / corrupt stream */
+#define TDG_ERR_UTF8     -7   /* tdg_count_file: the file is not valid UTF-8 (the reference reads in text mode) */
 
 /* flags for tdg_set_tags / tdg_begin_file */
 #define TDG_ANY_BASE      1u  /* the pattern set is the single empty pattern: matches
@@ -145,6 +146,12 @@ int         tdg_sync(tdg_ctx *ctx);
 int         tdg_file_totals(tdg_ctx *ctx, uint64_t totals[4]);
 /* Synchronise and copy the matrix to host (`out` may be NULL to skip). */
 int         tdg_read_matrix(tdg_ctx *ctx, int32_t *out);
+
+/* Overflow guard.  Cells are int32 on the device while the reference counts with unbounded
+ * Python integers (tagdigger_fun.py:237,266): *out receives the smallest cell of the matrix --
+ * counts only grow, so a negative value means that some cell passed INT32_MAX since the matrix
+ * was zeroed (callers raise OverflowError; see tagdigger_b200/counting.py).  Synchronous. */
+int         tdg_matrix_min(tdg_ctx *ctx, int32_t *out);
 
 /* Device pointer of the matrix and the CUDA stream the kernels run on, so the
  * caller can all-reduce the matrix in place (NCCL) right behind the last kernel:

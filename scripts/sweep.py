@@ -12,10 +12,11 @@ import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(REPO, "gpurun_variants")
 VARIANTS = {
-    "w15_c9": ["-DTDG_WARPS=15", "-DTDG_CHUNKS=9"],        # the library's geometry
-    "w16_c7": ["-DTDG_WARPS=16", "-DTDG_CHUNKS=7"],
-    "w14_c9": ["-DTDG_WARPS=14", "-DTDG_CHUNKS=9"],
-    "w12_c11": ["-DTDG_WARPS=12", "-DTDG_CHUNKS=11"],
+    "w14_c15": ["-DTDG_WARPS=14", "-DTDG_CHUNKS=15"],      # the library's geometry
+    "w13_c15": ["-DTDG_WARPS=13", "-DTDG_CHUNKS=15"],
+    "w12_c15": ["-DTDG_WARPS=12", "-DTDG_CHUNKS=15"],      # 3 warps per scheduler: up to 168 registers
+    "w15_c13": ["-DTDG_WARPS=15", "-DTDG_CHUNKS=13"],
+    "w16_c13": ["-DTDG_WARPS=16", "-DTDG_CHUNKS=13"],
 }
 
 

@@ -16,13 +16,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TDG_LIB") or os.path.join(_HERE, "libtagdigger_b200.so")   # TDG_LIB: tuning builds (scripts/sweep.py)
-_SOURCES = ["tdg_api.cu", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h", "tdg_trim.cuh", "tdg_split.cuh", "tdg_feed.h", "tdg_pgz.h", "tdg_csv.h"]
+_SOURCES = ["tdg_api.cu", "tdg_text.h", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h", "tdg_trim.cuh", "tdg_split.cuh", "tdg_feed.h", "tdg_pgz.h", "tdg_csv.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "20014,20011", "-shared"]
 
+ABI_VERSION = 2            # include/tagdigger_b200.h: TDG_ABI_VERSION
 TDG_OK = 0
-TDG_ERR_CUDA, TDG_ERR_ARG, TDG_ERR_IO, TDG_ERR_STATE, TDG_ERR_NOMEM, TDG_ERR_GZIP = -1, -2, -3, -4, -5, -6
+TDG_ERR_CUDA, TDG_ERR_ARG, TDG_ERR_IO, TDG_ERR_STATE, TDG_ERR_NOMEM, TDG_ERR_GZIP, TDG_ERR_UTF8 = -1, -2, -3, -4, -5, -6, -7
 TDG_ANY_BASE = 1
 TDG_PREV_NONE, TDG_PREV_LF, TDG_PREV_CR, TDG_PREV_OTHER = 0, 1, 2, 3
 TDG_LINE_CHAINED = (1 << 64) - 1
@@ -32,7 +33,7 @@ NO_LIMIT = (1 << 63)
 
 EXPORTS = """tdg_abi_version tdg_create tdg_destroy tdg_last_error tdg_set_tags tdg_set_matrix
 tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end_file tdg_count_device
-tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix
+tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix tdg_matrix_min
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
 tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch tdg_split_begin tdg_split_block tdg_feed_open tdg_feed_read tdg_feed_close tdg_match_batch tdg_write_counts_csv tdg_write_geno_csv""".split()
@@ -81,10 +82,17 @@ def lib():
     if _stale():
         try:
             build()
-        except (OSError, RuntimeError):
+        except (OSError, RuntimeError) as e:
             if not os.path.exists(LIB_PATH):
                 raise
+            import warnings
+            warnings.warn("tagdigger_b200: the sources are newer than %s and rebuilding failed (%s); loading the "
+                          "existing library -- its ABI version is checked below" % (LIB_PATH, str(e)[:200]), RuntimeWarning)
     L = ctypes.CDLL(LIB_PATH)
+    L.tdg_abi_version.restype = ctypes.c_int
+    if L.tdg_abi_version() != ABI_VERSION:
+        raise RuntimeError("%s has ABI version %d, this package needs %d: rebuild it (python -c 'import "
+                           "__graft_entry__ as g; g.build()')" % (LIB_PATH, L.tdg_abi_version(), ABI_VERSION))
     vp, u64, u32, i32, sz = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_size_t
     sig = {
         "tdg_abi_version": (i32, []),
@@ -105,6 +113,7 @@ def lib():
         "tdg_sync": (i32, [vp]),
         "tdg_file_totals": (i32, [vp, vp]),
         "tdg_read_matrix": (i32, [vp, vp]),
+        "tdg_matrix_min": (i32, [vp, vp]),
         "tdg_matrix_device_ptr": (vp, [vp]),
         "tdg_stream": (vp, [vp]),
         "tdg_stream_wait": (i32, [vp, vp]),
@@ -256,6 +265,7 @@ class Engine(object):
     def set_matrix(self, rows, cols):
         self._ck(self._L.tdg_set_matrix(self._h, rows, cols))
         self.rows, self.cols = rows, cols
+        self._hits = 0
 
     def bind_matrix(self, dev_ptr, rows, cols):
         self._ck(self._L.tdg_bind_matrix(self._h, dev_ptr, rows, cols))
@@ -263,6 +273,7 @@ class Engine(object):
 
     def zero_matrix(self):
         self._ck(self._L.tdg_zero_matrix(self._h))
+        self._hits = 0
 
     def begin_file(self, patterns, rows, tag_offs, any_base=False):
         blob, off = _csr(patterns, np.uint32)
@@ -302,6 +313,7 @@ class Engine(object):
     def count_file(self, path, gz, reads_limit=NO_LIMIT):
         tot = np.zeros(4, dtype=np.uint64)
         self._ck(self._L.tdg_count_file(self._h, os.fsencode(path), 1 if gz else 0, reads_limit, tot.ctypes.data))
+        self.note_hits(int(tot[2]))
         return [int(x) for x in tot]
 
     def sync(self):
@@ -311,6 +323,19 @@ class Engine(object):
         tot = np.zeros(4, dtype=np.uint64)
         self._ck(self._L.tdg_file_totals(self._h, tot.ctypes.data))
         return [int(x) for x in tot]
+
+    def note_hits(self, hits):
+        """Overflow guard (cells are int32, the reference's counts are unbounded Python ints):
+        ``hits`` more reads were counted since the last check.  While fewer than 2**31 reads have
+        been counted into the matrix no cell can have wrapped; beyond that the smallest cell is
+        looked at (a wrapped cell is negative) and OverflowError raised."""
+        self._hits = getattr(self, "_hits", 0) + int(hits)
+        if self._hits >= (1 << 31):
+            m = ctypes.c_int32(0)
+            self._ck(self._L.tdg_matrix_min(self._h, ctypes.byref(m)))
+            if m.value < 0 or int(hits) >= (1 << 32):
+                raise OverflowError("a count passed 2**31 - 1: the device matrix holds int32 cells "
+                                    "(the reference counts with unbounded integers); split the key")
 
     def read_matrix(self, out=None):
         if out is None:

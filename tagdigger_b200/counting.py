@@ -69,6 +69,10 @@ def _run_file(eng, fqfile, limit):
             raise _gzip_exception(e.message)
         if e.code == _native.TDG_ERR_IO:
             raise OSError(e.message)
+        if e.code == _native.TDG_ERR_UTF8:
+            # open(f, 'r') / gzip.open(f, 'rt') decode the file as UTF-8 (tagdigger_fun.py:240-243)
+            pos = int(e.message.split()[1].rstrip(":")) if e.message.startswith("position ") else 0
+            raise UnicodeDecodeError("utf-8", b"\xff", 0, 1, "invalid UTF-8 at byte %d (%s)" % (pos, e.message))
         raise
 
 

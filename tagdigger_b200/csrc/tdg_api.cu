@@ -18,6 +18,7 @@
 #include "tdg_kernel.cuh"
 #include "tdg_csv.h"
 #include "tdg_feed.h"
+#include "tdg_text.h"
 #include "tdg_tables.h"
 #include "tdg_trim.cuh"
 #include "tdg_split.cuh"
@@ -790,6 +791,26 @@ int tdg_read_matrix(tdg_ctx *ctx, int32_t *out)
     return TDG_OK;
 }
 
+int tdg_matrix_min(tdg_ctx *ctx, int32_t *out)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!ctx->d_matrix) return fail(ctx, TDG_ERR_STATE, "no matrix");
+    if (!out) return fail(ctx, TDG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    int32_t *d_min = (int32_t *)(ctx->d_totals + 3);          // the spare word behind the three totals
+    const int32_t init = 0x7FFFFFFF;
+    CK(cudaMemcpyAsync(d_min, &init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t cells = ctx->rows * ctx->cols;
+    unsigned grid = (unsigned)std::min<size_t>(((size_t)cells + 255) / 256, (size_t)ctx->sm_count * 8);
+    tdg::min_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_matrix, cells, d_min);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+    CK(cudaMemcpyAsync(out, d_min, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TDG_OK;
+}
+
 void *tdg_matrix_device_ptr(tdg_ctx *ctx) { return ctx ? ctx->d_matrix : nullptr; }
 void *tdg_stream(tdg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
@@ -924,6 +945,9 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
         uint8_t *p = nullptr;
         size_t n = 0;
         int state = 0;   // 0 free, 1 full
+        bool high = false;      // some byte >= 0x80: the text needs UTF-8 validation
+        int err = 0;            // the read that should have filled this buffer failed
+        std::string msg;
     } bufs[NBUF];
     static_assert(NBUF == 3, "tdg_ctx::file_buf holds three buffers");
     if (ctx->file_buf_cap < ctx->chunk_bytes) {
@@ -947,62 +971,81 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     for (int i = 0; i < NBUF; i++) bufs[i].p = ctx->file_buf[i];
     std::mutex mu;
     std::condition_variable cv;
-    bool eof = false, stop = false;
-    int io_err = 0;
-    std::string io_msg;
+    bool stop = false;
+    // With a read limit the reference stops reading at the maxreads'th sequence line
+    // (tagdigger_fun.py:272-273): feed smaller pieces, so that little is read, inflated and copied
+    // beyond that point.
+    const bool limited = reads_limit < ((uint64_t)1 << 61);
     size_t chunk = ctx->chunk_bytes;
+    if (limited) chunk = std::min<size_t>(chunk, (size_t)8 << 20);
 
     std::thread reader([&]() {
         // host feed: parallel pread / parallel BGZF inflate / zlib, see tdg_feed.h
         tdg::Feeder feed;
         int orc = feed.open(path, gz != 0);
-        if (orc) { io_err = orc; io_msg = feed.error(); }
         int bi = 0;
-        while (!io_err) {
+        for (;;) {
             Buf &b = bufs[bi];
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return b.state == 0 || stop; });
                 if (stop) break;
             }
-            long long r = feed.fill(b.p, chunk);
+            long long r = orc ? orc : feed.fill(b.p, chunk);
             size_t got = 0;
-            if (r < 0) { io_err = (int)r; io_msg = feed.error(); }
+            int err = 0;
+            std::string msg;
+            if (r < 0) { err = (int)r; msg = feed.error(); }
             else got = (size_t)r;
+            const bool high = got ? tdg::has_high_bit_mt(b.p, got, feed.threads()) : false;
             {
                 std::lock_guard<std::mutex> lk(mu);
                 b.n = got;
+                b.high = high;
+                b.err = err;
+                b.msg = msg;
                 b.state = 1;
-                if (got == 0 || io_err) eof = true;
             }
             cv.notify_all();
-            if (got == 0 || io_err) break;
+            if (got == 0 || err) break;           // end of file, or the defect: nothing comes after it
             bi = (bi + 1) % NBUF;
-        }
-        if (io_err) {
-            std::lock_guard<std::mutex> lk(mu);
-            eof = true;
-            cv.notify_all();
         }
     });
 
     int bi = 0;
     int result = TDG_OK;
+    tdg::Utf8State u8;
+    tdg::LineLimit ll;
+    // the read with index maxreads-1 is line 4*maxreads-3: everything up to line end number
+    // 4*maxreads-2 is needed, nothing beyond it is looked at
+    if (limited) ll.remaining = reads_limit ? 4 * reads_limit - 2 : 1;
+    bool at_eof = false;
     for (;;) {
         Buf &b = bufs[bi];
         {
             std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return b.state == 1 || (eof && b.state != 1); });
-            if (b.state != 1) break;      // reader ended (error before filling this buffer)
+            cv.wait(lk, [&] { return b.state == 1; });
         }
-        if (b.n == 0) break;
-        result = submit_impl(ctx, b.p, b.n, reads_limit, true);
+        if (b.err) { result = fail(ctx, b.err, b.msg); break; }
+        if (b.n == 0) { at_eof = true; break; }
+        size_t use = limited ? ll.feed(b.p, b.n) : b.n;
+        // text mode: the bytes the loop reads must be valid UTF-8 (open(f, 'r'), errors='strict')
+        if (b.high || u8.need) {
+            long long bad = tdg::utf8_feed(u8, b.p, use);
+            if (bad >= 0) {
+                result = fail(ctx, TDG_ERR_UTF8, "position " + std::to_string(bad) + ": invalid UTF-8 in " + path);
+                break;
+            }
+        } else {
+            u8.offset += use;
+        }
+        if (use) result = submit_impl(ctx, b.p, use, reads_limit, true);
         {
             std::lock_guard<std::mutex> lk(mu);
             b.state = 0;
         }
         cv.notify_all();
-        if (result) break;
+        if (result || ll.reached) break;
         bi = (bi + 1) % NBUF;
     }
     {
@@ -1011,7 +1054,8 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     }
     cv.notify_all();
     reader.join();
-    if (result == TDG_OK && io_err) result = fail(ctx, io_err, io_msg);
+    if (result == TDG_OK && at_eof && tdg::utf8_finish(u8) >= 0)
+        result = fail(ctx, TDG_ERR_UTF8, "position " + std::to_string(tdg::utf8_finish(u8)) + ": unexpected end of data in " + path);
     if (result == TDG_OK) result = end_file_impl(ctx, reads_limit);
     if (result != TDG_OK) ctx->carry_len = 0;
     cudaStreamSynchronize(ctx->copy_stream);

@@ -74,7 +74,10 @@ constexpr uint32_t HALF_WORDS = MWORDS / 2;        // a lane's span is handled a
 constexpr uint32_t TILE = 32 * SPAN;               // 7,680 bytes per warp tile: about one batch of 32 reads
 constexpr uint32_t HALO = TDG_HALO;                // bytes staged past a tile (<= TDG_HALO_BYTES)
 constexpr uint32_t STAGE = TILE + HALO;            // one ring stage
-constexpr int      STAGES = 2;                     // the tile being processed + the one in flight
+#ifndef TDG_STAGES
+#define TDG_STAGES 2
+#endif
+constexpr int      STAGES = TDG_STAGES;            // the tile being processed + the one(s) in flight
 constexpr uint32_t RING = STAGES * STAGE;          // bytes of shared memory per warp
 constexpr uint32_t QCAP = 64;                      // sequence-line starts a tile can queue on the common path
 constexpr uint32_t BAR_SMEM_MAX = 10240;           // barcode tables up to this size (384-plex: 7.2 KB) are copied to smem
@@ -433,6 +436,11 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 p_item = NONE;
                 p_ntiles = NONE;                                   // never equal to p_tix again: no more tickets
             }
+            // The ticket and (fix pass) the list entry are LOADED values: pin them down inside this rare
+            // branch.  Otherwise the wait for them is placed at their first use after the branch, where
+            // it runs every tile and -- scoreboards being few and shared -- also waits for the probe
+            // loads that batch_front has in flight.
+            asm volatile("" ::"r"(p_item), "r"(p_seg), "r"(p_ntiles));
         }
         m_tile = p_seg * a.seg_tiles + p_tix;
         m_item = p_item;
@@ -461,21 +469,19 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     }
     const uint4 *tag_entries = (const uint4 *)a.tags.entries;
     int32_t my_bar = 0, my_tag = 0;
-    long long my_reads = 0;               // uniform: reads numbered by this warp (signed: the fix pass subtracts)
 
     // ---- per-segment state (uniform across the warp) -----------------------------------------
     uint32_t seg_lines = 0;               // line starts numbered so far
     uint32_t seg_reads = 0;               // reads numbered so far (those below the limit)
-    uint32_t seg_id = 0;
-    unsigned long long seg_first = 0;     // fix pass: index of the segment's first line start
     uint32_t phase = 0;                   // (assumed) index of the segment's first line start, mod 4
     bool has_limit = false;               // fix pass, true numbering: a.reads_limit applies
     int32_t weight = 1;
     bool need_guess = false;
     bool classify_first = false;          // sticky: this input has control characters other than '\n'
 
-    // metadata of the tile being processed (cur) and of the one in flight (nxt)
-    uint32_t cur_tile = 0, cur_item = NONE, cur_tixf = 0, nxt_tile = 0, nxt_item = NONE, nxt_tixf = 0;
+    // metadata of the tile being processed (cur) and of the ones in flight (nxt, oldest first)
+    uint32_t cur_tile = 0, cur_item = NONE, cur_tixf = 0;
+    uint32_t nxt_tile[STAGES - 1], nxt_item[STAGES - 1], nxt_tixf[STAGES - 1];
 
     // 128-bit compare of a table entry with the read's key over the entry's length
     auto tag_differs = [&](const uint4 &k, uint32_t L, uint32_t T0, uint32_t T1, uint32_t T2, uint32_t T3) -> uint32_t {
@@ -655,12 +661,11 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
 
     // The count update of a batch is issued a scan later than its vote: MATCH.ANY takes a while,
     // and this way nothing waits for it.
-    uint32_t pr_cell = NONE, pr_peers = 0;
-    int32_t pr_w = 1;
+    uint32_t pr_cell = NONE, pr_peers = 0;         // (retired within the segment of their batch: `weight` still applies)
     auto red_retire = [&]() {
         // warp-aggregated: one red per distinct cell
         if (pr_cell != NONE && lane == (uint32_t)(__ffs(pr_peers) - 1))
-            atomicAdd(&wmatrix[pr_cell], pr_w * (int32_t)__popc(pr_peers));
+            asm volatile("red.global.add.s32 [%0], %1;" ::"l"(wmatrix + pr_cell), "r"(weight * (int32_t)__popc(pr_peers)) : "memory");
         pr_cell = NONE;
     };
 
@@ -701,7 +706,6 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             cell = (uint32_t)pb_row * a.cols + (uint32_t)pb_col;
         }
         pr_cell = cell;
-        pr_w = weight;
         pr_peers = __match_any_sync(FULL, cell);
         pb_pending = false;
     };
@@ -720,7 +724,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     bool opened = false;
 
     produce(0, cur_tile, cur_item, cur_tixf);
-    produce(1, nxt_tile, nxt_item, nxt_tixf);
+#pragma unroll
+    for (int k = 0; k < STAGES - 1; k++) produce(k + 1, nxt_tile[k], nxt_item[k], nxt_tixf[k]);
 
     for (;;) {
         if (opened) {
@@ -731,11 +736,17 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             // Only a chunk's last tiles can be cut by the end of the data, only its first tile can
             // follow an implicit line end: everything in between takes neither branch.
             const bool edge = (t == 0) | (t + 2 >= a.num_tiles);
-
             uint32_t avail = 0xFFFFFFFFu;         // bytes from the tile start to the end of the chunk, saturated
-            if (t + 2 >= a.num_tiles) {
-                const unsigned long long avail64 = a.n - (unsigned long long)t * TILE;
-                avail = avail64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)avail64;
+            uint32_t extra = 0;                   // 1: the tile's first byte starts a line (chunk start)
+            if (edge) {
+                if (t + 2 >= a.num_tiles) {
+                    const unsigned long long avail64 = a.n - (unsigned long long)t * TILE;
+                    avail = avail64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)avail64;
+                }
+                if (t == 0) {
+                    if (prev_kind == PREV_NONE || prev_kind == PREV_LF) extra = 1;
+                    else if (prev_kind == PREV_CR && buf[0] != '\n') extra = 1;
+                }
             }
             // Exact line ends: '\n' ends a line; '\r' ends one unless a '\n' follows (Python
             // universal newlines); every other control character is content.  The scan's masks
@@ -761,28 +772,34 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 }
                 __syncwarp();
             }
-            uint32_t cntA = 0, cntB = 0;
+            uint32_t cntA = 0, cntB = 0;          // line ends in the two halves of my span
 #pragma unroll
             for (uint32_t j = 0; j < MWORDS; j++) {
                 if (j < HALF_WORDS) cntA += __popc(mk[j]); else cntB += __popc(mk[j]);
             }
-            uint32_t cnt = cntA + cntB;
-            uint32_t total = 0, nlive = 0;
+            const uint32_t cnt = cntA + cntB;
 
-            // ---- the common tile: FASTQ text in the middle of a chunk ----------------------------
-            bool general = edge | has_limit | __any_sync(FULL, cnt >= 8u);
-            uint32_t incl = 0;
-            if (!general) {
-                // inclusive prefix sum of cnt over the lanes.  Counts are small: one ballot per bit
-                // of the count (independent of each other) instead of five dependent shuffles.
+            // ---- ranks: inclusive prefix sum of cnt over the lanes.  Counts are small: one ballot
+            // per bit of the count (independent of each other) instead of five dependent shuffles.
+            uint32_t incl, total;
+            if (!__any_sync(FULL, cnt >= 8u)) {
                 const uint32_t upto = 0xFFFFFFFFu >> (31u - lane);          // lanes 0..lane
                 const uint32_t b0 = __ballot_sync(FULL, (cnt & 1u) != 0), b1 = __ballot_sync(FULL, (cnt & 2u) != 0),
                                b2 = __ballot_sync(FULL, (cnt & 4u) != 0);
                 incl = __popc(b0 & upto) + 2u * __popc(b1 & upto) + 4u * __popc(b2 & upto);
-                total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+                total = extra + __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+            } else {
+                incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t o = __shfl_up_sync(FULL, incl, d);
+                    if (lane >= (uint32_t)d) incl += o;
+                }
+                total = extra + __shfl_sync(FULL, incl, 31);
             }
-            if (MATCH && !general) {
-                const uint32_t rhoA = incl - cnt;               // rank of the line start after my first line end
+            uint32_t nlive = 0;
+            if (MATCH) {
+                const uint32_t rhoA = extra + incl - cnt;       // rank of the line start after my first line end
                 if (need_guess) {
                     // First lines of a segment whose position in the file is not known yet:
                     // find a line that looks like a FASTQ header ('@', then '+' two lines on,
@@ -817,13 +834,24 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 // rank 0 of this tile has index F = (first index of the segment) + seg_lines
                 const uint32_t a4 = (1u - (phase + seg_lines)) & 3u;         // first rank that is a sequence line
                 const uint32_t nq = total > a4 ? (total - a4 + 3u) >> 2 : 0u;
-                // Each half of my span (HALF_WORDS mask words, then the rest) holds at most one
-                // such start in ordinary FASTQ: candidate number `skip` of the half.
+                nlive = nq;                                                  // those below the read limit (a prefix)
+                if (has_limit) {                                             // only the fix pass applies a limit
+                    const unsigned long long seg_first = a.fix[cur_item >> 1].true_first;   // index of the segment's first line start
+                    const unsigned long long first_idx = (seg_first + seg_lines + a4) >> 2;
+                    nlive = 0;
+                    if (nq && first_idx < a.reads_limit) {
+                        unsigned long long room = a.reads_limit - first_idx;
+                        nlive = nq < room ? nq : (uint32_t)room;
+                    }
+                }
+                // Each half of my span (HALF_WORDS mask words, then the rest; <= 128 bytes each) holds
+                // at most one such start in ordinary FASTQ: candidate number `skip` of the half.
                 const uint32_t rhoB = rhoA + cntA;
                 const uint32_t skipA = (a4 - rhoA) & 3u, skipB = (a4 - rhoB) & 3u;
-                if (__any_sync(FULL, (cntA > skipA + 4u) | (cntB > skipB + 4u)) | (nq > QCAP)) {
-                    general = true;                  // very short lines: the walk below handles any shape
-                } else {
+                // The common tile: the middle of a chunk, no read limit, no half with two starts.
+                const bool fast = !(edge | has_limit | (nq > QCAP)) &&
+                                  !__any_sync(FULL, (cntA > skipA + 4u) | (cntB > skipB + 4u));
+                if (fast) {
                     // candidate number `skip` of a half, found by counting through its mask words
                     uint32_t mA = 0, pA = 0, rA = skipA, seen = 0;
 #pragma unroll
@@ -849,77 +877,17 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     const uint32_t mine = sbase + lane * SPAN;
                     if (cntA > skipA) ws->q[(rhoA + skipA - a4) >> 2] = (uint16_t)(mine + pA + __ffs(mA));
                     if (cntB > skipB) ws->q[(rhoB + skipB - a4) >> 2] = (uint16_t)(mine + pB + __ffs(mB));
-                    __syncwarp();
-                    nlive = nq;
-                    if (nq != 0) {
-                        batch_front(0, nq < 32u ? nq : 32u, s);
-                        if (nq > 32u) {              // short records: a second batch from the same tile
-                            batch_back();
-                            batch_front(32, nq - 32u, s);
-                        }
-                    }
                 }
-            }
-
-            // ---- every other tile: chunk edges, very short lines, the read limit of the fix pass ------
-            if (general) {
-                uint32_t extra = 0;                   // 1: the tile's first byte starts a line (chunk start)
-                if (t == 0) {
-                    if (prev_kind == PREV_NONE || prev_kind == PREV_LF) extra = 1;
-                    else if (prev_kind == PREV_CR && buf[0] != '\n') extra = 1;
-                }
-                incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    uint32_t o = __shfl_up_sync(FULL, incl, d);
-                    if (lane >= (uint32_t)d) incl += o;
-                }
-                total = extra + __shfl_sync(FULL, incl, 31);
-                if (MATCH) {
-                    const uint32_t rho0 = extra + incl - cnt;
-                    if (need_guess) {
-                        if (rho0 < GUESS_LINES + 5) {
-                            uint32_t r = rho0;
-#pragma unroll
-                            for (uint32_t j = 0; j < MWORDS; j++) {
-                                uint32_t m = mk[j];
-                                while (m && r < GUESS_LINES + 5) {
-                                    const uint32_t b = __ffs(m) - 1u;
-                                    m &= m - 1u;
-                                    ws->gs[r] = (uint16_t)(lane * SPAN + 32 * j + b + 1);
-                                    r++;
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        const uint32_t have = total < GUESS_LINES + 5 ? total : GUESS_LINES + 5;
-                        bool hit = false;
-                        if (lane < GUESS_LINES && lane + 4 < have) {
-                            uint32_t p0 = ws->gs[lane], p1 = ws->gs[lane + 1], p2 = ws->gs[lane + 2], p3 = ws->gs[lane + 3],
-                                     p4 = ws->gs[lane + 4];
-                            hit = buf[p0] == '@' && buf[p2] == '+' && p2 - p1 == p4 - p3;
-                        }
-                        const uint32_t hits = __ballot_sync(FULL, hit);
-                        phase = hits ? ((4u - ((uint32_t)(__ffs(hits) - 1) & 3u)) & 3u) : 0u;
-                        need_guess = false;
-                    }
-                    const uint32_t a4 = (1u - (phase + seg_lines)) & 3u;
-                    const uint32_t nq = total > a4 ? (total - a4 + 3u) >> 2 : 0u;
-                    nlive = nq;                                                  // those below the read limit (a prefix)
-                    if (has_limit) {                                             // only the fix pass applies a limit
-                        const unsigned long long first_idx = (seg_first + seg_lines + a4) >> 2;
-                        nlive = 0;
-                        if (nq && first_idx < a.reads_limit) {
-                            unsigned long long room = a.reads_limit - first_idx;
-                            nlive = nq < room ? nq : (uint32_t)room;
-                        }
-                    }
-                    // my first sequence line: `skip0` candidates on, ordinal `jj0` among the tile's
-                    const uint32_t skip0 = (a4 - rho0) & 3u;
-                    const uint32_t jj0 = (rho0 + skip0 - a4) >> 2;
-                    // rounds of up to 32 starts, matched at once (no pipelining here)
-                    for (uint32_t w0 = 0; w0 < nlive; w0 += 32u) {
-                        const uint32_t room = nlive - w0 < 32u ? nlive - w0 : 32u;
+                // ---- batches of up to 32 starts, one per lane.  The common tile has one (about
+                // 30 reads of 250 bytes), whose probe loads stay in flight until the next tile's
+                // scan is half done; the loop is left through a forward branch (ptxas waits for
+                // everything outstanding at loop headers).
+                for (uint32_t w0 = 0; w0 < nlive;) {
+                    const uint32_t room = nlive - w0 < 32u ? nlive - w0 : 32u;
+                    if (!fast) {
+                        // any other tile (chunk edges, very short lines, the read limit of the fix
+                        // pass): walk my candidates; ordinals w0 .. w0+room go to q[0 .. room)
+                        const uint32_t skip0 = skipA, jj0 = (rhoA + skipA - a4) >> 2;
                         uint32_t skip = skip0, jj = jj0;
 #pragma unroll
                         for (uint32_t j = 0; j < MWORDS; j++) {
@@ -938,12 +906,12 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                         }
                         // the line that starts with the chunk's first byte
                         if (extra != 0 && lane == 0 && a4 == 0 && w0 == 0) ws->q[0] = (uint16_t)sbase;
-                        __syncwarp();
-                        if (pb_pending) batch_back();
-                        batch_front(0, room, s);
-                        batch_back();
-                        __syncwarp();
                     }
+                    __syncwarp();
+                    if (pb_pending) batch_back();
+                    batch_front(fast ? w0 : 0u, room, s);
+                    w0 += room;
+                    if (w0 >= nlive) break;
                 }
             }
             seg_lines += total;
@@ -954,12 +922,15 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     if (pb_pending) batch_back();
                     red_retire();
                 }
-                my_reads += weight * (long long)seg_reads;
-                if (lane == 0 && a.mode == MODE_MAIN) {
-                    SegInfo si;
-                    si.lines = seg_lines;
-                    si.guess = phase;
-                    a.seginfo[seg_id] = si;
+                if (lane == 0) {
+                    // reads numbered by this segment (signed: the fix pass subtracts)
+                    if (MATCH && seg_reads) atomicAdd(&a.totals[0], (unsigned long long)(weight * (long long)seg_reads));
+                    if (a.mode == MODE_MAIN) {
+                        SegInfo si;
+                        si.lines = seg_lines;
+                        si.guess = phase;
+                        a.seginfo[cur_item] = si;          // (main pass: the work item is the segment)
+                    }
                 }
                 seg_reads = 0;
             }
@@ -967,19 +938,21 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             // ---- refill this tile's stage (nothing points into it any more) --------------------
             __syncwarp();
             if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            cur_tile = nxt_tile;
-            cur_item = nxt_item;
-            cur_tixf = nxt_tixf;
-            produce(s, nxt_tile, nxt_item, nxt_tixf);
-            s ^= 1u;
-            if (s == 0) parity ^= 1u;
+            cur_tile = nxt_tile[0];
+            cur_item = nxt_item[0];
+            cur_tixf = nxt_tixf[0];
+#pragma unroll
+            for (int k = 0; k + 1 < STAGES - 1; k++) {
+                nxt_tile[k] = nxt_tile[k + 1];
+                nxt_item[k] = nxt_item[k + 1];
+                nxt_tixf[k] = nxt_tixf[k + 1];
+            }
+            produce(s, nxt_tile[STAGES - 2], nxt_item[STAGES - 2], nxt_tixf[STAGES - 2]);
+            if (++s == STAGES) { s = 0; parity ^= 1u; }
         }
 
         // ---- open the next tile ------------------------------------------------------
         if (cur_item == NONE) break;
-        // the probe loads of the pending batch went out before the refill: by now they are back, and
-        // the MATCH.ANY issued at the end of batch_back has the whole scan to finish
-        if (MATCH && pb_pending) batch_back();
         if (!mbar_test(&full_bar[warp][s], parity)) mbar_wait(&full_bar[warp][s], parity);   // usually there already
 
         if ((cur_tixf & ~TIX_LAST) == 0) {     // a new segment starts
@@ -987,29 +960,34 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             has_limit = false;
             weight = 1;
             need_guess = false;
-            seg_id = cur_item;
             if (a.mode == MODE_FIX) {
                 const FixEntry fe = a.fix[cur_item >> 1];
-                seg_id = fe.seg;
-                if (cur_item & 1u) { phase = (uint32_t)fe.true_first & 3u; has_limit = true; seg_first = fe.true_first; }
+                if (cur_item & 1u) { phase = (uint32_t)fe.true_first & 3u; has_limit = true; }
                 else               { phase = fe.guess & 3u; weight = -1; }
-            } else if (seg_id == 0) {
+            } else if (cur_item == 0) {
                 // known exactly
                 phase = (uint32_t)(a.use_arg_state ? a.line_base : a.state_in->next_line) & 3u;
             } else {
                 phase = 0;
                 need_guess = MATCH;
             }
+            asm volatile("" ::"r"(phase));     // a loaded value: see produce
         }
 
         // ---- scan: control-character mask of my SPAN bytes ----------------------
         // (lane l reads 16-byte units CHUNKS*l + i: with CHUNKS odd, eight consecutive
         // lanes hit eight different bank groups, so every 128-bit load is conflict free)
+        // The pending batch is finished in the middle of the scan: its probe loads went out before
+        // the refill and have had half a scan more to come back, and the vote (MATCH.ANY) issued
+        // at the end of batch_back has the other half to finish before red_retire.
         {
             const uint4 *src = (const uint4 *)(wbase + s * STAGE + lane * SPAN);
             scan_dev = 0;
 #pragma unroll
             for (uint32_t i = 0; i < CHUNKS; i++) {
+                if (MATCH && i == (CHUNKS + 1) / 2) {
+                    if (pb_pending) batch_back();
+                }
                 uint32_t m16 = ctl_mask16(src[i], scan_dev);
                 if (i & 1u) mk[i >> 1] |= m16 << 16; else mk[i >> 1] = m16;
             }
@@ -1047,7 +1025,6 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     }
     if (lane == 0) {
         if (MATCH) {
-            if (my_reads) atomicAdd(&a.totals[0], (unsigned long long)my_reads);
             if (my_bar) atomicAdd(&a.totals[1], (unsigned long long)(long long)my_bar);
             if (my_tag) atomicAdd(&a.totals[2], (unsigned long long)(long long)my_tag);
         }
@@ -1065,6 +1042,23 @@ __global__ void __launch_bounds__(256) fold_kernel(int32_t *matrix, int32_t *rep
         }
         if (sum) matrix[i] += sum;
     }
+}
+
+// Smallest cell of the count matrix (overflow guard: counts only grow, so a negative cell is a
+// cell that passed INT32_MAX; the reference counts with unbounded Python integers).
+__global__ void __launch_bounds__(256) min_kernel(const int32_t *matrix, uint32_t cells, int32_t *out)
+{
+    int32_t m = 0x7FFFFFFF;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) {
+        const int32_t v = matrix[i];
+        m = v < m ? v : m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int32_t v = __shfl_xor_sync(0xFFFFFFFFu, m, o);
+        m = v < m ? v : m;
+    }
+    if ((threadIdx.x & 31u) == 0) atomicMin(out, m);
 }
 
 // One CTA: prefix sum over the per-segment line counts, next chunk's state,

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "native", "feed_check.cpp")
 _LIB = os.path.join(_HERE, "native", "libfeed_check.so")
-_DEPS = [os.path.join(os.path.dirname(_HERE), "tagdigger_b200", "csrc", h) for h in ("tdg_feed.h", "tdg_pgz.h")]
+_DEPS = [os.path.join(os.path.dirname(_HERE), "tagdigger_b200", "csrc", h) for h in ("tdg_feed.h", "tdg_pgz.h", "tdg_text.h")]
 
 
 def build(force=False):
@@ -62,3 +62,17 @@ def bgzf_compress(data, block=65280, eof_marker=True, level=6):
     if eof_marker:
         out.append(bgzf_block(b""))
     return b"".join(out)
+
+
+def utf8_first_invalid(data, piece=1 << 16):
+    L = ctypes.CDLL(build())
+    L.fck_utf8.restype = ctypes.c_longlong
+    L.fck_utf8.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t]
+    return int(L.fck_utf8(data, len(data), piece))
+
+
+def line_limit(data, lines, piece=1 << 16):
+    L = ctypes.CDLL(build())
+    L.fck_line_limit.restype = ctypes.c_longlong
+    L.fck_line_limit.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint64]
+    return int(L.fck_line_limit(data, len(data), piece, lines))

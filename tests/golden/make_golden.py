@@ -729,10 +729,49 @@ def cases_script():
     return {"filesets": {"lanes": pack_files(files), "presplit": pack_files(pre)}, "cases": cases}
 
 
+
+def cases_find_tags_text():
+    """Text-mode behaviour of find_tags_fastq's file reading (tagdigger_fun.py:240-243, 272-273):
+    the file is decoded as UTF-8 (invalid bytes raise UnicodeDecodeError), and the loop stops at
+    maxreads, so defects located after that point are never met."""
+    cases = []
+
+    def add(fq, barcodes, tags, name="a.fq", **kw):
+        c = run_case("find_tags_fastq", {name: fq}, (name, barcodes, tags), kw)
+        c["stdout"] = ""
+        if len(fq) > 20000:               # the long filler compresses to nothing: keep the fixture small
+            c["files"][name] = {"gzb64": base64.b64encode(gzip.compress(fq, mtime=0)).decode()}
+        cases.append(c)
+
+    one = lambda s, h="@h": (h + "\n%s\n+\n%s\n" % (s, "I" * len(s))).encode("utf-8")
+    good = one("AACGTGCAGCCCC")
+    add(good * 3, ["AACG"], ["CCCC"])
+    add(one("AACGTGCAGCCCC", u"@h \u00e9\u20ac \U0001F9EC") * 3, ["AACG"], ["CCCC"])     # valid multi-byte text
+    add(b"@h\xff\n" + good[3:] + good, ["AACG"], ["CCCC"])                            # invalid start byte
+    add(good + b"@h\nAACG\xc3\x28TGCAGCCCC\n+\nIIII\n", ["AACG"], ["CCCC"])           # invalid continuation
+    add(good + b"@h\nAACGTGCAGCCCC\n+\nIII\xed\xa0\x80\n", ["AACG"], ["CCCC"])        # surrogate
+    add(good + b"@h\nAACGTGCAGCCCC\n+\nIII\xc0\xaf\n", ["AACG"], ["CCCC"])            # overlong form
+    add(good * 2 + b"@h \xe2\x82", ["AACG"], ["CCCC"])                               # sequence cut by the end of the file
+    add(good * 2 + b"@h \xf4\x90\x80\x80\n", ["AACG"], ["CCCC"])                      # above U+10FFFF
+    filler = good * 3000                                                              # ~96 KB: several text-layer chunks
+    add(good * 2 + filler + b"@h\xff\n" + good[3:], ["AACG"], ["CCCC"], maxreads=2)      # defect far behind the stop
+    add(good * 2 + filler + b"@h\xff\n" + good[3:], ["AACG"], ["CCCC"])                  # the same file read to the end
+    gz = gzip.compress(good * 2 + filler, mtime=0)
+    add(gz[:len(gz) // 2], ["AACG"], ["CCCC"], name="cut.fq.gz", maxreads=2)           # truncated far behind the stop
+    add(gz[:len(gz) // 2], ["AACG"], ["CCCC"], name="cut.fq.gz")
+    add(gzip.compress(good * 2 + filler + b"@h\xff\n" + good[3:], mtime=0), ["AACG"], ["CCCC"], name="bad.fq.gz", maxreads=2)
+    add(gzip.compress(good * 2 + b"@h\xff\n" + good[3:], mtime=0), ["AACG"], ["CCCC"], name="bad.fq.gz")
+    return cases
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "text":          # only the cases added in round 2
+        dump("find_tags_text.json", cases_find_tags_text())
+        sys.exit(0)
     dump("find_tags.json", cases_find_tags())
     dump("small_functions.json", cases_small())
     dump("readers.json", cases_readers())
     dump("trim.json", cases_trim())
     dump("splitter.json", cases_splitter())
     dump("script.json", cases_script())
+    dump("find_tags_text.json", cases_find_tags_text())

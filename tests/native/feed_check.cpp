@@ -8,6 +8,8 @@
 
 #include "../../tagdigger_b200/csrc/tdg_feed.h"
 
+#include "../../tagdigger_b200/csrc/tdg_text.h"
+
 static std::string g_err;
 
 extern "C" {
@@ -35,5 +37,34 @@ long long fck_read(const char *path, int gz, size_t chunk, uint8_t *out, size_t 
 }
 
 const char *fck_error(void) { return g_err.c_str(); }
+
+// tdg_text.h: UTF-8 validation of `data` fed in pieces of `piece` bytes.  Returns -1 (valid) or
+// the stream offset of the lead byte of the first invalid sequence.
+long long fck_utf8(const uint8_t *data, size_t n, size_t piece)
+{
+    tdg::Utf8State st;
+    for (size_t at = 0; at < n; at += piece) {
+        size_t m = n - at < piece ? n - at : piece;
+        if (!tdg::has_high_bit(data + at, m) && st.need == 0) { st.offset += m; continue; }   // as tdg_count_file does
+        long long bad = tdg::utf8_feed(st, data + at, m);
+        if (bad >= 0) return bad;
+    }
+    return tdg::utf8_finish(st);
+}
+
+// tdg_text.h: bytes of `data` (fed in pieces) up to and including line end number `lines`;
+// n + 1 when the data holds fewer line ends.
+long long fck_line_limit(const uint8_t *data, size_t n, size_t piece, uint64_t lines)
+{
+    tdg::LineLimit ll;
+    ll.remaining = lines;
+    size_t used = 0;
+    for (size_t at = 0; at < n; at += piece) {
+        size_t m = n - at < piece ? n - at : piece;
+        used += ll.feed(data + at, m);
+        if (ll.reached) return (long long)used;
+    }
+    return (long long)n + 1;
+}
 
 }  // extern "C"

@@ -19,7 +19,7 @@ from tagdigger_b200 import _native, counting, matchset, synth
 
 pytestmark = pytest.mark.gpu
 
-FIND = load_golden("find_tags.json")          # includes the tassel_tagcount=True cases
+FIND = load_golden("find_tags.json") + load_golden("find_tags_text.json")   # tassel_tagcount=True and text-mode cases included
 
 
 @pytest.fixture(scope="module")

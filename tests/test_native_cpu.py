@@ -25,7 +25,7 @@ def test_header_symbols_are_exported():
     L = _native.lib()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.tdg_abi_version() == 1
+    assert L.tdg_abi_version() == _native.ABI_VERSION == 2
 
 
 def test_no_cpu_fallback():

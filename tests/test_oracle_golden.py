@@ -13,7 +13,7 @@ import pytest
 from conftest import file_bytes, have_reference, import_reference, load_golden, materialize
 from oracle import tagdigger_oracle as orc
 
-FIND = load_golden("find_tags.json")
+FIND = load_golden("find_tags.json") + load_golden("find_tags_text.json")     # + text-mode cases (UTF-8, maxreads stop)
 
 
 def _call(fn, *a, **kw):
