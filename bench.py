@@ -188,6 +188,119 @@ def cpu_baseline_leg(args, bcs, tags):
             "host_cpus": os.cpu_count()}
 
 
+# ---- file -> matrix: the path tagdigger_script users run (tdg_count_file) ---------------------------
+
+def _deflate_piece(job):
+    """One piece of a pigz-style single-member gzip stream: raw deflate, ended by a sync flush (or
+    finished, for the last piece); returns (compressed bytes, crc32, length)."""
+    import zlib
+    path, a, b, last, level = job
+    with open(path, "rb") as fh:
+        fh.seek(a)
+        data = fh.read(b - a)
+    co = zlib.compressobj(level, zlib.DEFLATED, -15)
+    out = co.compress(data) + co.flush(zlib.Z_FINISH if last else zlib.Z_SYNC_FLUSH)
+    return out, zlib.crc32(data) & 0xFFFFFFFF, len(data)
+
+
+def _crc32_combine(crc1, crc2, len2):
+    """zlib's crc32_combine (not exposed by Python's zlib module)."""
+    def times(mat, vec):
+        s, i = 0, 0
+        while vec:
+            if vec & 1:
+                s ^= mat[i]
+            vec >>= 1
+            i += 1
+        return s
+
+    def square(mat):
+        return [times(mat, mat[n]) for n in range(32)]
+    if len2 == 0:
+        return crc1
+    odd = [0xEDB88320] + [1 << n for n in range(31)]
+    even = square(odd)
+    odd = square(even)
+    while True:
+        even = square(odd)
+        if len2 & 1:
+            crc1 = times(even, crc1)
+        len2 >>= 1
+        if not len2:
+            break
+        odd = square(even)
+        if len2 & 1:
+            crc1 = times(odd, crc1)
+        len2 >>= 1
+        if not len2:
+            break
+    return crc1 ^ crc2
+
+
+def write_gzip_parallel(src, dst, level=6, piece=32 << 20):
+    """`src` as ONE gzip member (what gzip/pigz write: a single deflate stream, no index), compressed
+    by all host cores in pieces joined with sync flushes."""
+    import multiprocessing as mp
+    import struct
+    size = os.path.getsize(src)
+    cuts = list(range(0, size, piece)) + [size]
+    jobs = [(src, a, b, b == size, level) for a, b in zip(cuts[:-1], cuts[1:])]
+    crc, total = 0, 0
+    with mp.get_context("fork").Pool(min(len(jobs), os.cpu_count() or 1)) as pool, open(dst, "wb") as out:
+        out.write(b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03")
+        for blob, c, n in pool.imap(_deflate_piece, jobs):
+            out.write(blob)
+            crc = _crc32_combine(crc, c, n) if total else c
+            total += n
+        out.write(struct.pack("<II", crc, total & 0xFFFFFFFF))
+
+
+def file_legs(args, eng, gen, bcs, tags, plan, local):
+    """File -> count matrix on the host through tdg_count_file (the call find_tags_fastq makes): a plain
+    FASTQ file and a single-member gzip file of the workload's shape, read from the page cache by the
+    library's host feed (parallel pread / speculative parallel inflate), H2D and counting overlapped."""
+    import shutil
+    import tempfile
+    from oracle import c_oracle
+    from tagdigger_b200 import _native
+    nreads = args.file_reads
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > (16 << 30) else None
+    tmpdir = tempfile.mkdtemp(prefix="tdg_bench_", dir=base)
+    out = {"reads": nreads, "io_threads": min(int(os.environ.get("TDG_IO_THREADS", "16")), os.cpu_count() or 1),
+           "where": "files written just before the run (page cache / %s)" % (base or "tmp")}
+    try:
+        dev, nbytes = gen.generate(local, 0, nreads)
+        img = np.empty(nbytes, dtype=np.uint8)
+        eng.memcpy_d2h(img.ctypes.data, dev, nbytes)
+        gen.free(local, dev)
+        plain = os.path.join(tmpdir, "c2.fq")
+        img.tofile(plain)
+        want, wtot = c_oracle.count_sharded(img, c_oracle.Counter(bcs, tags, CUTSITE))
+        del img
+        gz = os.path.join(tmpdir, "c2.fq.gz")
+        t0 = time.perf_counter()
+        write_gzip_parallel(plain, gz)
+        out["gzip_bytes"] = os.path.getsize(gz)
+        out["gzip_made_in_s"] = round(time.perf_counter() - t0, 1)
+        eng.set_matrix(plan.barnum, plan.ntags)
+        for name, path, isgz in (("plain", plain, False), ("gzip", gz, True)):
+            best = None
+            for rep in range(3):
+                eng.zero_matrix()
+                eng.reset_file()
+                t0 = time.perf_counter()
+                tot = eng.count_file(path, isgz)
+                got = eng.read_matrix()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            same = bool((got == want).all()) and tot[:3] == wtot
+            out[name] = {"reads_per_s": round(nreads / best, 1), "text_GBps": round(nbytes / best / 1e9, 2),
+                         "seconds": round(best, 3), "exact_vs_c_oracle": "ok" if same else "FAILED"}
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,6 +313,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=250_000, help="reads the 1-core reference counts for cpu_baseline")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-files", action="store_true")
+    ap.add_argument("--file-reads", type=int, default=8_000_000, help="reads in the files of the file -> matrix legs")
     ap.add_argument("--verify-reads", type=int, default=20_000_000,
                     help="reads of the job compared exactly with the C oracle (outside the timed region)")
     args = ap.parse_args()
@@ -232,6 +347,12 @@ def main():
     eng.set_tags(plan.tags.patterns, plan.tags.index, any_base=plan.tags.any_base)
     eng.bind_matrix(matrix.data_ptr(), plan.barnum, plan.ntags)
     eng.begin_file(plan.bar.patterns, plan.bar.index, plan.bar_tag_off, any_base=plan.bar.any_base)
+    if world > 1:
+        # the library's own communicator: the all-reduce runs on the counting stream (tdg_allreduce_matrix);
+        # torch.distributed only carries the 128-byte id to the ranks
+        ids = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng.comm_init(ids[0], world, rank)
 
     per = args.reads // world
     first = rank * per
@@ -247,9 +368,7 @@ def main():
         eng.zero_matrix()
         eng.count_device(dev, nbytes, 0, _native.TDG_PREV_NONE)
         if world > 1:
-            eng.other_stream_wait(tstream)          # NCCL stream order: after the last count kernel
-            dist.all_reduce(matrix)
-            eng.stream_wait(tstream)                # next step's memset after the all-reduce
+            eng.allreduce_matrix()                  # one ncclAllReduce in stream order behind the last count kernel
 
     # clocks are sampled over the warm-up and the timed steps (identical work; a timed region of
     # tens of milliseconds alone would give nvidia-smi time for one or two samples)
@@ -347,6 +466,16 @@ def main():
             check = "FAILED"
         eng.bind_matrix(matrix.data_ptr(), plan.barnum, plan.ntags)
 
+    # ---- file -> matrix through tdg_count_file (N = 1 only) ------------------------------------------
+    files = None
+    if rank == 0 and world == 1 and not args.no_files:
+        files = file_legs(args, eng, gen, bcs, tags, plan, local)
+        if any(isinstance(v, dict) and v.get("exact_vs_c_oracle") == "FAILED" for v in files.values()):
+            ok = False
+            check = "FAILED"
+        eng.bind_matrix(matrix.data_ptr(), plan.barnum, plan.ntags)
+        eng.begin_file(plan.bar.patterns, plan.bar.index, plan.bar_tag_off, any_base=plan.bar.any_base)
+
     # ---- CPU baseline (rank 0, N = 1 only): the unmodified reference on one core --------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -359,10 +488,10 @@ def main():
                "data": "synthetic",
                "config": {"workload": workload_name(args.reads), "reads_per_gpu": nreads,
                           "bytes_per_gpu": nbytes, "l2": "input per GPU far larger than the 126 MB L2; no flush needed",
-                          "sharding": "reads split %d ways, one NCCL all-reduce of the %dx%d int32 matrix per step"
+                          "sharding": "reads split %d ways, one ncclAllReduce of the %dx%d int32 matrix per step on the counting stream (tdg_allreduce_matrix)"
                                       % (world, plan.barnum, plan.ntags) if world > 1 else "single GPU"},
                "gpu_launches": launches, "check": check, "check_exact": exact, "clocks": clocks, "roofline": roofline,
-               "e2e": e2e, "cpu_baseline": cpu}
+               "e2e": e2e, "e2e_files": files, "cpu_baseline": cpu}
         print(json.dumps(out))
     gen.free(local, dev)
     if world > 1:
@@ -394,9 +523,7 @@ def e2e_leg(args, eng, gen, dev, nbytes, nreads, first, matrix, world, local, di
         eng.submit((host, size))
         eng.end_file()
         if world > 1:
-            eng.other_stream_wait(tstream)
-            dist.all_reduce(matrix)
-            eng.stream_wait(tstream)
+            eng.allreduce_matrix()
         eng.read_matrix(out)
 
     estep()                                    # warm-up (allocates the staging slots)

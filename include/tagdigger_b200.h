@@ -153,6 +153,22 @@ int         tdg_read_matrix(tdg_ctx *ctx, int32_t *out);
  * was zeroed (callers raise OverflowError; see tagdigger_b200/counting.py).  Synchronous. */
 int         tdg_matrix_min(tdg_ctx *ctx, int32_t *out);
 
+/* Multi-GPU: one context per GPU (one process or thread each).  The only exchange of the path
+ * is the sum of the per-GPU matrices -- the cross-file sum of combineReadCounts
+ * (tagdigger_fun.py:1088-1095) taken across GPUs -- done as ONE ncclAllReduce(int32, sum), in
+ * place, on the context's stream, i.e. in stream order behind the last count kernel and ahead
+ * of the next tdg_zero_matrix / tdg_read_matrix.  NCCL is bound at run time (libnccl.so.2).
+ *   tdg_comm_unique_id   rank 0 makes the 128-byte id and hands it to the other ranks
+ *                        (any channel: MPI, a file, torch.distributed ...)
+ *   tdg_comm_init        every rank joins (collective: blocks until all ranks have called)
+ *   tdg_allreduce_matrix asynchronous; a no-op on a context without communicator
+ *   tdg_finish           all-reduce, then the totals of this rank and the matrix on the host
+ *                        (the SURVEY's tdg_finish: sync, all-reduce, D2H) */
+int         tdg_comm_unique_id(void *out128);
+int         tdg_comm_init(tdg_ctx *ctx, const void *id128, int nranks, int rank);
+int         tdg_allreduce_matrix(tdg_ctx *ctx);
+int         tdg_finish(tdg_ctx *ctx, int32_t *out, uint64_t totals[4]);
+
 /* Device pointer of the matrix and the CUDA stream the kernels run on, so the
  * caller can all-reduce the matrix in place (NCCL) right behind the last kernel:
  * the multi-GPU replacement for the sum in combineReadCounts (:1081-1097). */

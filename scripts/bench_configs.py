@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
 """Kernel-only timing of the counting path on the OTHER BASELINE.json shapes (not bench
 lines: a check that no table shape or record length falls off a performance cliff).
-Every run is verified by construction (counts >= the generator's expected matrix,
-sum(counts) == tag hits, reads seen == reads generated).
+Every run is verified twice: by construction on the whole image (counts >= the generator's expected
+matrix, sum(counts) == tag hits, reads seen == reads generated) and EXACTLY against the C oracle on a
+slice of it (every cell and the three totals equal).
 
-    python scripts/bench_configs.py [reads]
+    python scripts/bench_configs.py [reads] [shape ...]
 """
 import json
 import os
@@ -16,26 +17,24 @@ sys.path.insert(0, REPO)
 
 import numpy as np  # noqa: E402
 
+PEAK = 6545.9
+try:
+    PEAK = float(json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except (OSError, ValueError, KeyError):
+    pass
 
-def run(name, nbar, npairs, readlen, reads, lengths=None, blank=False, cutsite="TGCAG", site=None, **mix):
+
+def run(name, reads, general=False, exact_reads=2_000_000):
     import torch
+    from oracle import c_oracle
     from tagdigger_b200 import _native, _synth_native, matchset, synth
-    rng = np.random.default_rng(7)
-    site = site or cutsite            # the concrete site written into tags and reads (IUPAC cut sites)
-    bcs = [""] if blank else synth.make_barcodes(nbar, rng, cutsite=site)
     t0 = time.time()
-    lens = None if lengths is None else rng.integers(lengths[0], lengths[1] + 1, size=npairs)
-    mnames, _, seqs = synth.make_marker_pairs(npairs, rng, cutsite=site, lengths=lens)
-    tags = [s for p in seqs for s in p]
-    if lengths is not None and lengths[0] != lengths[1]:
-        # random variable-length tags overlap now and then: drop those markers as the script would
-        import contextlib
-        import io
-        from tagdigger_b200 import hostio
-        names = ["%s_%d" % (m, k) for m in mnames for k in (0, 1)]
-        with contextlib.redirect_stdout(io.StringIO()):
-            tags = hostio.sanitizeTags([names, tags])[1]
+    bcs, tags, cutsite, site, readlen, mix = synth.shape_tables(name)
     plan = matchset.plan(bcs, tags, cutsite)
+    if general:
+        os.environ["TDG_GENERAL"] = "1"
+    else:
+        os.environ.pop("TDG_GENERAL", None)
     eng = _native.Engine(0)
     matrix = torch.zeros((plan.barnum, plan.ntags), dtype=torch.int32, device="cuda")
     eng.set_tags(plan.tags.patterns, plan.tags.index, any_base=plan.tags.any_base)
@@ -43,10 +42,22 @@ def run(name, nbar, npairs, readlen, reads, lengths=None, blank=False, cutsite="
     eng.begin_file(plan.bar.patterns, plan.bar.index, plan.bar_tag_off, any_base=plan.bar.any_base)
     setup = time.time() - t0
     gen = _synth_native.Generator(bcs, tags, site, readlen=readlen, seed=11, **mix)
+    # exact: a slice against the C oracle
+    dev, nbytes = gen.generate(0, 777, exact_reads)
+    img = np.empty(nbytes, dtype=np.uint8)
+    eng.memcpy_d2h(img.ctypes.data, dev, nbytes)
+    eng.count_device(dev, nbytes, 0, _native.TDG_PREV_NONE)
+    tot = eng.file_totals()
+    got = matrix.cpu().numpy().astype(np.int64)
+    gen.free(0, dev)
+    want, wtot = c_oracle.count_sharded(img, c_oracle.Counter(bcs, tags, cutsite))
+    exact = bool((got == want).all()) and tot[:3] == wtot
+    del img, got, want
+    # speed: the whole image
     expected = torch.zeros_like(matrix)
     dev, nbytes = gen.generate(0, 0, reads, expected.data_ptr())
     torch.cuda.synchronize()
-    for _ in range(2):
+    for _ in range(3):
         eng.zero_matrix()
         eng.count_device(dev, nbytes, 0, _native.TDG_PREV_NONE)
     eng.sync()
@@ -61,11 +72,17 @@ def run(name, nbar, npairs, readlen, reads, lengths=None, blank=False, cutsite="
     ok = bool((matrix >= expected).all().item()) and int(matrix.sum(dtype=torch.int64).item()) == tot[2] // steps \
         and tot[0] // steps == reads
     k = ms / n
-    out = {"config": name, "reads": reads, "barcodes": len(bcs), "tags": len(tags), "readlen": readlen,
+    p_bar, p_tag = tot[1] / tot[0], tot[2] / tot[0]
+    alg = nbytes / reads + 32.0 * p_bar + 8.0 * p_tag
+    out = {"config": name + (" (general matcher forced)" if general else ""), "reads": reads, "barcodes": len(bcs),
+           "tags": len(tags), "tag_len": [min(map(len, tags)), max(map(len, tags))], "readlen": readlen,
            "bytes_per_read": round(nbytes / reads, 1), "kernel_ms": round(k, 3),
            "reads_per_s": round(reads / (k * 1e-3), 1), "stream_GBps": round(nbytes / (k * 1e-3) / 1e9, 1),
-           "p_bar": round(tot[1] / tot[0], 3), "p_tag": round(tot[2] / tot[0], 3), "check": "ok" if ok else "FAILED",
-           "host_setup_s": round(setup, 1)}
+           "algorithmic_GBps": round(alg * reads / (k * 1e-3) / 1e9, 1),
+           "frac_of_hbm_peak": round(alg * reads / (k * 1e-3) / 1e9 / PEAK, 4),
+           "p_bar": round(p_bar, 3), "p_tag": round(p_tag, 3),
+           "check": "ok" if ok else "FAILED", "exact_vs_c_oracle": "ok (%d reads)" % exact_reads if exact else "FAILED",
+           "matrix_MB": round(plan.barnum * plan.ntags * 4 / 1e6, 1), "host_setup_s": round(setup, 1)}
     print(json.dumps(out), flush=True)
     gen.free(0, dev)
     eng.close()
@@ -75,13 +92,13 @@ def run(name, nbar, npairs, readlen, reads, lengths=None, blank=False, cutsite="
 
 def main():
     reads = int(sys.argv[1]) if len(sys.argv) > 1 else 50_000_000
-    run("C2 96-plex, 40k tags x 64 bp, 100 bp reads", 96, 20000, 100, reads)
-    run("C3 pre-split (blank barcode), 40k tags, 100 bp reads", 1, 20000, 100, reads, blank=True, p_nobar=0.05, p_unknown=0.30)
-    run("C4 384-plex, 500k tags of 20-64 bp, 100 bp reads", 384, 250000, 100, reads, lengths=(20, 64))
-    run("C4 384-plex, 500k tags of 20-64 bp, 150 bp reads", 384, 250000, 150, reads // 2, lengths=(20, 64))
-    run("C5-like 96-plex, 40k tags of 30-64 bp, 100 bp reads", 96, 20000, 100, reads, lengths=(30, 64))
-    run("ApeKI (CWGC, two cut sites) 96-plex, 40k tags, 100 bp reads", 96, 20000, 100, reads, cutsite="CWGC", site="CAGC")
-    run("short reads: 96-plex, 40k tags of 30 bp, 50 bp reads", 96, 20000, 50, reads, lengths=(30, 30))
+    from tagdigger_b200 import synth
+    names = sys.argv[2:] or list(synth.SHAPES)
+    for name in names:
+        general = name.endswith("+general")
+        base = name[:-len("+general")] if general else name
+        n = reads // 2 if synth.SHAPES[base]["readlen"] > 100 else reads
+        run(base, n // 4 if general else n, general=general)
 
 
 if __name__ == "__main__":

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TDG_LIB") or os.path.join(_HERE, "libtagdigger_b200.so")   # TDG_LIB: tuning builds (scripts/sweep.py)
-_SOURCES = ["tdg_api.cu", "tdg_text.h", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h", "tdg_trim.cuh", "tdg_split.cuh", "tdg_feed.h", "tdg_pgz.h", "tdg_csv.h"]
+_SOURCES = ["tdg_api.cu", "tdg_text.h", "tdg_comm.h", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h", "tdg_trim.cuh", "tdg_split.cuh", "tdg_feed.h", "tdg_pgz.h", "tdg_csv.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "20014,20011", "-shared"]
@@ -33,7 +33,7 @@ NO_LIMIT = (1 << 63)
 
 EXPORTS = """tdg_abi_version tdg_create tdg_destroy tdg_last_error tdg_set_tags tdg_set_matrix
 tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end_file tdg_count_device
-tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix tdg_matrix_min
+tdg_count_lines_device tdg_count_file tdg_sync tdg_file_totals tdg_read_matrix tdg_matrix_min tdg_comm_unique_id tdg_comm_init tdg_allreduce_matrix tdg_finish
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
 tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch tdg_split_begin tdg_split_block tdg_feed_open tdg_feed_read tdg_feed_close tdg_match_batch tdg_write_counts_csv tdg_write_geno_csv""".split()
@@ -114,6 +114,10 @@ def lib():
         "tdg_file_totals": (i32, [vp, vp]),
         "tdg_read_matrix": (i32, [vp, vp]),
         "tdg_matrix_min": (i32, [vp, vp]),
+        "tdg_comm_unique_id": (i32, [vp]),
+        "tdg_comm_init": (i32, [vp, vp, i32, i32]),
+        "tdg_allreduce_matrix": (i32, [vp]),
+        "tdg_finish": (i32, [vp, vp, vp]),
         "tdg_matrix_device_ptr": (vp, [vp]),
         "tdg_stream": (vp, [vp]),
         "tdg_stream_wait": (i32, [vp, vp]),
@@ -336,6 +340,23 @@ class Engine(object):
             if m.value < 0 or int(hits) >= (1 << 32):
                 raise OverflowError("a count passed 2**31 - 1: the device matrix holds int32 cells "
                                     "(the reference counts with unbounded integers); split the key")
+
+    # -- multi-GPU ---------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL id made by rank 0 (hand it to every rank, then comm_init everywhere)."""
+        buf = ctypes.create_string_buffer(128)
+        rc = lib().tdg_comm_unique_id(buf)
+        if rc != TDG_OK:
+            raise TdgError(rc, lib().tdg_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id, nranks, rank):
+        self._ck(self._L.tdg_comm_init(self._h, ctypes.c_char_p(unique_id), nranks, rank))
+
+    def allreduce_matrix(self):
+        """Sum the count matrices of all ranks in place (one ncclAllReduce on the engine's stream)."""
+        self._ck(self._L.tdg_allreduce_matrix(self._h))
 
     def read_matrix(self, out=None):
         if out is None:

@@ -17,6 +17,7 @@
 #include "../../include/tagdigger_b200.h"
 #include "tdg_kernel.cuh"
 #include "tdg_csv.h"
+#include "tdg_comm.h"
 #include "tdg_feed.h"
 #include "tdg_text.h"
 #include "tdg_tables.h"
@@ -50,6 +51,7 @@ struct tdg_ctx {
 
     cudaStream_t stream = nullptr;       // kernels
     cudaStream_t copy_stream = nullptr;  // H2D
+    cudaEvent_t handoff = nullptr;       // tdg_stream_wait / tdg_other_stream_wait
 
     // tables
     tdg::HostTagTable tags;
@@ -111,6 +113,10 @@ struct tdg_ctx {
     // pinned buffers of tdg_count_file (kept between files: pinning 192 MiB costs ~0.1 s)
     uint8_t *file_buf[3] = {nullptr, nullptr, nullptr};
     size_t file_buf_cap = 0;
+
+    // multi-GPU: the communicator of tdg_comm_init (one rank per context)
+    tdg::NcclApi::Comm comm = nullptr;
+    int comm_ranks = 1;
 
     // accounting
     uint64_t launches = 0;
@@ -190,14 +196,18 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
     }
     size_t max_grid = (size_t)per_sm * ctx->sm_count;
     size_t workers = max_grid * WARPS;      // every warp is an independent pipeline
-    // segments: runs of consecutive tiles handed to one warp; about 32 per warp so that the
-    // last, partly filled round of segments is a small part of the launch, at most 64 tiles
-    // (the fix pass redoes whole segments; each segment start costs one exact classification)
-    size_t seg_tiles = tiles / (workers * 32);
+    // Segments: runs of consecutive tiles handed to one warp through the ticket counter.  Long
+    // ones (about 16 per warp, at most 64 tiles: a segment start costs a ticket, a structure guess
+    // and -- when the guess is wrong -- a redo of the whole segment) for the first 7/8 of the
+    // launch, eight times shorter ones for the rest, so that the warps finish together.
+    size_t seg_tiles = tiles / (workers * 16);
     if (seg_tiles < 1) seg_tiles = 1;
     if (seg_tiles > 64) seg_tiles = 64;
-    if (ctx->force_seg_tiles) seg_tiles = ctx->force_seg_tiles;
-    size_t segs = (tiles + seg_tiles - 1) / seg_tiles;
+    size_t seg_small = seg_tiles / 8 ? seg_tiles / 8 : 1;
+    if (ctx->force_seg_tiles) seg_tiles = seg_small = ctx->force_seg_tiles;
+    size_t n_big = tiles / seg_tiles * 7 / 8;
+    size_t rest = tiles - n_big * seg_tiles;
+    size_t segs = n_big + (rest + seg_small - 1) / seg_small;
     size_t grid = (segs + WARPS - 1) / WARPS;
     if (grid > max_grid) grid = max_grid;
 
@@ -214,6 +224,8 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
     a.n = n;
     a.num_tiles = (uint32_t)tiles;
     a.seg_tiles = (uint32_t)seg_tiles;
+    a.n_big = (uint32_t)n_big;
+    a.seg_small = (uint32_t)seg_small;
     a.num_segs = (uint32_t)segs;
     a.mode = MODE_MAIN;
     VerifyArgs v;
@@ -549,6 +561,8 @@ void tdg_destroy(tdg_ctx *ctx)
             if (ctx->slot[i].done) cudaEventDestroy(ctx->slot[i].done);
         }
         for (cudaEvent_t ev : ctx->tev) cudaEventDestroy(ev);
+        if (ctx->handoff) cudaEventDestroy(ctx->handoff);
+        if (ctx->comm && tdg::nccl().CommDestroy) tdg::nccl().CommDestroy(ctx->comm);
         if (ctx->d_entries) cudaFree(ctx->d_entries);
         if (ctx->d_ext) cudaFree(ctx->d_ext);
         if (ctx->d_bar) cudaFree(ctx->d_bar);
@@ -819,11 +833,9 @@ int tdg_stream_wait(tdg_ctx *ctx, void *other_stream)
     int rc = need_device(ctx);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    cudaEvent_t ev;
-    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CK(cudaEventRecord(ev, (cudaStream_t)other_stream));
-    CK(cudaStreamWaitEvent(ctx->stream, ev, 0));
-    CK(cudaEventDestroy(ev));
+    if (!ctx->handoff) CK(cudaEventCreateWithFlags(&ctx->handoff, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->handoff, (cudaStream_t)other_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->handoff, 0));
     return TDG_OK;
 }
 
@@ -832,12 +844,68 @@ int tdg_other_stream_wait(tdg_ctx *ctx, void *other_stream)
     int rc = need_device(ctx);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
-    cudaEvent_t ev;
-    CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CK(cudaEventRecord(ev, ctx->stream));
-    CK(cudaStreamWaitEvent((cudaStream_t)other_stream, ev, 0));
-    CK(cudaEventDestroy(ev));
+    if (!ctx->handoff) CK(cudaEventCreateWithFlags(&ctx->handoff, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->handoff, ctx->stream));
+    CK(cudaStreamWaitEvent((cudaStream_t)other_stream, ctx->handoff, 0));
     return TDG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU: one process (or thread) per GPU, one context each; the only exchange of the path is
+// the sum of the count matrices.
+
+int tdg_comm_unique_id(void *out128)
+{
+    if (!out128) return fail(nullptr, TDG_ERR_ARG, "null argument");
+    tdg::NcclApi &N = tdg::nccl();
+    if (!N.load()) return fail(nullptr, TDG_ERR_STATE, N.why);
+    tdg::NcclApi::UniqueId id;
+    int rc = N.GetUniqueId(&id);
+    if (rc) return fail(nullptr, TDG_ERR_CUDA, "ncclGetUniqueId: " + N.message(rc));
+    memcpy(out128, &id, sizeof(id));
+    return TDG_OK;
+}
+
+int tdg_comm_init(tdg_ctx *ctx, const void *id128, int nranks, int rank)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, TDG_ERR_ARG, "bad communicator arguments");
+    tdg::NcclApi &N = tdg::nccl();
+    if (!N.load()) return fail(ctx, TDG_ERR_STATE, N.why);
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->comm) { N.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    tdg::NcclApi::UniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    int nrc = N.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (nrc) { ctx->comm = nullptr; return fail(ctx, TDG_ERR_CUDA, "ncclCommInitRank: " + N.message(nrc)); }
+    ctx->comm_ranks = nranks;
+    return TDG_OK;
+}
+
+int tdg_allreduce_matrix(tdg_ctx *ctx)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!ctx->d_matrix) return fail(ctx, TDG_ERR_STATE, "no matrix");
+    if (!ctx->comm) return ctx->comm_ranks == 1 ? TDG_OK : fail(ctx, TDG_ERR_STATE, "tdg_comm_init has not been called");
+    CK(cudaSetDevice(ctx->device));
+    tdg::NcclApi &N = tdg::nccl();
+    int nrc = N.AllReduce(ctx->d_matrix, ctx->d_matrix, (size_t)ctx->rows * ctx->cols, tdg::NcclApi::kInt32, tdg::NcclApi::kSum,
+                          ctx->comm, ctx->stream);
+    if (nrc) return fail(ctx, TDG_ERR_CUDA, "ncclAllReduce: " + N.message(nrc));
+    return TDG_OK;
+}
+
+int tdg_finish(tdg_ctx *ctx, int32_t *out, uint64_t totals[4])
+{
+    int rc = tdg_allreduce_matrix(ctx);
+    if (rc) return rc;
+    if (totals) {
+        rc = tdg_file_totals(ctx, totals);
+        if (rc) return rc;
+    }
+    return tdg_read_matrix(ctx, out);
 }
 
 void *tdg_host_alloc(tdg_ctx *ctx, size_t n)

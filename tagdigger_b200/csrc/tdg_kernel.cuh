@@ -114,7 +114,9 @@ struct ChunkArgs {
     const uint8_t *bytes;           // 16-byte aligned; allocation >= round_up(n, 16)
     unsigned long long n;
     uint32_t num_tiles;
-    uint32_t seg_tiles;             // tiles per segment
+    uint32_t seg_tiles;             // tiles per segment, segments [0, n_big)
+    uint32_t n_big;                 // the launch ends in SHORT segments (even finish): segments >= n_big have
+    uint32_t seg_small;             //   seg_small tiles each
     uint32_t num_segs;
     uint32_t mode;                  // MODE_*
     uint32_t use_arg_state;         // 1: (line_base, prev_kind) below; 0: *state_in
@@ -420,18 +422,24 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     // All of its state is warp-uniform and lives in registers; every lane runs the (uniform)
     // arithmetic, lane 0 alone draws the ticket and issues the copy.
     uint32_t p_item = NONE, p_seg = 0, p_tix = 0, p_ntiles = 0;
+    // The ticket of the NEXT segment is drawn one tile ahead (when the current segment's last tile
+    // is requested): the atomic's round trip to L2 is over by the time the ticket is needed.
+    uint32_t ticket = 0;
+    if (lane == 0) ticket = atomicAdd((unsigned int *)a.ticket, 1u);
     auto produce = [&](uint32_t st, uint32_t &m_tile, uint32_t &m_item, uint32_t &m_tixf) {
-        if (p_tix == p_ntiles) {                                   // draw the next segment
+        if (p_tix == p_ntiles) {                                   // the next segment
             const uint32_t n_items = a.mode == MODE_FIX ? 2u * *a.n_fix : a.num_segs;
-            uint32_t t = 0;
-            if (lane == 0) t = atomicAdd((unsigned int *)a.ticket, 1u);
-            t = __shfl_sync(FULL, t, 0);
+            const uint32_t t = __shfl_sync(FULL, ticket, 0);
             p_tix = 0;
             if (t < n_items) {
                 p_item = t;
-                p_seg = a.mode == MODE_FIX ? a.fix[t >> 1].seg : t;
-                const uint32_t left = a.num_tiles - p_seg * a.seg_tiles;
-                p_ntiles = left < a.seg_tiles ? left : a.seg_tiles;
+                const uint32_t seg = a.mode == MODE_FIX ? a.fix[t >> 1].seg : t;
+                // first tile and length of the segment: long segments first, short ones at the end
+                const bool big = seg < a.n_big;
+                const uint32_t want = big ? a.seg_tiles : a.seg_small;
+                p_seg = big ? seg * a.seg_tiles : a.n_big * a.seg_tiles + (seg - a.n_big) * a.seg_small;
+                const uint32_t left = a.num_tiles - p_seg;
+                p_ntiles = left < want ? left : want;
             } else {
                 p_item = NONE;
                 p_ntiles = NONE;                                   // never equal to p_tix again: no more tickets
@@ -442,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             // loads that batch_front has in flight.
             asm volatile("" ::"r"(p_item), "r"(p_seg), "r"(p_ntiles));
         }
-        m_tile = p_seg * a.seg_tiles + p_tix;
+        m_tile = p_seg + p_tix;                  // (p_seg: first tile of the segment)
         m_item = p_item;
         m_tixf = p_tix + 1 == p_ntiles ? (p_tix | TIX_LAST) : p_tix;
         if (p_item != NONE) {
@@ -457,6 +465,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 bulk_g2s(wbase + st * STAGE, a.bytes + off, bytes, &full_bar[warp][st]);
             }
             p_tix++;
+            if (p_tix == p_ntiles && lane == 0) ticket = atomicAdd((unsigned int *)a.ticket, 1u);
         }
     };
 
