@@ -394,3 +394,18 @@ def nccl_reduce(ptr, rows, cols, eng):
     eng.other_stream_wait(stream)
     dist.all_reduce(t)
     eng.stream_wait(stream)
+
+
+def init_comm(eng, rank, world):
+    """Give the engine its own NCCL communicator (``tdg_comm_init``): rank 0 makes the id, the
+    default torch.distributed group (any backend) carries the 128 bytes to the other ranks."""
+    import torch.distributed as dist
+    ids = [eng.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    eng.comm_init(ids[0], world, rank)
+
+
+def engine_reduce(ptr, rows, cols, eng):
+    """``reduce`` for :func:`count_files`: the library's own all-reduce on the counting stream
+    (``tdg_allreduce_matrix``; needs :func:`init_comm` first).  No torch tensor is involved."""
+    eng.allreduce_matrix()

@@ -127,11 +127,12 @@ def main(argv=None):
     if world > 1:
         import torch
         import torch.distributed as dist
-        from .counting import dist_gather, nccl_reduce
+        from .counting import dist_gather, engine_reduce, get_engine, init_comm
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl")
-        reduce = nccl_reduce
+        init_comm(get_engine(), rank, world)       # the library's own communicator (tdg_comm_init)
+        reduce = engine_reduce                      # one ncclAllReduce on the counting stream
         gather = dist_gather
     samples, counts = tdf.count_files(bckeys, tags[1], cutsite=cutsite, rank=rank, world=world, reduce=reduce,
                                       gather=gather, as_array=True)

@@ -730,6 +730,47 @@ def cases_script():
 
 
 
+def cases_flow():
+    """BASELINE config 5 as a flow, reduced: a two-enzyme (PstI-MspI) multiplexed library with adapter
+    read-through is split by barcode and trimmed (barcode_splitter_script.py:8-36), the per-sample
+    files are counted with a blank Barcode column and a marker-list filter (tagdigger_script.py -k).
+    Both stages are run with the reference's own scripts; inputs, the split files and the final CSV
+    are recorded."""
+    import numpy as np
+    from tagdigger_b200 import synth
+    rng = np.random.default_rng(20165)
+    bcs = synth.make_barcodes(8, rng)
+    lens = rng.integers(30, 65, size=60)
+    names, alleles, seqs = synth.make_marker_pairs(60, rng, lengths=lens)
+    tags = [s for pair in seqs for s in pair]
+    adapter = ref.adapters["PstI-MspI-Hall"]
+    tail = (adapter[0][0].replace("^", "") + adapter[0][1]).encode()      # MspI remnant + common adapter
+    fq, _ = synth.make_fastq(3000, bcs, tags, rng, adapter_tail=tail, p_nobarcode=0.10, p_unknown=0.25)
+    split_key = "Input File,Barcode,Output File\n" + "".join("lib.fq,%s,sample%02d.fq\n" % (b, i) for i, b in enumerate(bcs))
+    count_key = "File,Barcode,Sample\n" + "".join("sample%02d.fq,,S%02d\n" % (i, i % 6) for i in range(len(bcs)))
+    files = {"lib.fq": fq, "split_key.csv": split_key, "count_key.csv": count_key,
+             "tags.csv": synth.merged_csv(names, alleles, seqs), "keep.txt": "\n".join(names[::2]) + "\n"}
+    rec = {"files": pack_files(files), "split_argv": ["-b", "split_key.csv", "-a", "PstI-MspI-Hall"],
+           "count_argv": ["-e", "PstI", "--MergedTags", "tags.csv", "-k", "keep.txt", "-b", "count_key.csv", "-o", "counts.csv",
+                          "-g", "geno.csv"]}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, content in files.items():
+            with open(os.path.join(tmp, name), "wb" if isinstance(content, bytes) else "w") as fh:
+                fh.write(content)
+        p1 = subprocess.run([sys.executable, "-W", "ignore", os.path.join(REF, "barcode_splitter_script.py")] + rec["split_argv"],
+                            cwd=tmp, capture_output=True, text=True)
+        assert p1.returncode == 0, p1.stderr
+        p2 = subprocess.run([sys.executable, "-W", "ignore", os.path.join(REF, "tagdigger_script.py")] + rec["count_argv"],
+                            cwd=tmp, capture_output=True, text=True)
+        assert p2.returncode == 0, p2.stderr
+        import hashlib
+        rec["split_sha256"] = {"sample%02d.fq" % i: hashlib.sha256(open(os.path.join(tmp, "sample%02d.fq" % i), "rb").read()).hexdigest()
+                               for i in range(len(bcs))}                  # (the files themselves would triple the fixture)
+        rec["outfiles"] = {n: base64.b64encode(open(os.path.join(tmp, n), "rb").read()).decode()
+                           for n in ("counts.csv", "geno.csv")}
+    return {"cases": [rec]}
+
+
 def cases_find_tags_text():
     """Text-mode behaviour of find_tags_fastq's file reading (tagdigger_fun.py:240-243, 272-273):
     the file is decoded as UTF-8 (invalid bytes raise UnicodeDecodeError), and the loop stops at
@@ -767,6 +808,7 @@ def cases_find_tags_text():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "text":          # only the cases added in round 2
         dump("find_tags_text.json", cases_find_tags_text())
+        dump("flow.json", cases_flow())
         sys.exit(0)
     dump("find_tags.json", cases_find_tags())
     dump("small_functions.json", cases_small())
@@ -775,3 +817,4 @@ if __name__ == "__main__":
     dump("splitter.json", cases_splitter())
     dump("script.json", cases_script())
     dump("find_tags_text.json", cases_find_tags_text())
+    dump("flow.json", cases_flow())
