@@ -77,8 +77,8 @@ struct tdg_ctx {
     // per-launch scratch (ScratchHeader, SegInfo[], FixEntry[])
     unsigned long long *d_sync = nullptr;
     size_t sync_cap = 0;          // in 8-byte words
-    int occ_match = 0, occ_lines = 0;
-    size_t occ_match_smem = 0, occ_lines_smem = 0;
+    int occ[3] = {0, 0, 0};              // resident CTAs per SM of the three kernel instantiations, at
+    size_t occ_smem[3] = {0, 0, 0};      //   this much dynamic shared memory
     uint32_t force_seg_tiles = 0; // test hook (TDG_SEG_TILES)
     bool force_general = false;   // test hook (TDG_GENERAL=1): never use the fast matcher
     tdg::LineState *d_state = nullptr;   // [2]
@@ -163,10 +163,18 @@ int ensure_sync(tdg_ctx *ctx, size_t segs)
     return TDG_OK;
 }
 
-template <bool MATCH>
-int kernel_geometry(tdg_ctx *ctx, size_t smem, int *per_sm)
+typedef void (*CountKernel)(const tdg::ChunkArgs);
+
+// The three instantiations of the counting kernel: scan only, the matcher for tags that fit the
+// 128-bit key, and its long form (tags of up to 160 bases: key + 96 bases of tail).
+CountKernel pick_kernel(bool match, bool long_tags)
 {
-    auto kern = tdg::count_kernel<MATCH>;
+    if (!match) return tdg::count_kernel<false, false>;
+    return long_tags ? tdg::count_kernel<true, true> : tdg::count_kernel<true, false>;
+}
+
+int kernel_geometry(tdg_ctx *ctx, CountKernel kern, size_t smem, int *per_sm)
+{
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, tdg::THREADS, smem));
     if (*per_sm < 1) return fail(ctx, TDG_ERR_CUDA, "counting kernel does not fit on an SM");
@@ -187,10 +195,18 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
     if (MATCH && ctx->bar_blob.size() <= BAR_SMEM_MAX) bar_smem = round_up(ctx->bar_blob.size(), 16);
     if (SMEM_FIXED + bar_smem > ctx->smem_optin) bar_smem = 0;      // no room: the kernel reads the table from global memory
     size_t smem = SMEM_FIXED + bar_smem;
-    int &per_sm = MATCH ? ctx->occ_match : ctx->occ_lines;
-    size_t &occ_smem = MATCH ? ctx->occ_match_smem : ctx->occ_lines_smem;
+    uint32_t fast_words = 0;
+    bool long_tags = false;
+    if (MATCH) {
+        fast_words = ctx->force_general ? 0 : fast_words_for((const BarTable *)ctx->bar_blob.data(), ctx->tags.t);
+        long_tags = fast_words != 0 && fast_is_long(ctx->tags.t);
+    }
+    const CountKernel kern = pick_kernel(MATCH, long_tags);
+    const int ki = !MATCH ? 0 : (long_tags ? 2 : 1);
+    int &per_sm = ctx->occ[ki];
+    size_t &occ_smem = ctx->occ_smem[ki];
     if (per_sm == 0 || occ_smem != smem) {
-        int rc = kernel_geometry<MATCH>(ctx, smem, &per_sm);
+        int rc = kernel_geometry(ctx, kern, smem, &per_sm);
         if (rc) return rc;
         occ_smem = smem;
     }
@@ -249,7 +265,7 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
     a.halo_bytes = HALO;
     if (MATCH) {
         const BarTable *hbar = (const BarTable *)ctx->bar_blob.data();
-        a.fast_words = ctx->force_general ? 0 : fast_words_for(hbar, ctx->tags.t);
+        a.fast_words = fast_words;
         if (a.fast_words) {
             // the fast matcher reads whole 4-word groups from the aligned word of the line start
             uint32_t need = hbar->max_tag_off + ctx->tags.t.max_len + 36u;
@@ -291,7 +307,6 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
     v.fix = fix;
     v.n_fix = &hdr->n_fix;
 
-    auto kern = count_kernel<MATCH>;
     bool timed = ctx->timing && ctx->tev_used + 2 <= MAX_TIMED * 2;
     if (timed) CK(cudaEventRecord(ctx->tev[ctx->tev_used++], ctx->stream));
     kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(a);
@@ -521,7 +536,7 @@ int tdg_create(tdg_ctx **out, int device, size_t chunk_bytes)
         return fail(nullptr, TDG_ERR_CUDA, std::string("device ") + prop.name + " is not sm_100 class; this library is built for sm_100a only");
     // dynamic shared memory a block may ask for: the opt-in limit minus the kernel's static part
     cudaFuncAttributes fa;
-    CK(cudaFuncGetAttributes(&fa, tdg::count_kernel<true>));
+    CK(cudaFuncGetAttributes(&fa, tdg::count_kernel<true, false>));
     tdg_ctx *c = new (std::nothrow) tdg_ctx();
     if (!c) return fail(nullptr, TDG_ERR_NOMEM, "out of memory");
     c->device = device;

@@ -62,7 +62,7 @@ namespace tdg {
 #define TDG_CHUNKS 15
 #endif
 #ifndef TDG_HALO
-#define TDG_HALO 128
+#define TDG_HALO 256
 #endif
 
 constexpr int      WARPS = TDG_WARPS;              // independent pipelines per CTA (one CTA per SM)
@@ -82,9 +82,10 @@ constexpr uint32_t RING = STAGES * STAGE;          // bytes of shared memory per
 constexpr uint32_t QCAP = 64;                      // sequence-line starts a tile can queue on the common path
 constexpr uint32_t BAR_SMEM_MAX = 10240;           // barcode tables up to this size (384-plex: 7.2 KB) are copied to smem
 constexpr uint32_t GUESS_LINES = 16;               // lines inspected for the FASTQ structure guess
-constexpr uint32_t FAST_WORDS_MAX = 24;            // 4-character words the fast matcher packs per read
+constexpr uint32_t FAST_WORDS_MAX = 24;            // 4-character words the fast matcher packs per read (tags <= 64 bases)
+constexpr uint32_t LONG_WORDS_MAX = 48;            // ... in its long-tag form (tags <= 160 bases: key + 96 bases of tail)
+constexpr uint32_t LONG_TAIL_MAX = 96;             // bases past the 128-bit key that the long form compares
 constexpr uint32_t TIX_LAST = 0x80000000u;         // tile metadata: last tile of its segment
-static_assert(FAST_WORDS_MAX == 24, "the fast matcher's group flags are written out for six groups");
 static_assert(CHUNKS % 2 == 1, "an odd chunk count keeps the 128-bit scan loads free of bank conflicts");
 static_assert(TILE % 16 == 0 && STAGE % 16 == 0, "tiles must keep the 16-byte alignment TMA needs");
 static_assert(RING < 65536, "queue entries are 16-bit offsets into a warp's ring");
@@ -169,12 +170,14 @@ inline uint32_t fast_words_for(const BarTable *bar, const TagTable &tt)
 {
     if (bar->any_base || tt.any_base) return 0;
     if (bar->max_len > 16 || bar->max_tag_off > 28) return 0;
-    if (tt.n_classes != 1 || tt.max_len > 64 || tt.min_len < 1) return 0;
+    if (tt.n_classes != 1 || tt.max_len > 64 + LONG_TAIL_MAX || tt.min_len < 1) return 0;
     uint32_t chars = 3 + bar->max_tag_off + tt.max_len;       // 3: worst misalignment of the line start
     if (chars < 3 + 16) chars = 3 + 16;                       // the barcode key is always 16 bases
     uint32_t nw = (chars + 3) / 4;
-    return nw <= FAST_WORDS_MAX ? nw : 0;
+    return nw <= (tt.max_len > 64 ? LONG_WORDS_MAX : FAST_WORDS_MAX) ? nw : 0;
 }
+// Tags longer than the 128-bit key take the long form of the fast matcher (count_kernel<true, true>).
+inline bool fast_is_long(const TagTable &tt) { return tt.max_len > 64; }
 
 #if defined(__CUDACC__)
 
@@ -379,7 +382,7 @@ __device__ __forceinline__ uint32_t lowmask32(uint32_t nbases)    // first nbase
     return nbases >= 16 ? 0xFFFFFFFFu : ((1u << (2 * nbases)) - 1u);
 }
 
-template <bool MATCH>
+template <bool MATCH, bool LONG = false>
 __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant__ ChunkArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -511,6 +514,9 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
     uint32_t pb_T0 = 0, pb_T1 = 0, pb_T2 = 0, pb_T3 = 0, pb_h = 0, pb_V = 0xFFFFFFFFu, pb_end = 0;
     uint4 pb_k0 = make_uint4(0, 0, 0, 0), pb_k1 = pb_k0;
     uint2 pb_m0 = make_uint2(0, 0), pb_m1 = pb_m0;      // len | flags, column (the first half of an entry's second 16 bytes)
+    uint32_t pb_x0 = 0, pb_x1 = 0;                      // LONG: where the entries' bases 64.. sit in the side array
+    uint32_t pb_TL[LONG ? LONG_TAIL_MAX / 16 : 1];      // LONG: bases 64..159 of the read's tag window
+    constexpr uint32_t NG = (LONG ? LONG_WORDS_MAX : FAST_WORDS_MAX) / 4;     // groups of four packed words
 
     auto batch_front = [&](uint32_t qoff, uint32_t nb, uint32_t st) {
         uint32_t off = st * STAGE;
@@ -533,8 +539,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             // word that holds the line start, once, 2 bits per base
             const uint32_t sh = off & 3u;
             const uint32_t *wp = (const uint32_t *)(wbase + (off & ~3u));
-            uint32_t P[FAST_WORDS_MAX / 4];
-            uint32_t GB[FAST_WORDS_MAX / 4];  // non-zero: words 4g..4g+3 hold a character outside ACGTacgt
+            uint32_t P[NG + 1];
+            uint32_t GB[NG];                  // non-zero: words 4g..4g+3 hold a character outside ACGTacgt
             auto pack_group = [&](uint32_t g) {
                 uint32_t x[4], gbad = 0;
 #pragma unroll
@@ -550,7 +556,8 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             // groups 0..3 (64 characters) hold the barcode, the cut site and the first 32 bases
             // of the tag, which is all the hash needs: the probe loads go out before the rest
 #pragma unroll
-            for (uint32_t g = 0; g < FAST_WORDS_MAX / 4; g++) { P[g] = 0; GB[g] = 0; }
+            for (uint32_t g = 0; g < NG; g++) { P[g] = 0; GB[g] = 0; }
+            P[NG] = 0;
             // (always four groups: the halo covers them whatever the table shape)
             pack_group(0);
             pack_group(1);
@@ -603,23 +610,40 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 // staged through temporaries and copied, and the copy waits for the data at once
                 const uint4 *e0 = tag_entries + 2 * (size_t)(a.tags.cls[0].base + (want ? pb_h : 0u));
                 pb_k0 = __ldg(e0);
-                pb_m0 = __ldg((const uint2 *)(e0 + 1));
+                if (LONG) {
+                    const uint4 f0 = __ldg(e0 + 1), f1 = __ldg(e0 + 3);     // len, column, tail index
+                    pb_m0 = make_uint2(f0.x, f0.y);
+                    pb_m1 = make_uint2(f1.x, f1.y);
+                    pb_x0 = f0.z;
+                    pb_x1 = f1.z;
+                } else {
+                    pb_m0 = __ldg((const uint2 *)(e0 + 1));
+                    pb_m1 = __ldg((const uint2 *)(e0 + 3));
+                }
                 pb_k1 = __ldg(e0 + 2);
-                pb_m1 = __ldg((const uint2 *)(e0 + 3));
             }
-            // ---- the rest of the tag (bases 32..63) while the loads are in flight
-            if (nw > 16) {
-                pack_group(4);
-                if (nw > 20) pack_group(5);
-            }
+            // ---- the rest of the tag (bases 32..) while the loads are in flight
+#pragma unroll
+            for (uint32_t g = 4; g < NG; g++)
+                if (nw > 4 * g) pack_group(g);
             {
                 const uint32_t Q2 = up ? P[3] : P[2], Q3 = up ? P[4] : P[3], Q4 = up ? P[5] : P[4];
                 pb_T2 = __funnelshift_r(Q2, Q3, bit);
                 pb_T3 = __funnelshift_r(Q3, Q4, bit);
             }
+            if (LONG) {
+#pragma unroll
+                for (uint32_t j = 0; j < LONG_TAIL_MAX / 16; j++) {
+                    const uint32_t Qa = up ? P[5 + j] : P[4 + j], Qb = up ? P[6 + j] : P[5 + j];
+                    pb_TL[j] = __funnelshift_r(Qa, Qb, bit);
+                }
+            }
             // some character is not a base: matches stand only if they end before it
             uint32_t V = 0xFFFFFFFFu;                  // valid bases from the line start
-            if (((GB[0] | GB[1] | GB[2]) | (GB[3] | GB[4] | GB[5])) != 0) {
+            uint32_t anybad = 0;
+#pragma unroll
+            for (uint32_t g = 0; g < NG; g++) anybad |= GB[g];
+            if (anybad != 0) {
                 // The first flagged group of four words brackets the first such character:
                 // [Vmin, Vmax].  Mostly that decides already -- everything a match needs lies
                 // before the group, or some of it surely lies behind -- and V = Vmin gives the
@@ -627,7 +651,7 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                 // exact position.
                 uint32_t i0 = 0;
 #pragma unroll
-                for (int g = FAST_WORDS_MAX / 4 - 1; g >= 0; g--)
+                for (int g = (int)NG - 1; g >= 0; g--)
                     if (GB[g] != 0) i0 = 4u * g;
                 const uint32_t Vmin = i0 ? 4u * i0 - sh : 0u, Vmax = 4u * i0 + 15u - sh;
                 const uint32_t end_max = tag_off + a.tags.max_len, end_min = tag_off + a.tags.min_len;
@@ -685,10 +709,49 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
             // probing lanes use the result)
             const bool e0 = pb_m0.x == TDG_EMPTY_LEN, e1 = pb_m1.x == TDG_EMPTY_LEN;
             const uint32_t L0 = pb_m0.x & TDG_LEN_MASK;
-            const bool hit0 = !e0 & (tag_differs(pb_k0, L0, pb_T0, pb_T1, pb_T2, pb_T3) == 0);
-            const bool hit1 = !e0 & !e1 & !hit0 & (tag_differs(pb_k1, pb_m1.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0);
+            bool hit0 = !e0 & (tag_differs(pb_k0, L0, pb_T0, pb_T1, pb_T2, pb_T3) == 0);
+            bool hit1 = !e0 & !e1 & (LONG | !hit0) & (tag_differs(pb_k1, pb_m1.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0);
+            if (LONG) {
+                // Tags longer than the key: bases 64.. of both candidates come from the side array (one
+                // more round trip to L2, for both slots at once -- two alleles that differ past base 64
+                // share a key) and are compared with the read's packed tail.
+                const uint64_t *x0 = a.tags.ext + ((hit0 & pb_probe & (L0 > 64u)) ? pb_x0 : 0u);
+                const uint64_t *x1 = a.tags.ext + ((hit1 & pb_probe & (pb_m1.x > 64u)) ? pb_x1 : 0u);
+                uint2 t0[LONG_TAIL_MAX / 32], t1[LONG_TAIL_MAX / 32];
+#pragma unroll
+                for (uint32_t j = 0; j < LONG_TAIL_MAX / 32; j++) {
+                    t0[j] = __ldg((const uint2 *)(x0 + j));
+                    t1[j] = __ldg((const uint2 *)(x1 + j));
+                }
+                auto tail_differs = [&](const uint2 (&t)[LONG_TAIL_MAX / 32], uint32_t L) -> uint32_t {
+                    const uint32_t rest = L > 64u ? L - 64u : 0u;
+                    uint32_t d = 0;
+#pragma unroll
+                    for (uint32_t j = 0; j < LONG_TAIL_MAX / 32; j++) {
+                        d |= (t[j].x ^ pb_TL[2 * j]) & lowmask32(rest > 32u * j ? rest - 32u * j : 0u);
+                        d |= (t[j].y ^ pb_TL[2 * j + 1]) & lowmask32(rest > 32u * j + 16u ? rest - 32u * j - 16u : 0u);
+                    }
+                    return d;
+                };
+                hit0 = hit0 & (tail_differs(t0, L0) == 0);
+                hit1 = hit1 & !hit0 & (tail_differs(t1, pb_m1.x) == 0);
+            }
             int32_t col = hit0 ? (int32_t)pb_m0.y : (hit1 ? (int32_t)pb_m1.y : -1);
             uint32_t tlen = hit0 ? L0 : pb_m1.x;
+            // (LONG, rare path below) bases 64.. of the entry whose second half is at `half`
+            auto long_tail_ok = [&](const uint4 *half, uint32_t L) -> bool {
+                if (L <= 64u) return true;
+                const uint64_t *x = a.tags.ext + __ldg(half).z;
+                const uint32_t rest = L - 64u;
+                uint32_t d = 0;
+#pragma unroll
+                for (uint32_t j = 0; j < LONG_TAIL_MAX / 32; j++) {
+                    const uint2 t = __ldg((const uint2 *)(x + j));
+                    d |= (t.x ^ pb_TL[LONG ? 2 * j : 0]) & lowmask32(rest > 32u * j ? rest - 32u * j : 0u);
+                    d |= (t.y ^ pb_TL[LONG ? 2 * j + 1 : 0]) & lowmask32(rest > 32u * j + 16u ? rest - 32u * j - 16u : 0u);
+                }
+                return d == 0;
+            };
             // rare: both slots taken by other keys and something was stored beyond this pair
             if (pb_probe & !e0 & !e1 & !hit0 & !hit1 & ((pb_m0.x & TDG_LEN_MORE) != 0)) {
                 uint32_t h = pb_h;
@@ -699,9 +762,13 @@ __global__ void __launch_bounds__(THREADS, 1) count_kernel(const __grid_constant
                     const uint2 m0 = __ldg((const uint2 *)(e + 1)), m1 = __ldg((const uint2 *)(e + 3));
                     if (m0.x == TDG_EMPTY_LEN) break;
                     const uint32_t l0 = m0.x & TDG_LEN_MASK;
-                    if (tag_differs(k0, l0, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { col = (int32_t)m0.y; tlen = l0; break; }
+                    if (tag_differs(k0, l0, pb_T0, pb_T1, pb_T2, pb_T3) == 0 && (!LONG || long_tail_ok(e + 1, l0))) {
+                        col = (int32_t)m0.y; tlen = l0; break;
+                    }
                     if (m1.x == TDG_EMPTY_LEN) break;
-                    if (tag_differs(k1, m1.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0) { col = (int32_t)m1.y; tlen = m1.x; break; }
+                    if (tag_differs(k1, m1.x, pb_T0, pb_T1, pb_T2, pb_T3) == 0 && (!LONG || long_tail_ok(e + 3, m1.x))) {
+                        col = (int32_t)m1.y; tlen = m1.x; break;
+                    }
                     if (!(m0.x & TDG_LEN_MORE)) break;
                 }
             }

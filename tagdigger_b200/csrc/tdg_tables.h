@@ -152,7 +152,9 @@ inline std::string build_tag_table(const char *bases, const uint64_t *off, const
         }
         base += slots;
     }
-    if (out.ext.empty()) out.ext.push_back(0);
+    // the long form of the fast matcher reads three words per candidate without looking at its length,
+    // and index 0 for lanes that have no candidate
+    for (int k = 0; k < 3; k++) out.ext.push_back(0);
     return "";
 }
 

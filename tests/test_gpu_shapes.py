@@ -84,3 +84,48 @@ def test_config2_ten_million_reads_exact():
         assert (got == want).all()
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("maxlen", [65, 96, 97, 128, 129, 160, 161])
+def test_long_tags_share_their_key(maxlen):
+    """Tags longer than the 128-bit key (Stacks catalogs): alleles that differ only PAST base 64 share
+    a key and are told apart by the tail compare of the matcher's long form; lengths on both sides of
+    every word boundary of the tail, and one base beyond what the long form takes (161: the general
+    matcher).  Reads: exact copies, copies with the last base changed, copies cut one base short,
+    copies with an N inside the tail."""
+    import random
+    r = random.Random(maxlen)
+    cutsite = "TGCAG"
+    bcs = ["ACGT", "TTGCA", "GGATCC", "CATGA"]
+    tags, reads = [], []
+    for k in range(300):
+        L = r.choice([maxlen, maxlen, max(66, maxlen - r.randint(0, 40))])
+        body = "".join(r.choice("ACGT") for _ in range(L - len(cutsite)))
+        t0 = cutsite + body
+        pos = r.randint(64, L - 1)                       # SNP past the key
+        t1 = t0[:pos] + r.choice([c for c in "ACGT" if c != t0[pos]]) + t0[pos + 1:]
+        tags += [t0, t1]
+    # drop tags that are prefixes of others (the reference's trie would refuse them)
+    keep = [t for t in tags if not any(u != t and u.startswith(t) for u in tags)]
+    tags = keep
+    for _ in range(20000):
+        t = r.choice(tags)
+        b = r.choice(bcs)
+        kind = r.random()
+        s = t
+        if kind < 0.15:
+            s = t[:-1] + r.choice([c for c in "ACGT" if c != t[-1]])
+        elif kind < 0.25:
+            s = t[:-1]
+        elif kind < 0.35:
+            p = r.randint(64, len(t) - 1)
+            s = t[:p] + "N" + t[p + 1:]
+        tail = "".join(r.choice("ACGT") for _ in range(r.randint(0, 12))) if kind >= 0.25 or kind < 0.15 else ""
+        reads.append(b + s + tail)
+    fq = "".join("@r%d\n%s\n+\n%s\n" % (i, s, "I" * len(s)) for i, s in enumerate(reads)).encode()
+    want, wtot = c_oracle.Counter(bcs, tags, cutsite).count(fq)
+    assert wtot[2] > 5000
+    tot = []
+    got = np.asarray(counting.find_tags_bytes(fq, bcs, tags, cutsite, totals=tot))
+    assert tot[:3] == wtot
+    assert (got == want).all()
