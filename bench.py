@@ -301,6 +301,33 @@ def file_legs(args, eng, gen, bcs, tags, plan, local):
     return out
 
 
+def bind_to_gpu_numa(local):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off (sysfs), so that the pinned
+    buffers of the end-to-end leg are allocated in memory local to the GPU's PCIe root: with 4-8
+    ranks on a two-socket box, buffers on the wrong socket make the H2D copies cross the socket
+    link.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return {"gpu_pci": bus, "numa_node": node, "bound": False}
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"gpu_pci": bus, "numa_node": node, "bound": False}
+        os.sched_setaffinity(0, allowed)
+        return {"gpu_pci": bus, "numa_node": node, "bound": True, "cpus": len(allowed)}
+    except (OSError, ValueError, AttributeError, RuntimeError) as e:
+        return {"bound": False, "why": str(e)[:80]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -336,6 +363,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU counting path)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -491,7 +519,7 @@ def main():
                           "sharding": "reads split %d ways, one ncclAllReduce of the %dx%d int32 matrix per step on the counting stream (tdg_allreduce_matrix)"
                                       % (world, plan.barnum, plan.ntags) if world > 1 else "single GPU"},
                "gpu_launches": launches, "check": check, "check_exact": exact, "clocks": clocks, "roofline": roofline,
-               "e2e": e2e, "e2e_files": files, "cpu_baseline": cpu}
+               "e2e": e2e, "e2e_files": files, "cpu_baseline": cpu, "numa": numa}
         print(json.dumps(out))
     gen.free(local, dev)
     if world > 1:
@@ -546,6 +574,7 @@ def e2e_leg(args, eng, gen, dev, nbytes, nreads, first, matrix, world, local, di
     eng.host_free(host)
     return {"value": round(total_reads * steps / dt, 1), "unit": "reads/s",
             "h2d_bytes_per_step": total_h2d, "d2h_bytes_per_step": total_d2h,
+            "h2d_GBps_per_gpu": round(total_h2d * steps / dt / world / 1e9, 1),
             "steps": steps, "reads_per_step": total_reads, "ms_per_step": round(dt / steps * 1e3, 3),
             "timing": "host wall clock between device synchronisations, max over ranks",
             "path": "tdg_submit from pinned host memory in 64 MiB pieces (H2D overlapped with kernels) + tdg_read_matrix"}
