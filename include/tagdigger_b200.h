@@ -56,7 +56,14 @@ extern "C" {
 
 #define TDG_LINE_CHAINED  UINT64_MAX  /* take line_base/prev_kind from the previous chunk on this context */
 
-/* geometry the device-resident entry point needs from its caller */
+/* ALLOCATION SLACK the device-resident entry points need from their caller -- not the kernel's
+ * geometry.  A device image of n bytes passed to tdg_count_device / tdg_count_lines_device must
+ * be 16-byte aligned and sit in an allocation of at least
+ *     round_up(n, TDG_TILE_BYTES) + TDG_HALO_BYTES
+ * bytes (the bulk copies of the last tile read up to the next 16-byte boundary past n; the
+ * rest is never touched).  The kernel's own tile and halo (csrc/tdg_kernel.cuh: 7,680 and up
+ * to 256 bytes today) are smaller and may change from release to release without touching this
+ * contract; the library checks at compile time that they stay below these two numbers. */
 #define TDG_TILE_BYTES    16384u
 #define TDG_HALO_BYTES    512u
 

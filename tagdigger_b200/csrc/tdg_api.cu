@@ -25,6 +25,7 @@
 #include "tdg_split.cuh"
 
 static_assert(TDG_HALO_BYTES >= tdg::HALO, "the allocation slack promised by the header must cover the kernel halo");
+static_assert(TDG_TILE_BYTES >= tdg::TILE, "the allocation granule promised by the header must cover a kernel tile");
 
 namespace {
 
@@ -147,8 +148,10 @@ struct ScratchHeader {
     unsigned long long ticket_main, ticket_fix;
     uint32_t n_fix, last_kind;
     unsigned long long pad;
+    unsigned long long run_total[32 * 32];      // verify_sums -> verify_kernel (VERIFY_MAX_CTAS runs of 32 warps)
 };
-static_assert(sizeof(ScratchHeader) == 32, "scratch header layout");
+static_assert(offsetof(ScratchHeader, run_total) == 32, "scratch header layout");
+static_assert(sizeof(ScratchHeader::run_total) / 8 == tdg::VERIFY_MAX_CTAS * (tdg::VERIFY_THREADS / 32), "one total per run");
 
 int ensure_sync(tdg_ctx *ctx, size_t segs)
 {
@@ -232,7 +235,7 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
     ScratchHeader *hdr = (ScratchHeader *)ctx->d_sync;
     SegInfo *seginfo = (SegInfo *)(hdr + 1);
     FixEntry *fix = (FixEntry *)(seginfo + segs);
-    CK(cudaMemsetAsync(hdr, 0, sizeof(ScratchHeader), ctx->stream));
+    CK(cudaMemsetAsync(hdr, 0, offsetof(ScratchHeader, run_total), ctx->stream));
 
     ChunkArgs a;
     memset(&a, 0, sizeof(a));
@@ -306,14 +309,19 @@ int launch_chunk(tdg_ctx *ctx, const void *dev_bytes, size_t n, uint64_t line_ba
     v.last_kind = &hdr->last_kind;
     v.fix = fix;
     v.n_fix = &hdr->n_fix;
+    v.run_total = hdr->run_total;
 
     bool timed = ctx->timing && ctx->tev_used + 2 <= MAX_TIMED * 2;
     if (timed) CK(cudaEventRecord(ctx->tev[ctx->tev_used++], ctx->stream));
     kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
-    verify_kernel<<<1, VERIFY_THREADS, 0, ctx->stream>>>(v);
+    // every warp of the verify launches takes >= 256 segments
+    const unsigned vgrid = (unsigned)std::min<size_t>(VERIFY_MAX_CTAS, std::max<size_t>(1, segs / (32 * 256)));
+    verify_sums<<<vgrid, VERIFY_THREADS, 0, ctx->stream>>>(v);
     CK(cudaGetLastError());
-    ctx->launches += 2;
+    verify_kernel<<<vgrid, VERIFY_THREADS, 0, ctx->stream>>>(v);
+    CK(cudaGetLastError());
+    ctx->launches += 3;
     if (MATCH) {
         // redo mis-numbered segments (none for well-formed FASTQ: the CTAs exit at once)
         a.mode = MODE_FIX;

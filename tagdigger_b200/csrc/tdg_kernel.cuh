@@ -10,27 +10,38 @@
 //           mycounts[bar][tag] += 1         -> warp-aggregated red.global.add.s32
 //
 // Execution model: every WARP is an independent pipeline.  A warp draws SEGMENTS
-// (runs of consecutive tiles) from a global ticket counter and streams their tiles
-// through its own ring of three shared-memory stages filled by the TMA unit
-// (cp.async.bulk + mbarrier complete_tx).  There is no CTA-wide barrier after the
-// prologue, and every byte of the stream is read from HBM exactly once.
+// (runs of consecutive tiles; long ones first, short ones at the end of a launch) from
+// a global ticket counter -- the next ticket one tile ahead of its use -- and streams
+// their tiles through its own ring of TWO shared-memory stages filled by the TMA unit
+// (cp.async.bulk + mbarrier complete_tx, L2 evict-first).  There is no CTA-wide barrier
+// after the prologue, and every byte of the stream is read from HBM exactly once.
 //
-// Per tile (4,608 bytes + 128 of halo) a warp
-//   1. scans: each lane looks at its 144 contiguous bytes, 9 x 128-bit shared loads
-//      (144 = 9 x 16: consecutive lanes start in consecutive 16-byte bank groups, so
-//      the loads are conflict free); per 4 bytes an add, a PRMT with sign replication
-//      and a byte dot product leave the mask of the line-end CANDIDATES, and 1.5 LOP3
-//      check that every candidate is a line feed (otherwise the exact classifier runs);
+// A tile is sized to be ONE BATCH: 7,680 bytes (+ up to 256 of halo) hold about 30
+// reads of 250 bytes, one per lane of the matcher.  Per tile a warp
+//   1. scans: each lane looks at its 240 contiguous bytes, 15 x 128-bit shared loads
+//      (an odd number of 16-byte units per lane: consecutive lanes start in different
+//      bank groups, so the loads are conflict free); per 4 bytes an add, a PRMT with
+//      sign replication and a byte dot product leave the mask of the line-end
+//      CANDIDATES, and 1.5 LOP3 check that every candidate is a line feed (otherwise
+//      every candidate is classified exactly: '\n', '\r\n', lone '\r').  The masks stay
+//      in registers;
 //   2. ranks the line ends with three ballots, which gives every line start its index
-//      in the file, and pushes the starts of SEQUENCE lines (at most one per lane in
-//      ordinary FASTQ, selected without a loop) onto a small per-warp queue;
-//   3. whenever 32 starts are queued, matches them one per lane in two halves: pack 2
-//      bits per base, barcode bucket lookup in shared memory, 128-bit key, the loads of
-//      one hash probe of the L2-resident tag table (batch_front); compare and warp-
-//      aggregated count update once the next tile's bytes have arrived (batch_back).
-// The queue decouples "lines per tile" from "lanes per warp": matching runs with full
-// warps whatever the record length.  Warp-uniform state lives in the warp's control
-// block in shared memory (WarpShared), not in registers: 124 registers, 15 warps per SM.
+//      in the file; a lane's span is handled as two halves of <= 128 bytes, each of
+//      which holds at most one start of a SEQUENCE line in ordinary FASTQ -- selected
+//      without a loop and written to the tile's queue slot given by its rank;
+//   3. matches the tile's starts, one per lane (batch_front): pack 2 bits per base
+//      straight from the staged bytes, barcode bucket lookup in shared memory, 128-bit
+//      key, the loads of one hash probe of the L2-resident tag table.  The stage is
+//      then refilled; the compare and the warp vote (batch_back) run in the middle of
+//      the NEXT tile's scan, the warp-aggregated red.global.add.s32 at its end, so that
+//      the probe's round trip and the vote hide behind the scan.
+// Tiles that are not ordinary (chunk edges, lines shorter than half a span, the read
+// limit of the fix pass) take a general walk over the same masks; reads with leading
+// whitespace or non-ASCII text and table shapes outside the packed matcher's envelope
+// take match_general.  Tags longer than the 128-bit key (up to 160 bases) use the long
+// form, count_kernel<true, true>: the key is probed as usual and bases 64.. are
+// compared against the table's side array.  Warp-uniform producer and segment state
+// lives in registers: 128 registers, 14 warps per SM (two stages of 7.9 KB each).
 //
 // Line numbering.  Which lines are sequence lines is decided by the GLOBAL line
 // index (lineindex % 4 == 1 counted from the start of the file), which a warp that
@@ -161,6 +172,7 @@ struct VerifyArgs {
     const uint32_t *last_kind;
     FixEntry *fix;
     uint32_t *n_fix;
+    unsigned long long *run_total;  // [VERIFY_MAX_CTAS * 32] lines per run of segments (verify_sums -> verify_kernel)
 };
 
 // Can the fast matcher serve these tables?  Returns the number of 4-character
@@ -1137,22 +1149,28 @@ __global__ void __launch_bounds__(256) min_kernel(const int32_t *matrix, uint32_
     if ((threadIdx.x & 31u) == 0) atomicMin(out, m);
 }
 
-// One CTA: prefix sum over the per-segment line counts, next chunk's state,
-// and the list of segments the fix pass must redo.
-// Every warp takes a contiguous run of segments and walks it 32 entries at a time (coalesced
-// loads): first the run's total, then -- once the totals of the warps before it are known -- the
-// true first line index of every segment, by a warp scan per round.
+// Prefix sum over the per-segment line counts, next chunk's state, and the list of segments the
+// fix pass must redo.  Two launches of a few CTAs: every warp takes a contiguous run of segments
+// and walks it 32 entries at a time (coalesced loads).  verify_sums leaves the runs' totals in
+// `run_total`; verify_kernel adds up the totals of the runs before its own and gives every segment
+// its true first line index by a warp scan per round.  (One CTA doing both took 70 us for the
+// 170 k segments of a 200 M-read launch -- 5 % of an eighth of that launch.)
 constexpr int VERIFY_THREADS = 1024;
-__global__ void __launch_bounds__(VERIFY_THREADS) verify_kernel(const VerifyArgs v)
+constexpr uint32_t VERIFY_MAX_CTAS = 32;
+__device__ __forceinline__ void verify_run(const VerifyArgs &v, uint32_t &lo, uint32_t &hi)
 {
-    constexpr uint32_t NW = VERIFY_THREADS / 32;
-    __shared__ unsigned long long s_total[NW];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const unsigned long long line_base = v.use_arg_state ? v.line_base : v.state_in->next_line;
-    const uint32_t per = ((v.num_segs + NW - 1) / NW + 31u) & ~31u;          // segments per warp: whole rounds
-    const uint32_t lo = warp * per < v.num_segs ? warp * per : v.num_segs;
-    const uint32_t hi = lo + per < v.num_segs ? lo + per : v.num_segs;
+    const uint32_t nruns = gridDim.x * (VERIFY_THREADS / 32);
+    const uint32_t run = blockIdx.x * (VERIFY_THREADS / 32) + (threadIdx.x >> 5);
+    const uint32_t per = ((v.num_segs + nruns - 1) / nruns + 31u) & ~31u;    // segments per run: whole rounds
+    lo = (unsigned long long)run * per < v.num_segs ? run * per : v.num_segs;
+    hi = (unsigned long long)lo + per < v.num_segs ? lo + per : v.num_segs;
+}
 
+__global__ void __launch_bounds__(VERIFY_THREADS) verify_sums(const VerifyArgs v)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t lo, hi;
+    verify_run(v, lo, hi);
     unsigned long long sum = 0;
     for (uint32_t i = lo + lane; i < hi; i += 128) {
         uint32_t part[4];
@@ -1162,13 +1180,28 @@ __global__ void __launch_bounds__(VERIFY_THREADS) verify_kernel(const VerifyArgs
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-    if (lane == 0) s_total[warp] = sum;
-    __syncthreads();
-    unsigned long long before = 0, total = 0;                      // lines in the runs of the warps before mine / in all
-    for (uint32_t w = 0; w < NW; w++) {
-        const unsigned long long t = s_total[w];
-        if (w < warp) before += t;
+    if (lane == 0) v.run_total[blockIdx.x * (VERIFY_THREADS / 32) + (threadIdx.x >> 5)] = sum;
+}
+
+__global__ void __launch_bounds__(VERIFY_THREADS) verify_kernel(const VerifyArgs v)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const unsigned long long line_base = v.use_arg_state ? v.line_base : v.state_in->next_line;
+    const uint32_t nruns = gridDim.x * (VERIFY_THREADS / 32);
+    const uint32_t run = blockIdx.x * (VERIFY_THREADS / 32) + (tid >> 5);
+    uint32_t lo, hi;
+    verify_run(v, lo, hi);
+
+    unsigned long long before = 0, total = 0;                      // lines in the runs before mine / in all
+    for (uint32_t w = lane; w < nruns; w += 32) {
+        const unsigned long long t = v.run_total[w];
+        if (w < run) before += t;
         total += t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
+        total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
     }
 
     if (v.make_fixes) {
@@ -1207,7 +1240,7 @@ __global__ void __launch_bounds__(VERIFY_THREADS) verify_kernel(const VerifyArgs
             }
         }
     }
-    if (tid == 0) {
+    if (blockIdx.x == 0 && tid == 0) {
         v.state_out->next_line = line_base + total;
         v.state_out->prev_kind = *v.last_kind;
         v.state_out->pad = 0;
