@@ -1,0 +1,528 @@
+// One inflater per LANE: the device side of the gzip feed (csrc/tdg_gzdev.cuh) and its CPU test
+// harness (tests/native/gzlane_check.cpp) share this file.
+//
+// find_tags_fastq opens 'gz' files with gzip.open(f, 'rt') (/root/reference/tagdigger_fun.py:240-241):
+// one deflate stream, no index.  tdg_pgz.h inflates such a stream on host threads by entering it
+// speculatively at block starts and writing 16-bit symbols (a reference into the unknown 32 KiB
+// before the entry point becomes a marker); this file is the same idea shaped for a GPU, where
+// there are thousands of slow lanes instead of sixteen fast cores:
+//   * the compressed stream is cut into chunks, ONE LANE per chunk;
+//   * a lane's Huffman tables live in its own slice of shared memory, interleaved word by word
+//     with the slices of the other 31 lanes of its warp (STRIDE = 32), so that a table look-up of
+//     a whole warp never has a bank conflict whatever the lanes index;
+//   * entries are 16 bits: a 10-bit primary table for literal/length codes, an 8-bit one for
+//     distance codes, no subtables -- longer codes (rare) are decoded canonically, bit by bit,
+//     from the per-length counts and the symbols in code order;
+//   * length / distance bases come from arithmetic, not from tables.
+// Everything that decides whether a chunk's output is USED (the chain from chunk to chunk, member
+// trailers, CRC) is host logic in tdg_gzdev.cuh; a lane only reports where it started, where it
+// stopped and why.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TDG_GZ_HD __host__ __device__ __forceinline__
+#define TDG_GZ_FN __host__ __device__
+#else
+#define TDG_GZ_HD inline
+#define TDG_GZ_FN
+#endif
+
+namespace tdg {
+namespace gzl {
+
+constexpr uint32_t WIN = 32768;
+constexpr int LIT_ROOT = 10, DIST_ROOT = 8, PRE_ROOT = 7;
+
+// lane-private memory map, in 16-bit units (every region starts on a 32-bit word)
+constexpr uint32_t O_LIT = 0;                 // 1024 x u16  primary literal/length table (code-length table while a header is read)
+constexpr uint32_t O_LSORT = O_LIT + 1024;    //  288 x u16  literal/length symbols with codes longer than LIT_ROOT, in code order
+constexpr uint32_t O_LCNT = O_LSORT + 288;    //   16 x u16  codes per length
+constexpr uint32_t O_DIST = O_LCNT + 16;      //  256 x u16  primary distance table
+constexpr uint32_t O_DSORT = O_DIST + 256;    //   32 x u16  distance symbols with codes longer than DIST_ROOT
+constexpr uint32_t O_DCNT = O_DSORT + 32;     //   16 x u16
+constexpr uint32_t O_LENS = O_DCNT + 16;      //  320 x u8   code lengths of the header being read
+constexpr uint32_t LANE_U16 = O_LENS + 160;   // 1,792 units = 3,584 bytes per lane
+static_assert(LANE_U16 % 2 == 0, "a lane's slice is a whole number of 32-bit words");
+
+constexpr uint16_t E_LONG = 0x8000;           // primary entry: the code is longer than the root
+// other entries: symbol << 4 | code length; 0 = no code here
+
+enum : uint32_t {
+    F_FOUND = 1,       // decoding started (a block start was accepted)
+    F_FINAL = 2,       // stopped behind the last block of a member (end_bit = the bit after its end-of-block code)
+    F_ERROR = 4,       // invalid data after end_bit
+    F_SPACE = 8,       // the symbol buffer was full
+    F_INPUT = 16,      // ran out of compressed bytes
+};
+
+struct Meta {                 // what a lane reports about its chunk
+    uint64_t start_bit;       // where decoding started (absolute bit position in the file)
+    uint64_t end_bit;         // the block boundary at which out_len symbols were complete
+    uint32_t out_len;
+    uint32_t flags;
+    uint32_t min_pre;         // smallest index into the 32 KiB before the chunk that a match named directly (WIN: none)
+    uint32_t tried;           // candidates looked at (diagnostics)
+};
+
+template <int STRIDE>
+struct Mem {
+    uint16_t *base;           // the lane's first 16-bit unit
+    TDG_GZ_HD uint16_t &h(uint32_t i) const { return base[((i >> 1) * STRIDE) * 2 + (i & 1u)]; }
+    TDG_GZ_HD uint8_t &b(uint32_t off16, uint32_t i) const
+    {
+        const uint32_t byte = off16 * 2 + i;
+        return ((uint8_t *)base)[((byte >> 2) * STRIDE) * 4 + (byte & 3u)];
+    }
+};
+
+// LSB-first bit reader over 32-bit words (the buffer is padded: words past nwords read as zero)
+struct Bits {
+    const uint32_t *in;
+    uint64_t nwords;
+    uint64_t w;               // next word
+    uint64_t buf;
+    int cnt;
+    TDG_GZ_HD void fill()     // afterwards at least 32 bits are in the buffer
+    {
+        if (cnt <= 32) {
+            const uint32_t x = w < nwords ? in[w] : 0u;
+            w++;
+            buf |= (uint64_t)x << cnt;
+            cnt += 32;
+        }
+    }
+    TDG_GZ_HD void seek(uint64_t bit)
+    {
+        w = bit >> 5;
+        buf = 0;
+        cnt = 0;
+        fill();
+        drop((int)(bit & 31));
+    }
+    TDG_GZ_HD void drop(int n)
+    {
+        buf >>= n;
+        cnt -= n;
+    }
+    TDG_GZ_HD uint32_t take(int n)
+    {
+        const uint32_t v = (uint32_t)buf & ((1u << n) - 1u);
+        drop(n);
+        return v;
+    }
+    TDG_GZ_HD uint64_t pos() const { return w * 32 - (uint64_t)cnt; }
+};
+
+TDG_GZ_HD uint32_t bitrev(uint32_t c, int len)
+{
+    uint32_t r = 0;
+    for (int b = 0; b < len; b++) r |= ((c >> b) & 1u) << (len - 1 - b);
+    return r;
+}
+
+// Builds the decoding structures of one canonical code from the n code lengths that start at
+// byte `first` of the lane's byte array at 16-bit offset o_lens.  Acceptance as in zlib's inflate_table: over-subscribed and incomplete sets
+// are refused, except the incomplete set that is a single 1-bit code (allow_single); a set
+// without any code is accepted and decodes nothing.
+template <int STRIDE>
+TDG_GZ_FN bool build_code(const Mem<STRIDE> m, uint32_t o_lens, uint32_t first, uint32_t n, int root, uint32_t o_tab,
+                          uint32_t o_sort, uint32_t o_cnt, bool allow_single)
+{
+    for (uint32_t l = 0; l < 16; l++) m.h(o_cnt + l) = 0;
+    for (uint32_t i = 0; i < n; i++) m.h(o_cnt + m.b(o_lens, first + i))++;
+    m.h(o_cnt) = 0;
+    int max = 15;
+    while (max >= 1 && !m.h(o_cnt + max)) max--;
+    const uint32_t psize = 1u << root;
+    for (uint32_t j = 0; j < psize; j++) m.h(o_tab + j) = 0;
+    if (max == 0) return true;
+    int left = 1;
+    for (int len = 1; len <= 15; len++) {
+        left <<= 1;
+        left -= (int)m.h(o_cnt + len);
+        if (left < 0) return false;
+    }
+    if (left > 0 && !(allow_single && max == 1)) return false;
+    // codes of at most `root` bits: every table index that ends in the (bit-reversed) code
+    uint32_t code = 0;
+    for (int len = 1; len <= root && len <= max; len++) {
+        code = (code + m.h(o_cnt + len - 1)) << 1;          // first code of this length
+        if (!m.h(o_cnt + len)) continue;
+        uint32_t c = code;
+        for (uint32_t s = 0; s < n; s++) {
+            if (m.b(o_lens, first + s) != len) continue;
+            const uint32_t rev = bitrev(c++, len);
+            const uint16_t e = (uint16_t)(s << 4 | (uint32_t)len);
+            for (uint32_t j = rev; j < psize; j += 1u << len) m.h(o_tab + j) = e;
+        }
+    }
+    // longer codes: mark their root-bit prefixes, list the symbols in code order
+    uint32_t at = 0;
+    for (int len = root + 1; len <= max; len++) {
+        code = (code + m.h(o_cnt + len - 1)) << 1;
+        if (!m.h(o_cnt + len)) continue;
+        uint32_t c = code;
+        for (uint32_t s = 0; s < n; s++) {
+            if (m.b(o_lens, first + s) != len) continue;
+            m.h(o_tab + (bitrev(c >> (len - root), root))) = E_LONG;
+            c++;
+            m.h(o_sort + at++) = (uint16_t)s;
+        }
+    }
+    return true;
+}
+
+// A code longer than the root, bit by bit (canonical order: the first code of each length follows
+// from the counts).  Returns symbol << 4 | length, 0 when the bits are no code.
+template <int STRIDE>
+TDG_GZ_FN uint32_t decode_long(const Mem<STRIDE> m, uint64_t buf, int root, uint32_t o_sort, uint32_t o_cnt)
+{
+    uint32_t code = 0, first = 0;
+    for (int len = 1; len <= root; len++) {
+        code |= (uint32_t)(buf & 1u);
+        buf >>= 1;
+        first = (first + m.h(o_cnt + len)) << 1;
+        code <<= 1;
+    }
+    uint32_t index = 0;
+    for (int len = root + 1; len <= 15; len++) {
+        code |= (uint32_t)(buf & 1u);
+        buf >>= 1;
+        const uint32_t count = m.h(o_cnt + len);
+        if (code < first + count) return (uint32_t)m.h(o_sort + index + (code - first)) << 4 | (uint32_t)len;
+        index += count;
+        first = (first + count) << 1;
+        code <<= 1;
+    }
+    return 0;
+}
+
+template <int STRIDE>
+struct Lane {
+    Mem<STRIDE> m;
+    Bits bits;
+    uint64_t in_bits;         // valid bits of the buffer
+    uint64_t wmax;            // a word index beyond this means the input is exhausted for sure
+    uint16_t *out;
+    uint32_t cap;             // symbols `out` can hold
+    uint32_t o;               // symbols produced
+    uint32_t hist;            // how far back a distance may reach beyond o (WIN: unknown prehistory)
+    uint32_t min_pre;
+    bool fixed_loaded;
+
+    TDG_GZ_HD bool exhausted() const { return bits.pos() > in_bits; }
+
+    TDG_GZ_FN bool load_fixed()
+    {
+        for (uint32_t i = 0; i < 144; i++) m.b(O_LENS, i) = 8;
+        for (uint32_t i = 144; i < 256; i++) m.b(O_LENS, i) = 9;
+        for (uint32_t i = 256; i < 280; i++) m.b(O_LENS, i) = 7;
+        for (uint32_t i = 280; i < 288; i++) m.b(O_LENS, i) = 8;
+        if (!build_code<STRIDE>(m, O_LENS, 0, 288, LIT_ROOT, O_LIT, O_LSORT, O_LCNT, true)) return false;
+        for (uint32_t i = 0; i < 32; i++) m.b(O_LENS, i) = 5;
+        return build_code<STRIDE>(m, O_LENS, 0, 32, DIST_ROOT, O_DIST, O_DSORT, O_DCNT, true);
+    }
+
+    // dynamic block header at the reader's position (behind the three block bits)
+    TDG_GZ_FN bool read_dynamic()
+    {
+        bits.fill();
+        const uint32_t hlit = bits.take(5) + 257, hdist = bits.take(5) + 1, hclen = bits.take(4) + 4;
+        if (hlit > 286 || hdist > 30) return false;
+        // order of the code-length code's lengths: 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15, five bits each
+        const uint64_t ord0 = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 |
+                              10ull << 40 | 5ull << 45 | 11ull << 50 | 4ull << 55;
+        const uint64_t ord1 = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
+        // the code-length code: its lengths sit in the (still unused) distance table, its decoding
+        // structures borrow the literal/length regions -- both are rebuilt below
+        for (uint32_t i = 0; i < 19; i++) m.b(O_DIST, i) = 0;
+        for (uint32_t i = 0; i < hclen; i++) {
+            bits.fill();
+            const uint32_t sym = (uint32_t)((i < 12 ? ord0 >> (5 * i) : ord1 >> (5 * (i - 12))) & 31u);
+            m.b(O_DIST, sym) = (uint8_t)bits.take(3);
+        }
+        if (!build_code<STRIDE>(m, O_DIST, 0, 19, PRE_ROOT, O_LIT, O_LSORT, O_LCNT, false)) return false;
+        const uint32_t total = hlit + hdist;
+        uint32_t i = 0;
+        uint32_t prev = 0;
+        while (i < total) {
+            bits.fill();
+            const uint32_t e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << PRE_ROOT) - 1u)));
+            if (e == 0 || (e & E_LONG)) return false;       // (codes of the code-length code have at most 7 bits)
+            bits.drop((int)(e & 15u));
+            const uint32_t sym = e >> 4;
+            if (sym < 16) {
+                m.b(O_LENS, i) = (uint8_t)sym;
+                prev = sym;
+                i++;
+                continue;
+            }
+            uint32_t rep, val = 0;
+            if (sym == 16) {
+                if (i == 0) return false;
+                val = prev;
+                rep = 3 + bits.take(2);
+            } else if (sym == 17) {
+                rep = 3 + bits.take(3);
+            } else {
+                rep = 11 + bits.take(7);
+            }
+            if (i + rep > total) return false;
+            while (rep--) m.b(O_LENS, i++) = (uint8_t)val;
+            prev = val;
+        }
+        if (exhausted()) return false;
+        if (m.b(O_LENS, 256) == 0) return false;            // no end-of-block code
+        if (!build_code<STRIDE>(m, O_LENS, 0, hlit, LIT_ROOT, O_LIT, O_LSORT, O_LCNT, true)) return false;
+        if (!build_code<STRIDE>(m, O_LENS, hlit, hdist, DIST_ROOT, O_DIST, O_DSORT, O_DCNT, true)) return false;
+        fixed_loaded = false;
+        return true;
+    }
+
+    // The symbols of one Huffman block up to its end-of-block code.  0 done, else F_ERROR / F_SPACE / F_INPUT.
+    TDG_GZ_FN uint32_t huff_block()
+    {
+        for (;;) {
+            if (o + 260 > cap) return F_SPACE;
+            if (bits.w > wmax) return F_INPUT;
+            bits.fill();
+            uint32_t e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << LIT_ROOT) - 1u)));
+            if (e & E_LONG) e = decode_long<STRIDE>(m, bits.buf, LIT_ROOT, O_LSORT, O_LCNT);
+            if (e == 0) return F_ERROR;
+            bits.drop((int)(e & 15u));
+            uint32_t sym = e >> 4;
+            if (sym < 256) {
+                out[o++] = (uint16_t)sym;
+                // a second literal without another fill (at least 17 bits are left)
+                e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << LIT_ROOT) - 1u)));
+                if (e == 0 || e >= (256u << 4)) continue;   // not a short literal code: the next round looks again
+                bits.drop((int)(e & 15u));
+                out[o++] = (uint16_t)(e >> 4);
+                continue;
+            }
+            if (sym == 256) return exhausted() ? F_INPUT : 0;
+            if (sym > 285) return F_ERROR;
+            uint32_t len;
+            {
+                const uint32_t idx = sym - 257;
+                if (idx < 8) len = 3 + idx;
+                else if (idx == 28) len = 258;
+                else {
+                    const int eb = (int)((idx - 4) >> 2);
+                    len = 3 + ((4 + (idx & 3u)) << eb) + bits.take(eb);
+                }
+            }
+            bits.fill();
+            uint32_t f = m.h(O_DIST + ((uint32_t)bits.buf & ((1u << DIST_ROOT) - 1u)));
+            if (f & E_LONG) f = decode_long<STRIDE>(m, bits.buf, DIST_ROOT, O_DSORT, O_DCNT);
+            if (f == 0) return F_ERROR;
+            bits.drop((int)(f & 15u));
+            const uint32_t ds = f >> 4;
+            if (ds > 29) return F_ERROR;
+            uint32_t d;
+            if (ds < 4) d = 1 + ds;
+            else {
+                const int eb = (int)(ds >> 1) - 1;
+                d = 1 + ((2 + (ds & 1u)) << eb) + bits.take(eb);
+            }
+            if (d > o) {
+                if (d - o > hist) return F_ERROR;           // too far back
+                const uint32_t pre = WIN - (d - o);
+                if (pre < min_pre) min_pre = pre;
+            }
+            // symbol j of the stream seen from this chunk: j < 0 is prehistory -> marker 256 + (WIN + j)
+            int32_t j = (int32_t)o - (int32_t)d;
+            for (uint32_t k = 0; k < len; k++, j++) out[o + k] = j < 0 ? (uint16_t)(256 + WIN + j) : out[j];
+            o += len;
+        }
+    }
+
+    // Inflates blocks until a block boundary at or beyond stop_bit.  Returns 0 (stopped at the
+    // boundary), F_FINAL (behind a member's last block), or the reason decoding could not go on;
+    // last_bit / last_o are the last boundary passed.
+    TDG_GZ_FN uint32_t run(uint64_t stop_bit, uint64_t &last_bit, uint32_t &last_o, bool one_block)
+    {
+        for (;;) {
+            const uint64_t bp = bits.pos();
+            last_bit = bp;
+            last_o = o;
+            if (bp >= stop_bit) return 0;
+            if (bp + 3 > in_bits) return F_INPUT;
+            bits.fill();
+            const uint32_t h = bits.take(3);
+            const uint32_t type = h >> 1;
+            if (type == 0) {
+                bits.drop(bits.cnt & 7);
+                bits.fill();
+                const uint32_t len = bits.take(16);
+                bits.fill();
+                const uint32_t nlen = bits.take(16);
+                if ((len ^ 0xffffu) != nlen) return F_ERROR;
+                if (bits.pos() + (uint64_t)len * 8 > in_bits) return F_INPUT;
+                if (o + len + 260 > cap) return F_SPACE;
+                for (uint32_t k = 0; k < len; k++) {
+                    bits.fill();
+                    out[o++] = (uint16_t)bits.take(8);
+                }
+            } else if (type == 3) {
+                return F_ERROR;
+            } else {
+                if (type == 1) {
+                    if (!fixed_loaded) {
+                        if (!load_fixed()) return F_ERROR;
+                        fixed_loaded = true;
+                    }
+                } else if (!read_dynamic()) {
+                    return exhausted() ? F_INPUT : F_ERROR;
+                }
+                const uint32_t r = huff_block();
+                if (r) return r;
+            }
+            if (h & 1u) {
+                last_bit = bits.pos();
+                last_o = o;
+                return F_FINAL;
+            }
+            if (one_block) {
+                last_bit = bits.pos();
+                last_o = o;
+                return 0;
+            }
+        }
+    }
+
+    // Is the header at the reader's position (a copy of the reader is used) at least sane?
+    TDG_GZ_FN bool next_header_sane()
+    {
+        const Bits save = bits;
+        bool ok = true;
+        if (bits.pos() + 3 > in_bits) ok = false;
+        else {
+            bits.fill();
+            const uint32_t h = bits.take(3);
+            if ((h >> 1) == 3) ok = false;
+            else if ((h >> 1) == 0) {
+                bits.drop(bits.cnt & 7);
+                bits.fill();
+                const uint32_t len = bits.take(16);
+                bits.fill();
+                const uint32_t nlen = bits.take(16);
+                ok = (len ^ 0xffffu) == nlen;
+            } else if ((h >> 1) == 2) {
+                ok = read_dynamic();
+                fixed_loaded = false;
+            }
+            if (exhausted()) ok = false;
+        }
+        bits = save;
+        return ok;
+    }
+};
+
+// Cheap test of bit position p as the start of a non-final dynamic block: block bits, HLIT / HDIST
+// in range, and the code-length code exactly complete.  lo = the 64 bits at p, hi = the 32 after
+// them.  kraft3[v] = sum over the three 3-bit lengths in v of (128 >> length), zero lengths adding
+// nothing (512 entries, shared).
+TDG_GZ_HD bool quick_test(uint64_t lo, uint32_t hi, const uint8_t *kraft3)
+{
+    if (((uint32_t)lo & 7u) != 4u) return false;
+    if ((((uint32_t)lo >> 3) & 31u) > 29u || (((uint32_t)lo >> 8) & 31u) > 29u) return false;
+    const uint32_t n = (((uint32_t)lo >> 13) & 15u) + 4u;           // lengths present: 4..19
+    uint64_t v = lo >> 17 | (uint64_t)hi << 47;                      // 57 bits of lengths (bits 17..73 of the header)
+    if (n < 19) v &= (1ull << (3 * n)) - 1ull;
+    else v &= (1ull << 57) - 1ull;
+    uint32_t sum = 0;
+    for (int j = 0; j < 7; j++) sum += kraft3[(uint32_t)(v >> (9 * j)) & 511u];
+    return sum == 128u;
+}
+
+inline void make_kraft3(uint8_t *t)
+{
+    for (uint32_t v = 0; v < 512; v++) {
+        uint32_t s = 0;
+        for (int k = 0; k < 3; k++) {
+            const uint32_t l = (v >> (3 * k)) & 7u;
+            if (l) s += 128u >> l;
+        }
+        t[v] = (uint8_t)s;
+    }
+}
+
+// Does a dynamic block header parse at `bit` (both Huffman codes valid, an end-of-block code
+// present)?  The scan's second test for a position that passed quick_test.
+template <int STRIDE>
+TDG_GZ_FN bool header_parses(Mem<STRIDE> m, const uint32_t *in, uint64_t nwords, uint64_t in_bits, uint64_t bit)
+{
+    Lane<STRIDE> z;
+    z.m = m;
+    z.bits.in = in;
+    z.bits.nwords = nwords;
+    z.in_bits = in_bits;
+    z.wmax = (in_bits + 31) / 32 + 2;
+    z.fixed_loaded = false;
+    z.bits.seek(bit);
+    z.bits.fill();
+    z.bits.drop(3);
+    return z.read_dynamic();
+}
+
+// A lane's whole job for its chunk: try the candidate block starts `cand[0..ncand)` (bit offsets
+// from search_base, ascending; positions where the scan kernel saw a dynamic block header parse) until one holds -- its header parses,
+// its first block decodes and the header behind that block is sane -- then inflate up to the block
+// boundary at or beyond stop_bit.  `known`: start exactly at search_base with `hist` bytes of real
+// history (the first chunk of a round); nothing is tried, every defect is real.
+// Bit positions are relative to the buffer (`in`); the caller adds the buffer's place in the file.
+template <int STRIDE>
+TDG_GZ_FN void run_chunk(Mem<STRIDE> m, const uint32_t *in, uint64_t nwords, uint64_t in_bits, bool known, uint64_t search_base,
+                         const uint32_t *cand, uint32_t ncand, uint64_t stop_bit, uint32_t hist, uint16_t *out, uint32_t cap,
+                         Meta &r)
+{
+    Lane<STRIDE> z;
+    z.m = m;
+    z.bits.in = in;
+    z.bits.nwords = nwords;
+    z.in_bits = in_bits;
+    z.wmax = (in_bits + 31) / 32 + 2;
+    z.out = out;
+    z.cap = cap;
+    r.start_bit = search_base;
+    r.end_bit = search_base;
+    r.out_len = 0;
+    r.flags = 0;
+    r.min_pre = WIN;
+    r.tried = 0;
+    uint64_t last_bit = 0;
+    uint32_t last_o = 0;
+    uint32_t c = 0;
+    for (;;) {
+        uint64_t start;
+        if (known) start = search_base;
+        else {
+            if (c >= ncand) return;                          // nothing held: F_FOUND stays clear
+            start = search_base + cand[c++];
+            r.tried = c;
+        }
+        z.bits.seek(start);
+        z.o = 0;
+        z.hist = known ? hist : WIN;
+        z.min_pre = WIN;
+        z.fixed_loaded = false;
+        if (!known) {
+            // exactly one block, then a look at the next header
+            const uint32_t s = z.run(~0ull, last_bit, last_o, true);
+            if (s != 0 || !z.next_header_sane()) continue;
+        }
+        const uint32_t s = z.run(stop_bit, last_bit, last_o, false);
+        r.start_bit = start;
+        r.end_bit = last_bit;
+        r.out_len = last_o;
+        r.flags = F_FOUND | s;
+        r.min_pre = z.min_pre;
+        return;
+    }
+}
+
+}  // namespace gzl
+}  // namespace tdg

@@ -634,6 +634,28 @@ public:
         return true;
     }
 
+    // Continues a stream that another inflater (the device feed, csrc/tdg_gzdev.cuh) has brought to
+    // the block boundary at bit `pos_bit`: `window` holds the WIN bytes in front of it (the last
+    // `hist` of them belong to the member being inflated), `crc` / `member_len` are the member's
+    // running CRC-32 and length, `delivered` the uncompressed offset reached.
+    void resume(const uint8_t *data, size_t size, int threads, size_t chunk_bytes, uint64_t pos_bit, const uint8_t *window,
+                size_t hist, uint32_t crc, uint64_t member_len, uint64_t delivered)
+    {
+        in_ = data;
+        size_ = size;
+        threads_ = std::max(1, threads);
+        chunk_ = std::max<size_t>(chunk_bytes, 4096);
+        pos_bit_ = pos_bit;
+        hist_ = std::min<size_t>(hist, WIN);
+        window_.assign(window, window + WIN);
+        crc_ = crc;
+        member_len_ = member_len;
+        delivered_ = delivered;
+        eof_ = fallback_ = bad_check_ = false;
+        segs_.clear();
+        seg_ = 0;
+    }
+
     // Up to cap bytes into p.  >0 bytes delivered; 0 end of file; -1 the caller must continue
     // with zlib at uncompressed offset delivered(); -2 a member's CRC32 / ISIZE did not match.
     long long read(uint8_t *p, size_t cap)
