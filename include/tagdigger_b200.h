@@ -139,12 +139,30 @@ int         tdg_count_device(tdg_ctx *ctx, const void *dev_bytes, size_t n,
 int         tdg_count_lines_device(tdg_ctx *ctx, const void *dev_bytes, size_t n,
                                    uint64_t line_base, int prev_kind, uint64_t state[2]);
 
-/* Whole file: open (zlib inflate on a host thread when `gz` is non-zero -- the
- * reference decides gz by the last two characters of the name, :240; the
- * binding passes that decision), stream through pinned buffers, count.
+/* Whole file (replaces open / gzip.open + the loop, tagdigger_fun.py:240-277): `gz` non-zero = the
+ * file is gzip -- the reference decides that by the last two characters of the name, :240; the
+ * binding passes that decision.  Plain files are read by host threads into pinned buffers and
+ * copied to the device piece by piece.  Ordinary gzip files of 8 MiB and more are inflated ON THE
+ * DEVICE (csrc/tdg_gzdev.cuh: the compressed bytes cross PCIe, thousands of lanes enter the one
+ * deflate stream speculatively at block starts, the text is born in HBM and counted there); BGZF
+ * files, small files, reads behind a `reads_limit`, and the rest of any stream that holds something
+ * the device feed does not judge (stored data it cannot enter, a damaged or truncated stream, a
+ * header with unusual flags) are inflated by host threads (csrc/tdg_pgz.h, csrc/tdg_feed.h), which
+ * resume at exactly the bit the device feed reached -- so every error is raised by one code path:
+ * TDG_ERR_GZIP with zlib's words, which the binding maps to EOFError / zlib.error / BadGzipFile
+ * like gzip.open.  TDG_GZDEV=0 in the environment keeps all inflating on the host.
  * totals: reads, reads with barcode+cutsite, reads with tag, text lines. */
 int         tdg_count_file(tdg_ctx *ctx, const char *path, int gz,
                            uint64_t reads_limit, uint64_t totals[4]);
+
+/* The gzip feed of tdg_count_file by itself (tests, profiling): inflates `path` into the host
+ * buffer dst[0..cap) -- rounds on the device, the rest, if any, through the host feeder -- and
+ * reports the number of bytes in *n.  info: [0] device rounds, [1] chunks run, [2] chunks accepted,
+ * [3] 0 = everything on the device, 1 = the host's parallel reader resumed, 2 = zlib resumed,
+ * -1 = not a file the device feed takes; ms (may be null): milliseconds of upload, scan, decode,
+ * windows + resolve, CRC fold, copy-out.  Errors as tdg_count_file. */
+int         tdg_gz_inflate_host(tdg_ctx *ctx, const char *path, void *dst, size_t cap, uint64_t *n,
+                                int64_t info[4], double ms[6]);
 
 /* Wait for all submitted work. */
 int         tdg_sync(tdg_ctx *ctx);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <zlib.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +24,8 @@
 #include "tdg_tables.h"
 #include "tdg_trim.cuh"
 #include "tdg_split.cuh"
+#include "tdg_gzchain.h"
+#include "tdg_gzdev.cuh"
 
 static_assert(TDG_HALO_BYTES >= tdg::HALO, "the allocation slack promised by the header must cover the kernel halo");
 static_assert(TDG_TILE_BYTES >= tdg::TILE, "the allocation granule promised by the header must cover a kernel tile");
@@ -115,6 +118,13 @@ struct tdg_ctx {
     uint8_t *file_buf[3] = {nullptr, nullptr, nullptr};
     size_t file_buf_cap = 0;
 
+    // device-side gzip feed (tdg_gzdev.cuh): growable buffers, kept between files
+    Grow gz_comp, gz_syms, gz_meta, gz_cand, gz_ncand, gz_windows, gz_text, gz_crc, gz_lens, gz_offs, gz_tabs, gz_carry;   // device
+    Grow gz_hmeta, gz_hcrc, gz_htail;                                                                                       // pinned host
+    cudaEvent_t gz_up[3] = {nullptr, nullptr, nullptr};
+    bool gz_tables = false;
+    uint32_t gz_op[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
     // multi-GPU: the communicator of tdg_comm_init (one rank per context)
     tdg::NcclApi::Comm comm = nullptr;
     int comm_ranks = 1;
@@ -142,6 +152,27 @@ int fail(tdg_ctx *ctx, int code, const std::string &msg)
     } while (0)
 
 size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// growable device / pinned buffers (contents are NOT kept)
+int grow(tdg_ctx *ctx, tdg_ctx::Grow &g, size_t need, bool host)
+{
+    if (need <= g.cap) return TDG_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (g.p) {
+        if (g.host) cudaFreeHost(g.p); else cudaFree(g.p);
+        g.p = nullptr;
+        g.cap = 0;
+    }
+    const size_t cap = need + need / 4 + 4096;
+    cudaError_t e = host ? cudaHostAlloc(&g.p, cap, cudaHostAllocDefault) : cudaMalloc(&g.p, cap);
+    if (e != cudaSuccess) {
+        g.p = nullptr;
+        return fail(ctx, TDG_ERR_NOMEM, std::string("buffer of ") + std::to_string(cap) + " bytes: " + cudaGetErrorString(e));
+    }
+    g.cap = cap;
+    g.host = host;
+    return TDG_OK;
+}
 
 // per-launch scratch: header, then SegInfo[num_segs], then FixEntry[num_segs]
 struct ScratchHeader {
@@ -515,6 +546,386 @@ int end_file_impl(tdg_ctx *ctx, uint64_t reads_limit)
     return TDG_OK;
 }
 
+
+// ---------------------------------------------------------------------------
+// Device-side gzip feed (tdg_gzlane.h, tdg_gzchain.h, tdg_gzdev.cuh)
+
+struct GzHandover {              // how the host feeder continues when the device feed stops early
+    bool active = false;
+    bool to_zlib = false;
+    uint64_t pos_bit = 0, member_len = 0, delivered = 0;
+    uint32_t hist = 0, crc = 0;
+    std::vector<uint8_t> window;
+    std::string why;
+};
+
+struct GzStats {
+    uint32_t rounds = 0, chunks = 0, accepted = 0;
+    double ms_upload = 0, ms_scan = 0, ms_decode = 0, ms_host = 0, ms_resolve = 0, ms_sink = 0;
+};
+
+// what happens to a round's text: counted (tdg_count_file) or copied out (tdg_gz_inflate_host)
+struct GzSink {
+    virtual ~GzSink() {}
+    // d_buf[0 .. carry) = bytes kept from the round before, d_buf[carry .. carry + len) = new text.
+    // Sets `carry` to the number of bytes it wants to see again, in front of the next round's text
+    // (they must be at d_buf[0 ..) when it returns -- stream order).
+    virtual int text(tdg_ctx *ctx, uint8_t *d_buf, size_t &carry, size_t len) = 0;
+};
+
+int gz_io_threads()
+{
+    int t = 16;
+    if (const char *e = getenv("TDG_IO_THREADS")) t = std::max(1, atoi(e));
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw && t > (int)hw) t = (int)hw;
+    return t;
+}
+
+bool gz_pread_parallel(int fd, uint8_t *dst, size_t n, uint64_t off, int threads)
+{
+    int nt = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, n >> 22));
+    std::vector<char> ok(nt, 1);
+    auto work = [&](int t) {
+        size_t lo = n / nt * t, hi = t == nt - 1 ? n : n / nt * (t + 1);
+        while (lo < hi) {
+            ssize_t r = pread(fd, dst + lo, hi - lo, (off_t)(off + lo));
+            if (r <= 0) { ok[t] = 0; return; }
+            lo += (size_t)r;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    for (char c : ok)
+        if (!c) return false;
+    return true;
+}
+
+int gz_tables(tdg_ctx *ctx)
+{
+    if (ctx->gz_tables) return TDG_OK;
+    // [kraft3 512][crc table 256 x u32][window 32768]
+    int rc = grow(ctx, ctx->gz_tabs, 512 + 1024 + tdg::gzl::WIN, false);
+    if (rc) return rc;
+    std::vector<uint8_t> blob(512 + 1024);
+    tdg::gzl::make_kraft3(blob.data());
+    uint32_t *tab = (uint32_t *)(blob.data() + 512);
+    for (uint32_t i = 0; i < 256; i++) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
+        tab[i] = c;
+    }
+    CK(cudaMemcpy(ctx->gz_tabs.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    for (int j = 0; j < 8; j++) ctx->gz_op[j] = (uint32_t)crc32_combine_gen((z_off_t)(tdg::gzd::SUB << j));
+    for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&ctx->gz_up[i], cudaEventDisableTiming));
+    CK(cudaFuncSetAttribute(tdg::gzd::gz_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tdg::gzd::DEC_SMEM));
+    CK(cudaFuncSetAttribute(tdg::gzd::gz_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * tdg::gzl::WIN)));
+    ctx->gz_tables = true;
+    return TDG_OK;
+}
+
+// Inflates `path` (an ordinary gzip file) on the device round by round and hands every round's
+// text to `sink`.  handled = false: nothing was done (a header this feed does not take: the host
+// feeder starts from the beginning).  Otherwise the text went to the sink up to the end of the
+// file, or up to the place `ho` describes (ho.active), where the host feeder continues.
+int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, GzHandover &ho, size_t &carry, GzStats *stats,
+                   tdg::Utf8State *u8)
+{
+    using namespace tdg;
+    handled = false;
+    ho = GzHandover();
+    struct Map {
+        int fd = -1;
+        const uint8_t *p = nullptr;
+        size_t n = 0;
+        ~Map()
+        {
+            if (p) munmap(const_cast<uint8_t *>(p), n);
+            if (fd >= 0) ::close(fd);
+        }
+    } map;
+    map.fd = ::open(path, O_RDONLY);
+    if (map.fd < 0) return TDG_OK;                       // the host feeder reports it
+    struct stat sb;
+    if (fstat(map.fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size < 32) return TDG_OK;
+    map.n = (size_t)sb.st_size;
+    void *mp = mmap(nullptr, map.n, PROT_READ, MAP_PRIVATE, map.fd, 0);
+    if (mp == MAP_FAILED) return TDG_OK;
+    map.p = (const uint8_t *)mp;
+    if (tdg::Feeder::is_bgzf(map.p, std::min<size_t>(map.n, 1024))) return TDG_OK;     // BGZF: members inflate in parallel on the host
+    gzc::Stream st;
+    if (!st.open(map.p, map.n)) return TDG_OK;
+    int rc = gz_tables(ctx);
+    if (rc) return rc;
+    rc = ensure_slots(ctx);
+    if (rc) return rc;
+
+    size_t chunk = (size_t)128 << 10;
+    if (const char *e = getenv("TDG_GZDEV_CHUNK")) chunk = std::max<size_t>(4096, strtoull(e, nullptr, 10) / 16 * 16);
+    uint32_t symcap = (uint32_t)(8 * chunk);
+    if (const char *e = getenv("TDG_GZDEV_SYMCAP")) symcap = (uint32_t)std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
+    uint32_t max_chunks = (uint32_t)ctx->sm_count * gzd::DEC_THREADS;
+    if (const char *e = getenv("TDG_GZDEV_MAXCHUNKS")) max_chunks = (uint32_t)std::max(1, atoi(e));
+    const bool debug = getenv("TDG_GZDEV_DEBUG") != nullptr;
+    const int threads = gz_io_threads();
+    uint8_t *d_tabs = (uint8_t *)ctx->gz_tabs.p;
+    uint8_t *d_window = d_tabs + 512 + 1024;
+    CK(cudaMemsetAsync(d_window, 0, gzl::WIN, ctx->stream));
+    handled = true;
+    carry = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+
+    while (!st.eof && !st.handover) {
+        const gzc::Round r = st.plan(chunk, max_chunks);
+        const size_t nb = r.buf_end - r.buf_off;
+        const size_t nwords = (nb + 3) / 4;
+        // ---- the round's compressed bytes: file -> pinned pieces -> device
+        auto t0 = now();
+        rc = grow(ctx, ctx->gz_comp, nwords * 4 + 256, false);
+        if (rc) return rc;
+        {
+            const size_t piece = ctx->file_buf_cap;
+            int bi = 0;
+            for (size_t at = 0; at < nb; at += piece, bi = (bi + 1) % 3) {
+                const size_t m = std::min(piece, nb - at);
+                CK(cudaEventSynchronize(ctx->gz_up[bi]));
+                if (!gz_pread_parallel(map.fd, ctx->file_buf[bi], m, r.buf_off + at, threads))
+                    return fail(ctx, TDG_ERR_IO, std::string("read error on ") + path);
+                CK(cudaMemcpyAsync((uint8_t *)ctx->gz_comp.p + at, ctx->file_buf[bi], m, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaEventRecord(ctx->gz_up[bi], ctx->stream));
+            }
+            CK(cudaMemsetAsync((uint8_t *)ctx->gz_comp.p + nb, 0, nwords * 4 + 256 - nb, ctx->stream));
+        }
+        if ((rc = grow(ctx, ctx->gz_syms, (size_t)r.nchunks * symcap * 2, false))) return rc;
+        if ((rc = grow(ctx, ctx->gz_meta, (size_t)r.nchunks * sizeof(gzl::Meta), false))) return rc;
+        if ((rc = grow(ctx, ctx->gz_cand, (size_t)r.nchunks * gzd::MAXC * 4, false))) return rc;
+        if ((rc = grow(ctx, ctx->gz_ncand, (size_t)r.nchunks * 4, false))) return rc;
+        if ((rc = grow(ctx, ctx->gz_hmeta, (size_t)r.nchunks * sizeof(gzl::Meta), true))) return rc;
+        if (debug) CK(cudaStreamSynchronize(ctx->stream));
+        auto t1 = now();
+        // ---- scan + decode
+        gzd::RoundArgs a;
+        a.in = (const uint32_t *)ctx->gz_comp.p;
+        a.nwords = nwords;
+        a.in_bits = (uint64_t)nb * 8;
+        a.nchunks = r.nchunks;
+        a.chunk_bytes = chunk;
+        a.file_left = map.n - r.grid;
+        a.pos_rel = r.pos_bit - (uint64_t)r.grid * 8;
+        a.base_bit = (uint64_t)r.grid * 8;
+        a.hist = r.hist;
+        a.symcap = symcap;
+        a.cand = (uint32_t *)ctx->gz_cand.p;
+        a.ncand = (uint32_t *)ctx->gz_ncand.p;
+        a.syms = (uint16_t *)ctx->gz_syms.p;
+        a.meta = (gzl::Meta *)ctx->gz_meta.p;
+        a.kraft3 = d_tabs;
+        CK(cudaMemsetAsync(ctx->gz_ncand.p, 0, (size_t)r.nchunks * 4, ctx->stream));
+        if (r.nchunks > 1) {
+            const unsigned g = (r.nchunks - 1 + gzd::SCAN_WARPS - 1) / gzd::SCAN_WARPS;
+            gzd::gz_scan<<<g, gzd::SCAN_WARPS * 32, gzd::SCAN_SMEM, ctx->stream>>>(a);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
+        if (debug) CK(cudaStreamSynchronize(ctx->stream));
+        auto t2 = now();
+        gzd::gz_decode<<<(r.nchunks + gzd::DEC_THREADS - 1) / gzd::DEC_THREADS, gzd::DEC_THREADS, gzd::DEC_SMEM, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        gzl::Meta *meta = (gzl::Meta *)ctx->gz_hmeta.p;
+        CK(cudaMemcpyAsync(meta, ctx->gz_meta.p, (size_t)r.nchunks * sizeof(gzl::Meta), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        auto t3 = now();
+        // ---- which chunks continue the stream
+        const gzc::Outcome o = st.chain(r, meta);
+        uint64_t text_len = o.text_off.back();
+        uint32_t text_crc = 0;
+        auto t4 = t3, t5 = t3;
+        if (o.accepted && text_len) {
+            const uint32_t pieces = (uint32_t)((text_len + gzd::PIECE - 1) / gzd::PIECE);
+            if ((rc = grow(ctx, ctx->gz_windows, ((size_t)o.accepted + 1) * gzl::WIN, false))) return rc;
+            if ((rc = grow(ctx, ctx->gz_lens, (size_t)o.accepted * 4, false))) return rc;
+            if ((rc = grow(ctx, ctx->gz_offs, ((size_t)o.accepted + 1) * 8, false))) return rc;
+            if ((rc = grow(ctx, ctx->gz_crc, (size_t)pieces * 4 + 16, false))) return rc;
+            if ((rc = grow(ctx, ctx->gz_hcrc, (size_t)pieces * 4 + 16, true))) return rc;
+            // the text buffer keeps the carried bytes in front
+            const size_t need = round_up(carry + text_len, TDG_TILE_BYTES) + TDG_HALO_BYTES + 64;
+            if (need > ctx->gz_text.cap) {
+                if (carry) {
+                    if ((rc = grow(ctx, ctx->gz_carry, carry, false))) return rc;
+                    CK(cudaMemcpyAsync(ctx->gz_carry.p, ctx->gz_text.p, carry, cudaMemcpyDeviceToDevice, ctx->stream));
+                }
+                if ((rc = grow(ctx, ctx->gz_text, need, false))) return rc;
+                if (carry) CK(cudaMemcpyAsync(ctx->gz_text.p, ctx->gz_carry.p, carry, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            std::vector<uint32_t> lens(o.accepted);
+            for (uint32_t k = 0; k < o.accepted; k++) lens[k] = meta[k].out_len;
+            CK(cudaMemcpyAsync(ctx->gz_lens.p, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->gz_offs.p, o.text_off.data(), o.text_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->gz_windows.p, d_window, gzl::WIN, cudaMemcpyDeviceToDevice, ctx->stream));
+            gzd::WinArgs w;
+            w.syms = a.syms;
+            w.symcap = symcap;
+            w.out_len = (const uint32_t *)ctx->gz_lens.p;
+            w.accepted = o.accepted;
+            w.windows = (uint8_t *)ctx->gz_windows.p;
+            gzd::gz_windows<<<1, gzd::WIN_THREADS, 2 * gzl::WIN, ctx->stream>>>(w);
+            CK(cudaGetLastError());
+            if (debug) {
+                CK(cudaStreamSynchronize(ctx->stream));
+                fprintf(stderr, "gzdev windows: %.1f ms\n", ms(t3, now()));
+            }
+            uint32_t *d_flag = (uint32_t *)ctx->gz_crc.p + pieces;
+            CK(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
+            gzd::ResArgs ra;
+            ra.syms = a.syms;
+            ra.symcap = symcap;
+            ra.text_off = (const uint64_t *)ctx->gz_offs.p;
+            ra.accepted = o.accepted;
+            ra.windows = (const uint8_t *)ctx->gz_windows.p;
+            ra.text = (uint8_t *)ctx->gz_text.p + carry;
+            ra.text_len = text_len;
+            ra.crc = (uint32_t *)ctx->gz_crc.p;
+            ra.flag = d_flag;
+            ra.table = (const uint32_t *)(d_tabs + 512);
+            for (int j = 0; j < 8; j++) ra.op[j] = ctx->gz_op[j];
+            gzd::gz_resolve<<<pieces, gzd::RES_THREADS, 0, ctx->stream>>>(ra);
+            CK(cudaGetLastError());
+            ctx->launches += 2;
+            // the window behind the last accepted chunk opens the next round
+            CK(cudaMemcpyAsync(d_window, (uint8_t *)ctx->gz_windows.p + (size_t)o.accepted * gzl::WIN, gzl::WIN, cudaMemcpyDeviceToDevice,
+                               ctx->stream));
+            uint32_t *hcrc = (uint32_t *)ctx->gz_hcrc.p;
+            CK(cudaMemcpyAsync(hcrc, ctx->gz_crc.p, (size_t)pieces * 4 + 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            t4 = now();
+            // CRC-32 of the round's text from the pieces' raw CRCs
+            const uLong op_full = crc32_combine_gen((z_off_t)gzd::PIECE);
+            uLong raw = 0;
+            for (uint32_t p = 0; p + 1 < pieces; p++) raw = crc32_combine_op(raw, hcrc[p], op_full);
+            const uint64_t last_len = text_len - (uint64_t)(pieces - 1) * gzd::PIECE;
+            raw = crc32_combine_op(raw, hcrc[pieces - 1], crc32_combine_gen((z_off_t)last_len));
+            text_crc = (uint32_t)(raw ^ crc32_combine_op(0xFFFFFFFFul, 0, crc32_combine_gen((z_off_t)text_len)) ^ 0xFFFFFFFFul);
+            // text mode: bytes >= 0x80 must form valid UTF-8 (open(f, 'rt'))
+            if (u8) {
+                if ((hcrc[pieces] & 0x80u) || u8->need) {
+                    std::vector<uint8_t> host(text_len);
+                    CK(cudaMemcpy(host.data(), (uint8_t *)ctx->gz_text.p + carry, text_len, cudaMemcpyDeviceToHost));
+                    long long bad = tdg::utf8_feed(*u8, host.data(), host.size());
+                    if (bad >= 0) return fail(ctx, TDG_ERR_UTF8, "position " + std::to_string(bad) + ": invalid UTF-8 in " + path);
+                } else {
+                    u8->offset += text_len;
+                }
+            }
+            t5 = now();
+        }
+        if (!st.advance(r, o, meta, text_len, text_crc))
+            return fail(ctx, TDG_ERR_GZIP, std::string("gzip error in ") + path + ": incorrect data check");
+        if (o.accepted && text_len) {
+            rc = sink.text(ctx, (uint8_t *)ctx->gz_text.p, carry, (size_t)text_len);
+            if (rc) return rc;
+        }
+        auto t6 = now();
+        if (stats) {
+            stats->rounds++;
+            stats->chunks += r.nchunks;
+            stats->accepted += o.accepted;
+            stats->ms_upload += ms(t0, t1);
+            stats->ms_scan += ms(t1, t2);
+            stats->ms_decode += ms(t2, t3);
+            stats->ms_host += ms(t3, t3) + ms(t4, t5);
+            stats->ms_resolve += ms(t3, t4);
+            stats->ms_sink += ms(t5, t6);
+        }
+        if (debug)
+            fprintf(stderr, "gzdev round: %u chunks, %u accepted, %llu bytes of text; upload %.1f scan %.1f decode %.1f windows+resolve %.1f "
+                            "crc/utf8 %.1f sink %.1f ms%s%s\n",
+                    r.nchunks, o.accepted, (unsigned long long)text_len, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5),
+                    ms(t5, t6), st.handover ? "  -> host reader: " : "", st.handover ? st.why : "");
+    }
+    if (st.handover) {
+        ho.active = true;
+        ho.to_zlib = st.to_zlib;
+        ho.pos_bit = st.pos_bit;
+        ho.hist = st.hist;
+        ho.crc = st.crc;
+        ho.member_len = st.member_len;
+        ho.delivered = st.delivered;
+        ho.why = st.why;
+        ho.window.resize(gzl::WIN);
+        CK(cudaMemcpyAsync(ho.window.data(), d_window, gzl::WIN, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return TDG_OK;
+}
+
+// tdg_count_file's sink: whole lines go to the counting kernel, the rest is carried
+struct GzCountSink : GzSink {
+    uint64_t reads_limit;
+    explicit GzCountSink(uint64_t limit) : reads_limit(limit) {}
+    int text(tdg_ctx *ctx, uint8_t *d_buf, size_t &carry, size_t len) override
+    {
+        const size_t total = carry + len;
+        // the last line end: look at the tail on the host
+        size_t cut = 0;
+        for (size_t tail = std::min<size_t>(total, (size_t)1 << 20);; tail = std::min(total, tail * 8)) {
+            int rc = grow(ctx, ctx->gz_htail, tail, true);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(ctx->gz_htail.p, d_buf + (total - tail), tail, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const size_t c = line_cut((const uint8_t *)ctx->gz_htail.p, tail);
+            if (c) { cut = total - tail + c; break; }
+            if (tail == total) break;
+        }
+        if (cut) {
+            int rc = launch_chunk<true>(ctx, d_buf, cut, TDG_LINE_CHAINED, 0, reads_limit);
+            if (rc) return rc;
+        }
+        const size_t rest = total - cut;
+        if (rest && cut) {
+            int rc = grow(ctx, ctx->gz_carry, rest, false);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(ctx->gz_carry.p, d_buf + cut, rest, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(d_buf, ctx->gz_carry.p, rest, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        carry = rest;
+        return TDG_OK;
+    }
+};
+
+// tdg_gz_inflate_host's sink: the text goes to a host buffer
+struct GzCopySink : GzSink {
+    uint8_t *dst;
+    size_t cap, used = 0;
+    GzCopySink(uint8_t *d, size_t c) : dst(d), cap(c) {}
+    int text(tdg_ctx *ctx, uint8_t *d_buf, size_t &carry, size_t len) override
+    {
+        if (used + len > cap) return fail(ctx, TDG_ERR_ARG, "output buffer too small");
+        CK(cudaMemcpyAsync(dst + used, d_buf + carry, len, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        used += len;
+        carry = 0;
+        return TDG_OK;
+    }
+};
+
+bool gz_device_wanted(const char *path, uint64_t reads_limit)
+{
+    if (const char *e = getenv("TDG_GZDEV")) {
+        if (atoi(e) == 0) return false;
+    }
+    if (reads_limit < ((uint64_t)1 << 61)) return false;           // with maxreads the reader stops early: small host pieces
+    uint64_t min_size = (uint64_t)8 << 20;
+    if (const char *e = getenv("TDG_GZDEV_MIN")) min_size = strtoull(e, nullptr, 10);
+    struct stat sb;
+    return stat(path, &sb) == 0 && S_ISREG(sb.st_mode) && (uint64_t)sb.st_size >= min_size;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -599,6 +1010,13 @@ void tdg_destroy(tdg_ctx *ctx)
             if (g->p) cudaFree(g->p);
         for (tdg_ctx::Grow *g : {&ctx->sp_hout, &ctx->sp_hflags, &ctx->sp_hbase})
             if (g->p) cudaFreeHost(g->p);
+        for (tdg_ctx::Grow *g : {&ctx->gz_comp, &ctx->gz_syms, &ctx->gz_meta, &ctx->gz_cand, &ctx->gz_ncand, &ctx->gz_windows,
+                                 &ctx->gz_text, &ctx->gz_crc, &ctx->gz_lens, &ctx->gz_offs, &ctx->gz_tabs, &ctx->gz_carry})
+            if (g->p) cudaFree(g->p);
+        for (tdg_ctx::Grow *g : {&ctx->gz_hmeta, &ctx->gz_hcrc, &ctx->gz_htail})
+            if (g->p) cudaFreeHost(g->p);
+        for (int i = 0; i < 3; i++)
+            if (ctx->gz_up[i]) cudaEventDestroy(ctx->gz_up[i]);
         if (ctx->d_replicas) cudaFree(ctx->d_replicas);
         for (int i = 0; i < 3; i++)
             if (ctx->file_buf[i]) cudaFreeHost(ctx->file_buf[i]);
@@ -1070,10 +1488,48 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     size_t chunk = ctx->chunk_bytes;
     if (limited) chunk = std::min<size_t>(chunk, (size_t)8 << 20);
 
+    // Ordinary gzip files are inflated on the DEVICE (tdg_gzdev.cuh): the compressed bytes cross
+    // PCIe, the text is born in HBM.  Whatever that feed does not take -- BGZF, small files, a read
+    // limit, and the rest of any stream with something unusual in it -- goes through the host
+    // feeder below, which resumes exactly where the device feed stopped.
+    tdg::Utf8State u8;
+    GzHandover ho;
+    if (gz && gz_device_wanted(path, reads_limit)) {
+        bool handled = false;
+        size_t dcarry = 0;
+        GzCountSink sink(reads_limit);
+        int drc = gz_device_feed(ctx, path, sink, handled, ho, dcarry, nullptr, &u8);
+        if (drc == TDG_OK && handled && dcarry) {
+            // the bytes behind the last line end become the host path's carry
+            Slot &cs = ctx->slot[ctx->next_slot];
+            drc = grow_carry(ctx, cs, dcarry, 0);
+            if (drc == TDG_OK) {
+                CK(cudaMemcpyAsync(cs.carry, ctx->gz_text.p, dcarry, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+                ctx->carry_len = dcarry;
+            }
+        }
+        if (drc == TDG_OK && handled && !ho.active) {
+            // the whole file went through the device
+            if (tdg::utf8_finish(u8) >= 0)
+                drc = fail(ctx, TDG_ERR_UTF8, "position " + std::to_string(tdg::utf8_finish(u8)) + ": unexpected end of data in " + path);
+            if (drc == TDG_OK) drc = end_file_impl(ctx, reads_limit);
+        }
+        if (drc != TDG_OK || (handled && !ho.active)) {
+            if (drc != TDG_OK) ctx->carry_len = 0;
+            cudaStreamSynchronize(ctx->copy_stream);
+            cudaStreamSynchronize(ctx->stream);
+            if (drc == TDG_OK && totals) drc = tdg_file_totals(ctx, totals);
+            return drc;
+        }
+    }
+
     std::thread reader([&]() {
         // host feed: parallel pread / parallel BGZF inflate / zlib, see tdg_feed.h
         tdg::Feeder feed;
-        int orc = feed.open(path, gz != 0);
+        int orc = ho.active ? feed.open_resume(path, ho.pos_bit, ho.to_zlib ? nullptr : ho.window.data(), ho.hist, ho.crc, ho.member_len,
+                                               ho.delivered)
+                            : feed.open(path, gz != 0);
         int bi = 0;
         for (;;) {
             Buf &b = bufs[bi];
@@ -1105,7 +1561,6 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
 
     int bi = 0;
     int result = TDG_OK;
-    tdg::Utf8State u8;
     tdg::LineLimit ll;
     // the read with index maxreads-1 is line 4*maxreads-3: everything up to line end number
     // 4*maxreads-2 is needed, nothing beyond it is looked at
@@ -1153,6 +1608,71 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     cudaStreamSynchronize(ctx->stream);
     if (result == TDG_OK && totals) result = tdg_file_totals(ctx, totals);
     return result;
+}
+
+// The device-side gzip feed by itself: inflates `path` into dst (host memory) the way
+// tdg_count_file does -- rounds on the device, the rest, if any, through the host feeder -- and
+// reports what happened.  info[0] rounds, [1] chunks, [2] chunks accepted, [3] 0 all on the device /
+// 1 host reader resumed / 2 zlib / -1 not taken by the device feed at all; ms[0..5]: upload, scan,
+// decode, windows + resolve, CRC fold / UTF-8, sink.
+int tdg_gz_inflate_host(tdg_ctx *ctx, const char *path, void *dst, size_t cap, uint64_t *n_out, int64_t info[4], double ms[6])
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!path || !dst || !n_out) return fail(ctx, TDG_ERR_ARG, "null argument");
+    CK(cudaSetDevice(ctx->device));
+    rc = ensure_slots(ctx);
+    if (rc) return rc;
+    if (ctx->file_buf_cap < ctx->chunk_bytes) {
+        for (int i = 0; i < 3; i++) {
+            if (ctx->file_buf[i]) cudaFreeHost(ctx->file_buf[i]);
+            ctx->file_buf[i] = nullptr;
+        }
+        ctx->file_buf_cap = 0;
+        for (int i = 0; i < 3; i++) CK(cudaHostAlloc(&ctx->file_buf[i], ctx->chunk_bytes, cudaHostAllocDefault));
+        ctx->file_buf_cap = ctx->chunk_bytes;
+    }
+    GzCopySink sink((uint8_t *)dst, cap);
+    GzHandover ho;
+    GzStats st;
+    bool handled = false;
+    size_t carry = 0;
+    rc = gz_device_feed(ctx, path, sink, handled, ho, carry, &st, nullptr);
+    if (rc) return rc;
+    if (info) {
+        info[0] = st.rounds;
+        info[1] = st.chunks;
+        info[2] = st.accepted;
+        info[3] = !handled ? -1 : (!ho.active ? 0 : (ho.to_zlib ? 2 : 1));
+    }
+    if (ms) {
+        ms[0] = st.ms_upload;
+        ms[1] = st.ms_scan;
+        ms[2] = st.ms_decode;
+        ms[3] = st.ms_resolve;
+        ms[4] = st.ms_host;
+        ms[5] = st.ms_sink;
+    }
+    size_t used = sink.used;
+    if (!handled || ho.active) {
+        tdg::Feeder feed;
+        int orc = ho.active ? feed.open_resume(path, ho.pos_bit, ho.to_zlib ? nullptr : ho.window.data(), ho.hist, ho.crc, ho.member_len,
+                                               ho.delivered)
+                            : feed.open(path, true);
+        if (orc) return fail(ctx, orc, feed.error());
+        for (;;) {
+            if (used == cap) return fail(ctx, TDG_ERR_ARG, "output buffer too small");
+            long long r = feed.fill((uint8_t *)dst + used, std::min<size_t>(cap - used, (size_t)64 << 20));
+            if (r < 0) {
+                *n_out = used;
+                return fail(ctx, (int)r, feed.error());
+            }
+            if (r == 0) break;
+            used += (size_t)r;
+        }
+    }
+    *n_out = used;
+    return TDG_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -1321,30 +1841,6 @@ int tdg_split_batch(tdg_ctx *ctx, const char *seqs, const uint64_t *off, uint32_
 
 // ---------------------------------------------------------------------------
 // Streaming barcode splitter, csrc/tdg_split.cuh
-
-namespace {
-
-int grow(tdg_ctx *ctx, tdg_ctx::Grow &g, size_t need, bool host)
-{
-    if (need <= g.cap) return TDG_OK;
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (g.p) {
-        if (g.host) cudaFreeHost(g.p); else cudaFree(g.p);
-        g.p = nullptr;
-        g.cap = 0;
-    }
-    const size_t cap = need + need / 4 + 4096;
-    cudaError_t e = host ? cudaHostAlloc(&g.p, cap, cudaHostAllocDefault) : cudaMalloc(&g.p, cap);
-    if (e != cudaSuccess) {
-        g.p = nullptr;
-        return fail(ctx, TDG_ERR_NOMEM, std::string("splitter buffer of ") + std::to_string(cap) + " bytes: " + cudaGetErrorString(e));
-    }
-    g.cap = cap;
-    g.host = host;
-    return TDG_OK;
-}
-
-}  // namespace
 
 int tdg_split_begin(tdg_ctx *ctx, const char *barcodes, const uint32_t *bar_off, uint32_t nbar, uint32_t cutlen)
 {

@@ -85,6 +85,47 @@ public:
         return 0;
     }
 
+    // Continue a gzip file behind what another inflater (the device feed, tdg_gzdev.cuh) has
+    // delivered: with `window` at the block boundary `pos_bit` (parallel reader), or -- window
+    // null -- with zlib re-reading the file up to the uncompressed offset `delivered`.
+    int open_resume(const char *path, uint64_t pos_bit, const uint8_t *window, size_t hist, uint32_t crc, uint64_t member_len,
+                    uint64_t delivered)
+    {
+        path_ = path;
+        threads_ = 16;
+        if (const char *e = getenv("TDG_IO_THREADS")) threads_ = std::max(1, atoi(e));
+        unsigned hw = std::thread::hardware_concurrency();
+        if (hw && threads_ > (int)hw) threads_ = (int)hw;
+        fd_ = ::open(path, O_RDONLY);
+        if (fd_ < 0) return fail(-3, std::string("cannot open ") + path);
+        struct stat st;
+        if (fstat(fd_, &st) != 0 || !S_ISREG(st.st_mode)) return fail(-3, std::string("not a regular file: ") + path);
+        size_ = (uint64_t)st.st_size;
+        mode_ = GZ;
+        if (window) {
+            size_t pchunk = (size_t)2 << 20;
+            if (const char *e = getenv("TDG_PGZ_CHUNK")) pchunk = (size_t)strtoull(e, nullptr, 10);
+            void *m = mmap(nullptr, (size_t)size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+            if (m != MAP_FAILED) {
+                map_ = (const uint8_t *)m;
+                pgz_.reset(new pgz::Reader());
+                pgz_->resume(map_, (size_t)size_, threads_, pchunk, pos_bit, window, hist, crc, member_len, delivered);
+                mode_ = PGZ;
+                return 0;
+            }
+        }
+        int rc = open_gz(delivered);
+        gz_first_ = false;
+        return rc;
+    }
+
+    // does the file image start with a BGZF member?
+    static bool is_bgzf(const uint8_t *h, size_t n)
+    {
+        uint32_t csize = 0, hlen = 0;
+        return n >= 18 && bgzf_header(h, n, csize, hlen);
+    }
+
     Mode mode() const { return mode_; }
     int threads() const { return threads_; }
     const std::string &error() const { return err_; }

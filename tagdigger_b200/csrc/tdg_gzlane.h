@@ -77,25 +77,30 @@ struct Mem {
     }
 };
 
-// LSB-first bit reader over 32-bit words (the buffer is padded: words past nwords read as zero)
+// LSB-first bit reader over 32-bit words (the buffer is padded: words past nwords read as zero).
+// The word after the ones in the buffer is always on its way already (`ahead`): a lane's refill
+// never waits for memory unless it drains 32 bits faster than a load takes.
 struct Bits {
     const uint32_t *in;
     uint64_t nwords;
-    uint64_t w;               // next word
+    uint64_t w;               // index of the word in `ahead`
     uint64_t buf;
+    uint32_t ahead;
     int cnt;
+    TDG_GZ_HD uint32_t word(uint64_t i) const { return i < nwords ? in[i] : 0u; }
     TDG_GZ_HD void fill()     // afterwards at least 32 bits are in the buffer
     {
         if (cnt <= 32) {
-            const uint32_t x = w < nwords ? in[w] : 0u;
-            w++;
-            buf |= (uint64_t)x << cnt;
+            buf |= (uint64_t)ahead << cnt;
             cnt += 32;
+            w++;
+            ahead = word(w);
         }
     }
     TDG_GZ_HD void seek(uint64_t bit)
     {
         w = bit >> 5;
+        ahead = word(w);
         buf = 0;
         cnt = 0;
         fill();
@@ -199,6 +204,14 @@ TDG_GZ_FN uint32_t decode_long(const Mem<STRIDE> m, uint64_t buf, int root, uint
     return 0;
 }
 
+// A lane as a STATE MACHINE: step() does one small piece of work -- a symbol or two of a Huffman
+// block, 64 bytes of a stored block, a block header, the next candidate -- and returns.  The
+// kernel steps all 32 lanes of a warp in lock step behind a vote, so the lanes stay CONVERGED on
+// the hot path (symbols) however differently their blocks are cut; a lane that runs its whole
+// chunk in one call tree diverges from its neighbours at the first block end and the warp
+// executes one lane at a time from then on (measured: 30 x slower).
+enum : uint32_t { S_CAND = 0, S_HEADER = 1, S_HUFF = 2, S_STORED = 3, S_DONE = 4 };
+
 template <int STRIDE>
 struct Lane {
     Mem<STRIDE> m;
@@ -211,8 +224,79 @@ struct Lane {
     uint32_t hist;            // how far back a distance may reach beyond o (WIN: unknown prehistory)
     uint32_t min_pre;
     bool fixed_loaded;
+    // the job
+    bool known;
+    uint32_t known_hist;
+    uint64_t search_base, stop_bit;
+    const uint32_t *cand;
+    uint32_t ncand, c;
+    // progress
+    uint32_t state;
+    bool probation;           // a candidate start is on trial until its first block is done and the header behind it is sane
+    bool final_block;
+    uint32_t stored_left, blocks_done;
+    uint64_t start, last_bit;
+    uint32_t last_o;
+    Meta *r;
 
     TDG_GZ_HD bool exhausted() const { return bits.pos() > in_bits; }
+
+    TDG_GZ_FN void init(Mem<STRIDE> mem, const uint32_t *in, uint64_t nwords, uint64_t inbits, bool known_start, uint64_t base,
+                        const uint32_t *cands, uint32_t ncands, uint64_t stop, uint32_t history, uint16_t *dst, uint32_t dst_cap,
+                        Meta *report)
+    {
+        m = mem;
+        bits.in = in;
+        bits.nwords = nwords;
+        bits.w = 0;
+        bits.buf = 0;
+        bits.ahead = 0;
+        bits.cnt = 0;
+        in_bits = inbits;
+        wmax = (inbits + 31) / 32 + 2;
+        out = dst;
+        cap = dst_cap;
+        o = 0;
+        hist = WIN;
+        min_pre = WIN;
+        fixed_loaded = false;
+        known = known_start;
+        known_hist = history;
+        search_base = base;
+        stop_bit = stop;
+        cand = cands;
+        ncand = ncands;
+        c = 0;
+        state = S_CAND;
+        probation = false;
+        final_block = false;
+        stored_left = blocks_done = 0;
+        start = last_bit = base;
+        last_o = 0;
+        r = report;
+        r->start_bit = base;
+        r->end_bit = base;
+        r->out_len = 0;
+        r->flags = 0;
+        r->min_pre = WIN;
+        r->tried = 0;
+    }
+
+    TDG_GZ_FN void finish(uint32_t flags)
+    {
+        r->start_bit = start;
+        r->end_bit = last_bit;
+        r->out_len = last_o;
+        r->flags = F_FOUND | flags;
+        r->min_pre = min_pre;
+        state = S_DONE;
+    }
+    // decoding cannot go on: a candidate on trial is dropped, anything else is reported with the last boundary passed
+    TDG_GZ_FN void fail(uint32_t why)
+    {
+        if (probation) state = S_CAND;
+        else finish(why);
+    }
 
     TDG_GZ_FN bool load_fixed()
     {
@@ -281,143 +365,260 @@ struct Lane {
         return true;
     }
 
-    // The symbols of one Huffman block up to its end-of-block code.  0 done, else F_ERROR / F_SPACE / F_INPUT.
-    TDG_GZ_FN uint32_t huff_block()
+    TDG_GZ_FN void block_end()
     {
-        for (;;) {
-            if (o + 260 > cap) return F_SPACE;
-            if (bits.w > wmax) return F_INPUT;
-            bits.fill();
-            uint32_t e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << LIT_ROOT) - 1u)));
-            if (e & E_LONG) e = decode_long<STRIDE>(m, bits.buf, LIT_ROOT, O_LSORT, O_LCNT);
-            if (e == 0) return F_ERROR;
-            bits.drop((int)(e & 15u));
-            uint32_t sym = e >> 4;
-            if (sym < 256) {
-                out[o++] = (uint16_t)sym;
-                // a second literal without another fill (at least 17 bits are left)
-                e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << LIT_ROOT) - 1u)));
-                if (e == 0 || e >= (256u << 4)) continue;   // not a short literal code: the next round looks again
-                bits.drop((int)(e & 15u));
-                out[o++] = (uint16_t)(e >> 4);
-                continue;
-            }
-            if (sym == 256) return exhausted() ? F_INPUT : 0;
-            if (sym > 285) return F_ERROR;
-            uint32_t len;
-            {
-                const uint32_t idx = sym - 257;
-                if (idx < 8) len = 3 + idx;
-                else if (idx == 28) len = 258;
-                else {
-                    const int eb = (int)((idx - 4) >> 2);
-                    len = 3 + ((4 + (idx & 3u)) << eb) + bits.take(eb);
-                }
-            }
-            bits.fill();
-            uint32_t f = m.h(O_DIST + ((uint32_t)bits.buf & ((1u << DIST_ROOT) - 1u)));
-            if (f & E_LONG) f = decode_long<STRIDE>(m, bits.buf, DIST_ROOT, O_DSORT, O_DCNT);
-            if (f == 0) return F_ERROR;
-            bits.drop((int)(f & 15u));
-            const uint32_t ds = f >> 4;
-            if (ds > 29) return F_ERROR;
-            uint32_t d;
-            if (ds < 4) d = 1 + ds;
-            else {
-                const int eb = (int)(ds >> 1) - 1;
-                d = 1 + ((2 + (ds & 1u)) << eb) + bits.take(eb);
-            }
-            if (d > o) {
-                if (d - o > hist) return F_ERROR;           // too far back
-                const uint32_t pre = WIN - (d - o);
-                if (pre < min_pre) min_pre = pre;
-            }
-            // symbol j of the stream seen from this chunk: j < 0 is prehistory -> marker 256 + (WIN + j)
-            int32_t j = (int32_t)o - (int32_t)d;
-            for (uint32_t k = 0; k < len; k++, j++) out[o + k] = j < 0 ? (uint16_t)(256 + WIN + j) : out[j];
-            o += len;
+        if (exhausted()) {
+            fail(F_INPUT);
+            return;
         }
-    }
-
-    // Inflates blocks until a block boundary at or beyond stop_bit.  Returns 0 (stopped at the
-    // boundary), F_FINAL (behind a member's last block), or the reason decoding could not go on;
-    // last_bit / last_o are the last boundary passed.
-    TDG_GZ_FN uint32_t run(uint64_t stop_bit, uint64_t &last_bit, uint32_t &last_o, bool one_block)
-    {
-        for (;;) {
-            const uint64_t bp = bits.pos();
-            last_bit = bp;
+        blocks_done++;
+        if (final_block) {
+            last_bit = bits.pos();
             last_o = o;
-            if (bp >= stop_bit) return 0;
-            if (bp + 3 > in_bits) return F_INPUT;
+            finish(F_FINAL);
+            return;
+        }
+        state = S_HEADER;
+    }
+
+    // S_CAND: the next place to start from
+    TDG_GZ_FN void step_cand()
+    {
+        if (known) {
+            if (c++) {                                       // (a known start is never on trial: this is not reached)
+                state = S_DONE;
+                return;
+            }
+            start = search_base;
+            hist = known_hist;
+            probation = false;
+        } else {
+            if (c >= ncand) {                                // nothing held: F_FOUND stays clear
+                state = S_DONE;
+                return;
+            }
+            start = search_base + cand[c++];
+            r->tried = c;
+            hist = WIN;
+            probation = true;
+        }
+        bits.seek(start);
+        o = 0;
+        min_pre = WIN;
+        fixed_loaded = false;
+        blocks_done = 0;
+        state = S_HEADER;
+    }
+
+    // S_HEADER: at a block boundary.  A lane stops at the first boundary at or behind stop_bit that
+    // the NEXT lane's scan can find: one in front of a non-final dynamic block.
+    TDG_GZ_FN void step_header()
+    {
+        const uint64_t bp = bits.pos();
+        last_bit = bp;
+        last_o = o;
+        if (bp + 3 > in_bits) {
+            fail(F_INPUT);
+            return;
+        }
+        bits.fill();
+        const uint32_t h = bits.take(3);
+        const uint32_t type = h >> 1;
+        final_block = (h & 1u) != 0;
+        if (type == 3) {
+            fail(F_ERROR);
+            return;
+        }
+        if (type == 2) {
+            const bool at_stop = bp >= stop_bit && !final_block;
+            if (at_stop && !probation) {
+                finish(0);
+                return;
+            }
+            if (!read_dynamic()) {
+                fail(exhausted() ? F_INPUT : F_ERROR);
+                return;
+            }
+            if (blocks_done) probation = false;              // the header behind the first block is sane
+            if (at_stop) {
+                finish(0);
+                return;
+            }
+            state = S_HUFF;
+            return;
+        }
+        if (type == 1) {
+            if (!fixed_loaded) {
+                if (!load_fixed()) {
+                    fail(F_ERROR);
+                    return;
+                }
+                fixed_loaded = true;
+            }
+            if (blocks_done) probation = false;
+            state = S_HUFF;
+            return;
+        }
+        bits.drop(bits.cnt & 7);
+        bits.fill();
+        const uint32_t len = bits.take(16);
+        bits.fill();
+        const uint32_t nlen = bits.take(16);
+        if ((len ^ 0xffffu) != nlen) {
+            fail(F_ERROR);
+            return;
+        }
+        if (bits.pos() + (uint64_t)len * 8 > in_bits) {
+            fail(F_INPUT);
+            return;
+        }
+        if (o + len + 260 > cap) {
+            fail(F_SPACE);
+            return;
+        }
+        if (blocks_done) probation = false;
+        stored_left = len;
+        state = S_STORED;
+    }
+
+    TDG_GZ_FN void step_stored()
+    {
+        uint32_t n = stored_left < 64 ? stored_left : 64;
+        stored_left -= n;
+        while (n--) {
             bits.fill();
-            const uint32_t h = bits.take(3);
-            const uint32_t type = h >> 1;
-            if (type == 0) {
-                bits.drop(bits.cnt & 7);
-                bits.fill();
-                const uint32_t len = bits.take(16);
-                bits.fill();
-                const uint32_t nlen = bits.take(16);
-                if ((len ^ 0xffffu) != nlen) return F_ERROR;
-                if (bits.pos() + (uint64_t)len * 8 > in_bits) return F_INPUT;
-                if (o + len + 260 > cap) return F_SPACE;
-                for (uint32_t k = 0; k < len; k++) {
-                    bits.fill();
-                    out[o++] = (uint16_t)bits.take(8);
-                }
-            } else if (type == 3) {
-                return F_ERROR;
-            } else {
-                if (type == 1) {
-                    if (!fixed_loaded) {
-                        if (!load_fixed()) return F_ERROR;
-                        fixed_loaded = true;
-                    }
-                } else if (!read_dynamic()) {
-                    return exhausted() ? F_INPUT : F_ERROR;
-                }
-                const uint32_t r = huff_block();
-                if (r) return r;
+            out[o++] = (uint16_t)bits.take(8);
+        }
+        if (stored_left == 0) block_end();
+    }
+
+    // S_HUFF: one literal/length symbol (and a second literal when it is there for the taking), or a whole match
+    TDG_GZ_FN void step_huff()
+    {
+        if (o + 260 > cap) {
+            fail(F_SPACE);
+            return;
+        }
+        if (bits.w > wmax) {
+            fail(F_INPUT);
+            return;
+        }
+        bits.fill();
+        uint32_t e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << LIT_ROOT) - 1u)));
+        if (e & E_LONG) e = decode_long<STRIDE>(m, bits.buf, LIT_ROOT, O_LSORT, O_LCNT);
+        if (e == 0) {
+            fail(F_ERROR);
+            return;
+        }
+        bits.drop((int)(e & 15u));
+        const uint32_t sym = e >> 4;
+        if (sym < 256) {
+            out[o++] = (uint16_t)sym;
+            // a second literal without another fill (at least 17 bits are left)
+            e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << LIT_ROOT) - 1u)));
+            if (e == 0 || e >= (256u << 4)) return;          // not a short literal code: the next step looks again
+            bits.drop((int)(e & 15u));
+            out[o++] = (uint16_t)(e >> 4);
+            return;
+        }
+        if (sym == 256) {
+            block_end();
+            return;
+        }
+        if (sym > 285) {
+            fail(F_ERROR);
+            return;
+        }
+        uint32_t len;
+        {
+            const uint32_t idx = sym - 257;
+            if (idx < 8) len = 3 + idx;
+            else if (idx == 28) len = 258;
+            else {
+                const int eb = (int)((idx - 4) >> 2);
+                len = 3 + ((4 + (idx & 3u)) << eb) + bits.take(eb);
             }
-            if (h & 1u) {
-                last_bit = bits.pos();
-                last_o = o;
-                return F_FINAL;
+        }
+        bits.fill();
+        uint32_t f = m.h(O_DIST + ((uint32_t)bits.buf & ((1u << DIST_ROOT) - 1u)));
+        if (f & E_LONG) f = decode_long<STRIDE>(m, bits.buf, DIST_ROOT, O_DSORT, O_DCNT);
+        if (f == 0) {
+            fail(F_ERROR);
+            return;
+        }
+        bits.drop((int)(f & 15u));
+        const uint32_t ds = f >> 4;
+        if (ds > 29) {
+            fail(F_ERROR);
+            return;
+        }
+        uint32_t d;
+        if (ds < 4) d = 1 + ds;
+        else {
+            const int eb = (int)(ds >> 1) - 1;
+            d = 1 + ((2 + (ds & 1u)) << eb) + bits.take(eb);
+        }
+        if (d > o) {
+            if (d - o > hist) {                              // too far back
+                fail(F_ERROR);
+                return;
             }
-            if (one_block) {
-                last_bit = bits.pos();
-                last_o = o;
-                return 0;
+            const uint32_t pre = WIN - (d - o);
+            if (pre < min_pre) min_pre = pre;
+        }
+        copy_match(len, d);
+    }
+
+    // out[o .. o + len) = the len symbols that start d symbols back.  Symbol j of the stream seen
+    // from this chunk: j < 0 is prehistory -> marker 256 + (WIN + j).  Sources are read eight at a
+    // time before anything is written (a lane's load-store-load chain through L2 is what a
+    // symbol-by-symbol copy costs); a distance below eight repeats a pattern held in registers.
+    TDG_GZ_HD uint16_t sym_at(int32_t j) const { return j < 0 ? (uint16_t)(256 + WIN + j) : out[j]; }
+    TDG_GZ_FN void copy_match(uint32_t len, uint32_t d)
+    {
+        int32_t j = (int32_t)o - (int32_t)d;
+        uint16_t *q = out + o;
+        o += len;
+        if (d >= 8) {
+            while (len >= 8) {
+                const uint16_t a0 = sym_at(j), a1 = sym_at(j + 1), a2 = sym_at(j + 2), a3 = sym_at(j + 3), a4 = sym_at(j + 4),
+                               a5 = sym_at(j + 5), a6 = sym_at(j + 6), a7 = sym_at(j + 7);
+                q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3; q[4] = a4; q[5] = a5; q[6] = a6; q[7] = a7;
+                q += 8;
+                j += 8;
+                len -= 8;
             }
+            uint16_t a[7];
+#pragma unroll
+            for (uint32_t k = 0; k < 7; k++) a[k] = k < len ? sym_at(j + (int32_t)k) : (uint16_t)0;
+#pragma unroll
+            for (uint32_t k = 0; k < 7; k++)
+                if (k < len) q[k] = a[k];
+            return;
+        }
+        // the d symbols of the pattern, packed 16 bits each
+        uint64_t lo = 0, hi = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 7; k++) {
+            if (k < d) {
+                const uint64_t v = sym_at(j + (int32_t)k);
+                if (k < 4) lo |= v << (16 * k);
+                else hi |= v << (16 * (k - 4));
+            }
+        }
+        uint32_t t = 0;
+        for (uint32_t k = 0; k < len; k++) {
+            q[k] = (uint16_t)(t < 4 ? lo >> (16 * t) : hi >> (16 * (t - 4)));
+            if (++t == d) t = 0;
         }
     }
 
-    // Is the header at the reader's position (a copy of the reader is used) at least sane?
-    TDG_GZ_FN bool next_header_sane()
+    TDG_GZ_FN void step()
     {
-        const Bits save = bits;
-        bool ok = true;
-        if (bits.pos() + 3 > in_bits) ok = false;
-        else {
-            bits.fill();
-            const uint32_t h = bits.take(3);
-            if ((h >> 1) == 3) ok = false;
-            else if ((h >> 1) == 0) {
-                bits.drop(bits.cnt & 7);
-                bits.fill();
-                const uint32_t len = bits.take(16);
-                bits.fill();
-                const uint32_t nlen = bits.take(16);
-                ok = (len ^ 0xffffu) == nlen;
-            } else if ((h >> 1) == 2) {
-                ok = read_dynamic();
-                fixed_loaded = false;
-            }
-            if (exhausted()) ok = false;
-        }
-        bits = save;
-        return ok;
+        if (state == S_HUFF) step_huff();
+        else if (state == S_STORED) step_stored();
+        else if (state == S_HEADER) step_header();
+        else if (state == S_CAND) step_cand();
     }
 };
 
@@ -456,72 +657,29 @@ template <int STRIDE>
 TDG_GZ_FN bool header_parses(Mem<STRIDE> m, const uint32_t *in, uint64_t nwords, uint64_t in_bits, uint64_t bit)
 {
     Lane<STRIDE> z;
-    z.m = m;
-    z.bits.in = in;
-    z.bits.nwords = nwords;
-    z.in_bits = in_bits;
-    z.wmax = (in_bits + 31) / 32 + 2;
-    z.fixed_loaded = false;
+    Meta dummy;
+    z.init(m, in, nwords, in_bits, true, bit, nullptr, 0, 0, 0, nullptr, 0, &dummy);
     z.bits.seek(bit);
     z.bits.fill();
     z.bits.drop(3);
     return z.read_dynamic();
 }
 
-// A lane's whole job for its chunk: try the candidate block starts `cand[0..ncand)` (bit offsets
-// from search_base, ascending; positions where the scan kernel saw a dynamic block header parse) until one holds -- its header parses,
-// its first block decodes and the header behind that block is sane -- then inflate up to the block
-// boundary at or beyond stop_bit.  `known`: start exactly at search_base with `hist` bytes of real
-// history (the first chunk of a round); nothing is tried, every defect is real.
-// Bit positions are relative to the buffer (`in`); the caller adds the buffer's place in the file.
+// A lane's whole job for its chunk, one call (the CPU harness; the kernel steps its lanes itself):
+// try the candidate block starts `cand[0..ncand)` (bit offsets from search_base, ascending;
+// positions where the scan saw a dynamic block header parse) until one holds -- its first block
+// decodes and the header behind that block is sane -- then inflate up to the block boundary at or
+// beyond stop_bit that stands in front of a non-final dynamic block.  `known`: start exactly at
+// search_base with `hist` bytes of real history (the first chunk of a round); nothing is tried,
+// every defect is real.  Bit positions are relative to the buffer (`in`).
 template <int STRIDE>
 TDG_GZ_FN void run_chunk(Mem<STRIDE> m, const uint32_t *in, uint64_t nwords, uint64_t in_bits, bool known, uint64_t search_base,
                          const uint32_t *cand, uint32_t ncand, uint64_t stop_bit, uint32_t hist, uint16_t *out, uint32_t cap,
                          Meta &r)
 {
     Lane<STRIDE> z;
-    z.m = m;
-    z.bits.in = in;
-    z.bits.nwords = nwords;
-    z.in_bits = in_bits;
-    z.wmax = (in_bits + 31) / 32 + 2;
-    z.out = out;
-    z.cap = cap;
-    r.start_bit = search_base;
-    r.end_bit = search_base;
-    r.out_len = 0;
-    r.flags = 0;
-    r.min_pre = WIN;
-    r.tried = 0;
-    uint64_t last_bit = 0;
-    uint32_t last_o = 0;
-    uint32_t c = 0;
-    for (;;) {
-        uint64_t start;
-        if (known) start = search_base;
-        else {
-            if (c >= ncand) return;                          // nothing held: F_FOUND stays clear
-            start = search_base + cand[c++];
-            r.tried = c;
-        }
-        z.bits.seek(start);
-        z.o = 0;
-        z.hist = known ? hist : WIN;
-        z.min_pre = WIN;
-        z.fixed_loaded = false;
-        if (!known) {
-            // exactly one block, then a look at the next header
-            const uint32_t s = z.run(~0ull, last_bit, last_o, true);
-            if (s != 0 || !z.next_header_sane()) continue;
-        }
-        const uint32_t s = z.run(stop_bit, last_bit, last_o, false);
-        r.start_bit = start;
-        r.end_bit = last_bit;
-        r.out_len = last_o;
-        r.flags = F_FOUND | s;
-        r.min_pre = z.min_pre;
-        return;
-    }
+    z.init(m, in, nwords, in_bits, known, search_base, cand, ncand, stop_bit, hist, out, cap, &r);
+    while (z.state != S_DONE) z.step();
 }
 
 }  // namespace gzl
