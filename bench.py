@@ -257,8 +257,9 @@ def write_gzip_parallel(src, dst, level=6, piece=32 << 20):
 
 def file_legs(args, eng, gen, bcs, tags, plan, local):
     """File -> count matrix on the host through tdg_count_file (the call find_tags_fastq makes): a plain
-    FASTQ file and a single-member gzip file of the workload's shape, read from the page cache by the
-    library's host feed (parallel pread / speculative parallel inflate), H2D and counting overlapped."""
+    FASTQ file (parallel pread into pinned buffers, H2D and counting overlapped) and a single-member
+    gzip file of the workload's shape, read from the page cache -- inflated on the device (the
+    library's default: the compressed bytes cross PCIe) and, for comparison, by the host threads."""
     import shutil
     import tempfile
     from oracle import c_oracle
@@ -283,9 +284,15 @@ def file_legs(args, eng, gen, bcs, tags, plan, local):
         out["gzip_bytes"] = os.path.getsize(gz)
         out["gzip_made_in_s"] = round(time.perf_counter() - t0, 1)
         eng.set_matrix(plan.barnum, plan.ntags)
-        for name, path, isgz in (("plain", plain, False), ("gzip", gz, True)):
+        for name, path, isgz in (("plain", plain, False), ("gzip", gz, True), ("gzip_host_feed", gz, True)):
+            # "gzip": the library's default -- the deflate stream is inflated on the DEVICE (csrc/tdg_gzdev.cuh);
+            # "gzip_host_feed": the same file with TDG_GZDEV=0, inflated by the host threads (csrc/tdg_pgz.h)
+            if name == "gzip_host_feed":
+                os.environ["TDG_GZDEV"] = "0"
+            else:
+                os.environ.pop("TDG_GZDEV", None)
             best = None
-            for rep in range(3):
+            for rep in range(3 if name != "gzip_host_feed" else 2):
                 eng.zero_matrix()
                 eng.reset_file()
                 t0 = time.perf_counter()
@@ -296,6 +303,7 @@ def file_legs(args, eng, gen, bcs, tags, plan, local):
             same = bool((got == want).all()) and tot[:3] == wtot
             out[name] = {"reads_per_s": round(nreads / best, 1), "text_GBps": round(nbytes / best / 1e9, 2),
                          "seconds": round(best, 3), "exact_vs_c_oracle": "ok" if same else "FAILED"}
+        os.environ.pop("TDG_GZDEV", None)
     finally:
         shutil.rmtree(tmpdir, ignore_errors=True)
     return out

@@ -119,7 +119,7 @@ struct tdg_ctx {
     size_t file_buf_cap = 0;
 
     // device-side gzip feed (tdg_gzdev.cuh): growable buffers, kept between files
-    Grow gz_comp, gz_syms, gz_meta, gz_cand, gz_ncand, gz_windows, gz_text, gz_crc, gz_lens, gz_offs, gz_tabs, gz_carry;   // device
+    Grow gz_comp, gz_syms, gz_meta, gz_cand, gz_ncand, gz_windows, gz_text, gz_crc, gz_lens, gz_offs, gz_tabs, gz_carry, gz_cold;   // device
     Grow gz_hmeta, gz_hcrc, gz_htail;                                                                                       // pinned host
     cudaEvent_t gz_up[3] = {nullptr, nullptr, nullptr};
     bool gz_tables = false;
@@ -621,7 +621,6 @@ int gz_tables(tdg_ctx *ctx)
     for (int j = 0; j < 8; j++) ctx->gz_op[j] = (uint32_t)crc32_combine_gen((z_off_t)(tdg::gzd::SUB << j));
     for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&ctx->gz_up[i], cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(tdg::gzd::gz_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tdg::gzd::DEC_SMEM));
-    CK(cudaFuncSetAttribute(tdg::gzd::gz_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * tdg::gzl::WIN)));
     ctx->gz_tables = true;
     return TDG_OK;
 }
@@ -662,12 +661,16 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
     rc = ensure_slots(ctx);
     if (rc) return rc;
 
-    size_t chunk = (size_t)128 << 10;
-    if (const char *e = getenv("TDG_GZDEV_CHUNK")) chunk = std::max<size_t>(4096, strtoull(e, nullptr, 10) / 16 * 16);
-    uint32_t symcap = (uint32_t)(8 * chunk);
-    if (const char *e = getenv("TDG_GZDEV_SYMCAP")) symcap = (uint32_t)std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
-    uint32_t max_chunks = (uint32_t)ctx->sm_count * gzd::DEC_THREADS;
+    uint32_t max_chunks = (uint32_t)ctx->sm_count * gzd::DEC_THREADS;          // one lane per chunk, one CTA per SM
     if (const char *e = getenv("TDG_GZDEV_MAXCHUNKS")) max_chunks = (uint32_t)std::max(1, atoi(e));
+    max_chunks = std::min<uint32_t>(max_chunks, 65000);             // gz_ptr_*: a chunk index has 16 bits
+    // chunk size: every lane gets work when the file is large enough, in steps of 16 KiB between 32 and 128 KiB
+    // (a chunk should hold a block start: zlib's blocks are 10 - 30 KB of compressed data)
+    size_t chunk = round_up((map.n + max_chunks - 1) / max_chunks, (size_t)16 << 10);
+    chunk = std::min<size_t>(std::max<size_t>(chunk, (size_t)32 << 10), (size_t)128 << 10);
+    if (const char *e = getenv("TDG_GZDEV_CHUNK")) chunk = std::max<size_t>(4096, strtoull(e, nullptr, 10) / 16 * 16);
+    uint32_t symcap = (uint32_t)std::max<size_t>(8 * chunk, (size_t)256 << 10);     // symbols a lane may write: 8 x its chunk, and room for a large block
+    if (const char *e = getenv("TDG_GZDEV_SYMCAP")) symcap = (uint32_t)std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
     const bool debug = getenv("TDG_GZDEV_DEBUG") != nullptr;
     const int threads = gz_io_threads();
     uint8_t *d_tabs = (uint8_t *)ctx->gz_tabs.p;
@@ -706,6 +709,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         if ((rc = grow(ctx, ctx->gz_cand, (size_t)r.nchunks * gzd::MAXC * 4, false))) return rc;
         if ((rc = grow(ctx, ctx->gz_ncand, (size_t)r.nchunks * 4, false))) return rc;
         if ((rc = grow(ctx, ctx->gz_hmeta, (size_t)r.nchunks * sizeof(gzl::Meta), true))) return rc;
+        if ((rc = grow(ctx, ctx->gz_cold, (size_t)(r.nchunks + 8) * gzl::COLD_U16 * 2, false))) return rc;
         if (debug) CK(cudaStreamSynchronize(ctx->stream));
         auto t1 = now();
         // ---- scan + decode
@@ -725,6 +729,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         a.syms = (uint16_t *)ctx->gz_syms.p;
         a.meta = (gzl::Meta *)ctx->gz_meta.p;
         a.kraft3 = d_tabs;
+        a.cold = (uint16_t *)ctx->gz_cold.p;
         CK(cudaMemsetAsync(ctx->gz_ncand.p, 0, (size_t)r.nchunks * 4, ctx->stream));
         if (r.nchunks > 1) {
             const unsigned g = (r.nchunks - 1 + gzd::SCAN_WARPS - 1) / gzd::SCAN_WARPS;
@@ -748,7 +753,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         auto t4 = t3, t5 = t3;
         if (o.accepted && text_len) {
             const uint32_t pieces = (uint32_t)((text_len + gzd::PIECE - 1) / gzd::PIECE);
-            if ((rc = grow(ctx, ctx->gz_windows, ((size_t)o.accepted + 1) * gzl::WIN, false))) return rc;
+            if ((rc = grow(ctx, ctx->gz_windows, ((size_t)o.accepted + 1) * (gzl::WIN * 4 + 1), false))) return rc;
             if ((rc = grow(ctx, ctx->gz_lens, (size_t)o.accepted * 4, false))) return rc;
             if ((rc = grow(ctx, ctx->gz_offs, ((size_t)o.accepted + 1) * 8, false))) return rc;
             if ((rc = grow(ctx, ctx->gz_crc, (size_t)pieces * 4 + 16, false))) return rc;
@@ -763,22 +768,27 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
                 if ((rc = grow(ctx, ctx->gz_text, need, false))) return rc;
                 if (carry) CK(cudaMemcpyAsync(ctx->gz_text.p, ctx->gz_carry.p, carry, cudaMemcpyDeviceToDevice, ctx->stream));
             }
-            std::vector<uint32_t> lens(o.accepted);
-            for (uint32_t k = 0; k < o.accepted; k++) lens[k] = meta[k].out_len;
-            CK(cudaMemcpyAsync(ctx->gz_lens.p, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->gz_lens.p, o.lens.data(), o.lens.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
             CK(cudaMemcpyAsync(ctx->gz_offs.p, o.text_off.data(), o.text_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->gz_windows.p, d_window, gzl::WIN, cudaMemcpyDeviceToDevice, ctx->stream));
             gzd::WinArgs w;
             w.syms = a.syms;
             w.symcap = symcap;
             w.out_len = (const uint32_t *)ctx->gz_lens.p;
             w.accepted = o.accepted;
-            w.windows = (uint8_t *)ctx->gz_windows.p;
-            gzd::gz_windows<<<1, gzd::WIN_THREADS, 2 * gzl::WIN, ctx->stream>>>(w);
+            w.window_in = d_window;
+            w.ptrs = (uint32_t *)ctx->gz_windows.p;
+            w.done = (uint8_t *)ctx->gz_windows.p + ((size_t)o.accepted + 1) * gzl::WIN * 4;
+            w.window_out = d_window;
+            gzd::gz_ptr_init<<<o.accepted + 1, gzd::WIN_THREADS, 0, ctx->stream>>>(w);
             CK(cudaGetLastError());
+            uint32_t passes = 1;
+            while ((1u << (passes - 1)) < o.accepted + 1) passes++;          // chains are at most accepted + 1 long
+            for (uint32_t ps = 0; ps < passes; ps++) gzd::gz_ptr_jump<<<o.accepted, gzd::WIN_THREADS, 0, ctx->stream>>>(w);
+            CK(cudaGetLastError());
+            ctx->launches += 1 + passes;
             if (debug) {
                 CK(cudaStreamSynchronize(ctx->stream));
-                fprintf(stderr, "gzdev windows: %.1f ms\n", ms(t3, now()));
+                fprintf(stderr, "gzdev windows: %u passes, %.1f ms\n", passes, ms(t3, now()));
             }
             uint32_t *d_flag = (uint32_t *)ctx->gz_crc.p + pieces;
             CK(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
@@ -787,7 +797,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             ra.symcap = symcap;
             ra.text_off = (const uint64_t *)ctx->gz_offs.p;
             ra.accepted = o.accepted;
-            ra.windows = (const uint8_t *)ctx->gz_windows.p;
+            ra.ptrs = (const uint32_t *)ctx->gz_windows.p;
             ra.text = (uint8_t *)ctx->gz_text.p + carry;
             ra.text_len = text_len;
             ra.crc = (uint32_t *)ctx->gz_crc.p;
@@ -796,10 +806,10 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             for (int j = 0; j < 8; j++) ra.op[j] = ctx->gz_op[j];
             gzd::gz_resolve<<<pieces, gzd::RES_THREADS, 0, ctx->stream>>>(ra);
             CK(cudaGetLastError());
-            ctx->launches += 2;
             // the window behind the last accepted chunk opens the next round
-            CK(cudaMemcpyAsync(d_window, (uint8_t *)ctx->gz_windows.p + (size_t)o.accepted * gzl::WIN, gzl::WIN, cudaMemcpyDeviceToDevice,
-                               ctx->stream));
+            gzd::gz_ptr_take<<<8, gzd::WIN_THREADS, 0, ctx->stream>>>(w);
+            CK(cudaGetLastError());
+            ctx->launches += 2;
             uint32_t *hcrc = (uint32_t *)ctx->gz_hcrc.p;
             CK(cudaMemcpyAsync(hcrc, ctx->gz_crc.p, (size_t)pieces * 4 + 4, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
@@ -824,7 +834,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             }
             t5 = now();
         }
-        if (!st.advance(r, o, meta, text_len, text_crc))
+        if (!st.advance(r, o, text_len, text_crc))
             return fail(ctx, TDG_ERR_GZIP, std::string("gzip error in ") + path + ": incorrect data check");
         if (o.accepted && text_len) {
             rc = sink.text(ctx, (uint8_t *)ctx->gz_text.p, carry, (size_t)text_len);
@@ -1011,7 +1021,7 @@ void tdg_destroy(tdg_ctx *ctx)
         for (tdg_ctx::Grow *g : {&ctx->sp_hout, &ctx->sp_hflags, &ctx->sp_hbase})
             if (g->p) cudaFreeHost(g->p);
         for (tdg_ctx::Grow *g : {&ctx->gz_comp, &ctx->gz_syms, &ctx->gz_meta, &ctx->gz_cand, &ctx->gz_ncand, &ctx->gz_windows,
-                                 &ctx->gz_text, &ctx->gz_crc, &ctx->gz_lens, &ctx->gz_offs, &ctx->gz_tabs, &ctx->gz_carry})
+                                 &ctx->gz_text, &ctx->gz_crc, &ctx->gz_lens, &ctx->gz_offs, &ctx->gz_tabs, &ctx->gz_carry, &ctx->gz_cold})
             if (g->p) cudaFree(g->p);
         for (tdg_ctx::Grow *g : {&ctx->gz_hmeta, &ctx->gz_hcrc, &ctx->gz_htail})
             if (g->p) cudaFreeHost(g->p);

@@ -42,6 +42,8 @@ struct Round {
 struct Outcome {
     uint32_t accepted = 0;             // chunks 0..accepted-1 continue the stream
     std::vector<uint64_t> text_off;    // [accepted + 1] offsets of their bytes in the round's text
+    std::vector<uint32_t> lens;        // [accepted] symbols each of them contributes (0: the lane before ran through the whole chunk)
+    uint64_t end_bit = 0;              // where the last of them stopped
     bool member_end = false;           // the last accepted chunk ends a member (trailer follows at end_bit)
     bool handover = false;             // the host reader must take over behind the accepted chunks
     const char *why = "";
@@ -95,8 +97,16 @@ struct Stream {
         o.text_off.push_back(0);
         uint64_t pos = r.pos_bit;
         uint64_t h = r.hist;
+        o.end_bit = pos;
         for (uint32_t k = 0; k < r.nchunks; k++) {
             const gzl::Meta &c = meta[k];
+            if (k > 0 && pos >= r.nominal(k + 1, size)) {
+                // no block starts inside this chunk: the lane before it went through all of it
+                o.accepted = k + 1;
+                o.text_off.push_back(o.text_off.back());
+                o.lens.push_back(0);
+                continue;
+            }
             if (!(c.flags & gzl::F_FOUND)) break;
             if (c.start_bit != pos) break;
             if (k > 0 && c.min_pre < gzl::WIN - std::min<uint64_t>(gzl::WIN, h)) {
@@ -121,7 +131,9 @@ struct Stream {
             }
             o.accepted = k + 1;
             o.text_off.push_back(o.text_off.back() + c.out_len);
+            o.lens.push_back(c.out_len);
             pos = c.end_bit;
+            o.end_bit = pos;
             h += c.out_len;
             if (c.flags & gzl::F_FINAL) {
                 o.member_end = true;
@@ -149,14 +161,14 @@ struct Stream {
 
     // The accepted chunks' bytes (text_len of them, CRC-32 text_crc) are part of the file: move on.
     // Returns false when a member's trailer does not match (crc / length).
-    bool advance(const Round &r, const Outcome &o, const gzl::Meta *meta, uint64_t text_len, uint32_t text_crc)
+    bool advance(const Round &r, const Outcome &o, uint64_t text_len, uint32_t text_crc)
     {
         if (o.accepted) {
             if (text_len) crc = (uint32_t)crc32_combine(crc, text_crc, (z_off_t)text_len);
             member_len += text_len;
             delivered += text_len;
             hist = (uint32_t)std::min<uint64_t>(gzl::WIN, (uint64_t)hist + text_len);
-            pos_bit = meta[o.accepted - 1].end_bit;
+            pos_bit = o.end_bit;
             // poor rounds: the lanes found little to do (huge blocks, stored data ...)
             const uint64_t span = pos_bit - r.pos_bit, want = r.nominal(r.nchunks, size) - r.pos_bit;
             if (!o.member_end && r.nchunks >= 8 && span * 4 < want) poor_rounds++;

@@ -13,11 +13,12 @@
 //               the block boundary at or behind the next chunk's nominal offset, and reports
 //               where it started and stopped.  A lane is a state machine and the 32 lanes of a
 //               warp take their steps together behind a vote, so they stay converged on the
-//               symbol path however their blocks are cut.  Two warps per SM: a lane's tables take
-//               3.5 KB of shared memory, interleaved with those of the other lanes of its warp;
+//               symbol path however their blocks are cut.  Four warps per SM: a lane's hot tables take
+//               1.7 KB of shared memory, interleaved with those of the other lanes of its warp;
 //   (host)      the chain decides which chunks continue the stream (tdg_gzchain.h);
-//   gz_windows  one CTA hands the last 32 KiB from accepted chunk to accepted chunk, resolving
-//               markers against the window before (shared memory, 32 symbols per thread);
+//   gz_ptr_*    the 32 KiB in front of every accepted chunk, all chunks at once: every entry is a
+//               byte or a pointer into the window before, and log2(chunks) passes of pointer
+//               jumping leave bytes only;
 //   gz_resolve  every accepted symbol becomes its byte at its place in the round's text; the CTA
 //               of a 16 KiB piece also takes the piece's raw CRC-32 (64 bytes per thread, then a
 //               tree of carry-less multiplications by x^(8 * 64 * 2^j)) and notes whether any byte
@@ -33,7 +34,10 @@
 namespace tdg {
 namespace gzd {
 
-constexpr int DEC_THREADS = 64;                      // lanes (= chunks) per CTA of gz_decode: two warps
+#ifndef TDG_GZ_WARPS
+#define TDG_GZ_WARPS 4
+#endif
+constexpr int DEC_THREADS = 32 * TDG_GZ_WARPS;       // lanes (= chunks) per CTA of gz_decode, one CTA per SM
 constexpr size_t DEC_SMEM = (size_t)DEC_THREADS * gzl::LANE_U16 * 2;
 constexpr int SCAN_WARPS = 8;
 constexpr size_t SCAN_SMEM = (size_t)SCAN_WARPS * gzl::LANE_U16 * 2;
@@ -42,6 +46,7 @@ constexpr uint32_t PIECE = 16384;                    // bytes of text per CTA of
 constexpr int RES_THREADS = 256;
 constexpr uint32_t SUB = PIECE / RES_THREADS;        // bytes per thread in the CRC
 constexpr int WIN_THREADS = 1024;
+static_assert(DEC_SMEM <= 232448, "a CTA's lanes must fit the 227 KB of shared memory");
 static_assert(SUB == 64, "the CRC tree's first operator is x^(8*64)");
 
 struct RoundArgs {
@@ -57,6 +62,7 @@ struct RoundArgs {
     uint16_t *syms;              // [nchunks][symcap]
     gzl::Meta *meta;
     const uint8_t *kraft3;
+    uint16_t *cold;              // [nchunks][COLD_U16]: a lane's list of long-code symbols (the scan's warps use it first)
 };
 
 __device__ __forceinline__ uint64_t nominal_rel(const RoundArgs &a, uint64_t k)
@@ -75,7 +81,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) gz_scan(const RoundArgs a)
     const uint32_t k = blockIdx.x * SCAN_WARPS + warp + 1;       // chunk 0 starts at a known bit
     if (k >= a.nchunks) return;
     const uint64_t from = nominal_rel(a, k), to = nominal_rel(a, k + 1);
-    const gzl::Mem<1> m{s_lane + warp * gzl::LANE_U16};
+    const gzl::Mem<1> m{s_lane + warp * gzl::LANE_U16, a.cold + ((size_t)blockIdx.x * SCAN_WARPS + warp) * gzl::COLD_U16};
     uint32_t n = 0;
     for (uint64_t base = from; base < to && n < MAXC; base += 32) {
         const uint64_t idx = base >> 5;                          // `from` is a multiple of 128 bits
@@ -110,7 +116,7 @@ __global__ void __launch_bounds__(DEC_THREADS) gz_decode(const RoundArgs a)
     gzl::Meta r;
     z.state = gzl::S_DONE;
     if (mine) {
-        const gzl::Mem<32> m{s_lane + (size_t)warp * gzl::LANE_U16 * 32 + lane * 2};
+        const gzl::Mem<32> m{s_lane + (size_t)warp * gzl::LANE_U16 * 32 + lane * 2, a.cold + (size_t)k * gzl::COLD_U16};
         const uint64_t stop = nominal_rel(a, k + 1);
         uint16_t *out = a.syms + (size_t)k * a.symcap;
         if (k == 0) z.init(m, a.in, a.nwords, a.in_bits, true, a.pos_rel, nullptr, 0, stop, a.hist, out, a.symcap, &r);
@@ -125,57 +131,75 @@ __global__ void __launch_bounds__(DEC_THREADS) gz_decode(const RoundArgs a)
     }
 }
 
-// windows[0] holds the 32 KiB in front of the round; windows[k + 1] = the 32 KiB behind accepted chunk k
+// The 32 KiB in front of every accepted chunk.  R_0 is the window in front of the round (known
+// bytes), R_q the window behind accepted chunk q - 1: its entry i is the chunk's symbol WIN - i
+// from the end -- a byte, or a marker = entry s - 256 of R_{q-1} -- or, for a chunk shorter than
+// WIN, entry i + len of R_{q-1}.  Headers copied from record to record make these chains as long
+// as the round, so they are shortened by POINTER JUMPING, in place, all chunks at once: an entry
+// is a byte (bit 31 set) or a pointer (q' << 15 | i'); a pass replaces every pointer by what it
+// points to; ceil(log2(chunks)) + 1 passes leave bytes only.  (Handing the window from chunk to
+// chunk in one CTA took 6.4 us per chunk: 57 ms for the 8,861 chunks of a 1.2 GB round.)
+constexpr uint32_t P_BYTE = 0x80000000u;
+
 struct WinArgs {
     const uint16_t *syms;
     uint32_t symcap;
     const uint32_t *out_len;     // [accepted]
     uint32_t accepted;
-    uint8_t *windows;            // [accepted + 1][WIN]
+    const uint8_t *window_in;    // R_0
+    uint32_t *ptrs;              // [accepted + 1][WIN]
+    uint8_t *done;               // [accepted + 1] R_q holds bytes only
+    uint8_t *window_out;         // the bytes of R_accepted (gz_ptr_take)
 };
 
-__global__ void __launch_bounds__(WIN_THREADS) gz_windows(const WinArgs a)
+__global__ void __launch_bounds__(WIN_THREADS) gz_ptr_init(const WinArgs a)
 {
-    extern __shared__ uint8_t s_w[];                 // two windows
-    constexpr uint32_t PER = gzl::WIN / WIN_THREADS; // 32 entries per thread
-    const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i < gzl::WIN; i += WIN_THREADS) s_w[i] = a.windows[i];
-    // the last WIN symbols of a chunk do not depend on the chain: the next chunk's are loaded
-    // while this chunk's are resolved (a step is then shared-memory work only)
-    uint32_t cur_s[PER / 2], nxt_s[PER / 2];          // two symbols per register
-    auto load = [&](uint32_t k, uint32_t *dst) {
-        const uint32_t len = a.out_len[k];
-        const uint16_t *src = a.syms + (size_t)k * a.symcap;
-        const uint32_t keep = len >= gzl::WIN ? 0u : gzl::WIN - len;
-#pragma unroll
-        for (uint32_t j = 0; j < PER; j += 2) {
-            const uint32_t i0 = tid + j * WIN_THREADS, i1 = i0 + WIN_THREADS;
-            const uint32_t s0 = i0 < keep ? 0u : src[len - (gzl::WIN - i0)];
-            const uint32_t s1 = i1 < keep ? 0u : src[len - (gzl::WIN - i1)];
-            dst[j / 2] = s0 | s1 << 16;
-        }
-    };
-    if (a.accepted) load(0, cur_s);
-    __syncthreads();
-    for (uint32_t k = 0; k < a.accepted; k++) {
-        const uint8_t *cur = s_w + (k & 1u) * gzl::WIN;
-        uint8_t *nxt = s_w + ((k & 1u) ^ 1u) * gzl::WIN;
-        const uint32_t len = a.out_len[k];
-        uint8_t *dst = a.windows + (size_t)(k + 1) * gzl::WIN;
-        const uint32_t keep = len >= gzl::WIN ? 0u : gzl::WIN - len;     // bytes of the old window that stay
-        if (k + 1 < a.accepted) load(k + 1, nxt_s);
-#pragma unroll
-        for (uint32_t j = 0; j < PER; j++) {
-            const uint32_t i = tid + j * WIN_THREADS;
-            const uint32_t s = (j & 1u) ? cur_s[j / 2] >> 16 : cur_s[j / 2] & 0xFFFFu;
-            const uint8_t v = i < keep ? cur[i + len] : (s < 256 ? (uint8_t)s : cur[s - 256]);
-            nxt[i] = v;
-            dst[i] = v;
-        }
-#pragma unroll
-        for (uint32_t j = 0; j < PER / 2; j++) cur_s[j] = nxt_s[j];
-        __syncthreads();
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    uint32_t *dst = a.ptrs + (size_t)q * gzl::WIN;
+    if (q == 0) {
+        for (uint32_t i = tid; i < gzl::WIN; i += WIN_THREADS) dst[i] = P_BYTE | a.window_in[i];
+        if (tid == 0) a.done[0] = 1;
+        return;
     }
+    const uint32_t len = a.out_len[q - 1];
+    const uint16_t *src = a.syms + (size_t)(q - 1) * a.symcap;
+    const uint32_t keep = len >= gzl::WIN ? 0u : gzl::WIN - len;         // entries that are the old window, moved up
+    const uint32_t up = (q - 1) << 15;
+    for (uint32_t i = tid; i < gzl::WIN; i += WIN_THREADS) {
+        uint32_t e;
+        if (i < keep) e = up | (i + len);
+        else {
+            const uint32_t s = src[len - (gzl::WIN - i)];
+            e = s < 256 ? (P_BYTE | s) : (up | (s - 256));
+        }
+        dst[i] = e;
+    }
+    if (tid == 0) a.done[q] = 0;
+}
+
+__global__ void __launch_bounds__(WIN_THREADS) gz_ptr_jump(const WinArgs a)
+{
+    const uint32_t q = blockIdx.x + 1, tid = threadIdx.x;
+    if (a.done[q]) return;
+    uint32_t *mine = a.ptrs + (size_t)q * gzl::WIN;
+    int left = 0;
+    for (uint32_t i = tid; i < gzl::WIN; i += WIN_THREADS) {
+        const uint32_t e = mine[i];
+        if (e & P_BYTE) continue;
+        // whatever the entry pointed to says now is true of this entry too (in-place passes may see
+        // a target before or after its own update: both are right, the later one is shorter)
+        const uint32_t t = a.ptrs[(size_t)(e >> 15) * gzl::WIN + (e & 0x7FFFu)];
+        mine[i] = t;
+        left |= !(t & P_BYTE);
+    }
+    left = __syncthreads_or(left);
+    if (tid == 0 && !left) a.done[q] = 1;
+}
+
+__global__ void __launch_bounds__(WIN_THREADS) gz_ptr_take(const WinArgs a)
+{
+    const uint32_t *src = a.ptrs + (size_t)a.accepted * gzl::WIN;
+    for (uint32_t i = blockIdx.x * WIN_THREADS + threadIdx.x; i < gzl::WIN; i += gridDim.x * WIN_THREADS) a.window_out[i] = (uint8_t)src[i];
 }
 
 struct ResArgs {
@@ -183,7 +207,7 @@ struct ResArgs {
     uint32_t symcap;
     const uint64_t *text_off;    // [accepted + 1]
     uint32_t accepted;
-    const uint8_t *windows;
+    const uint32_t *ptrs;        // the windows in front of the accepted chunks (bytes by now)
     uint8_t *text;               // where byte 0 of the round's text goes
     uint64_t text_len;
     uint32_t *crc;               // [pieces] raw CRC-32 (register starts at 0, no final inversion)
@@ -231,7 +255,7 @@ __global__ void __launch_bounds__(RES_THREADS) gz_resolve(const ResArgs a)
         const uint64_t g = g0 + i;
         while (g >= c_end) c_end = a.text_off[++c + 1];
         const uint16_t s = a.syms[(size_t)c * a.symcap + (g - a.text_off[c])];
-        const uint8_t v = s < 256 ? (uint8_t)s : a.windows[(size_t)c * gzl::WIN + (s - 256)];
+        const uint8_t v = s < 256 ? (uint8_t)s : (uint8_t)a.ptrs[(size_t)c * gzl::WIN + (s - 256)];
         a.text[g] = v;
         const uint32_t u = i + shift;
         s_txt[u + (u >> 6) * 4] = v;

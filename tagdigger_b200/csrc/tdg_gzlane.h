@@ -33,18 +33,29 @@ namespace tdg {
 namespace gzl {
 
 constexpr uint32_t WIN = 32768;
-constexpr int LIT_ROOT = 10, DIST_ROOT = 8, PRE_ROOT = 7;
+#ifndef TDG_GZ_LIT_ROOT
+#define TDG_GZ_LIT_ROOT 9
+#endif
+#ifndef TDG_GZ_DIST_ROOT
+#define TDG_GZ_DIST_ROOT 8
+#endif
+constexpr int LIT_ROOT = TDG_GZ_LIT_ROOT, DIST_ROOT = TDG_GZ_DIST_ROOT, PRE_ROOT = 7;
+static_assert(LIT_ROOT >= 7 && LIT_ROOT <= 12 && DIST_ROOT >= 6 && DIST_ROOT <= 10, "table roots");
 
-// lane-private memory map, in 16-bit units (every region starts on a 32-bit word)
-constexpr uint32_t O_LIT = 0;                 // 1024 x u16  primary literal/length table (code-length table while a header is read)
-constexpr uint32_t O_LSORT = O_LIT + 1024;    //  288 x u16  literal/length symbols with codes longer than LIT_ROOT, in code order
-constexpr uint32_t O_LCNT = O_LSORT + 288;    //   16 x u16  codes per length
-constexpr uint32_t O_DIST = O_LCNT + 16;      //  256 x u16  primary distance table
-constexpr uint32_t O_DSORT = O_DIST + 256;    //   32 x u16  distance symbols with codes longer than DIST_ROOT
-constexpr uint32_t O_DCNT = O_DSORT + 32;     //   16 x u16
-constexpr uint32_t O_LENS = O_DCNT + 16;      //  320 x u8   code lengths of the header being read
-constexpr uint32_t LANE_U16 = O_LENS + 160;   // 1,792 units = 3,584 bytes per lane
+// A lane's HOT memory (shared memory on the device), in 16-bit units; every region starts on a
+// 32-bit word.  What bounds the lanes per SM is this: 1,760 bytes per lane = 128 lanes = 4 warps.
+constexpr uint32_t O_LIT = 0;                              // primary literal/length table (code-length table while a header is read)
+constexpr uint32_t O_DIST = O_LIT + (1u << LIT_ROOT);      // primary distance table (scratch while the other codes are built)
+constexpr uint32_t O_LCNT = O_DIST + (1u << DIST_ROOT);    // 16: codes per length; [0]: the first code of length root + 1
+constexpr uint32_t O_DCNT = O_LCNT + 16;                   // 16
+constexpr uint32_t O_LENS = O_DCNT + 16;                   // 320 x 4 bits: code lengths of the header being read
+constexpr uint32_t LANE_U16 = O_LENS + 80;
 static_assert(LANE_U16 % 2 == 0, "a lane's slice is a whole number of 32-bit words");
+// A lane's COLD memory (global memory on the device): the symbols whose codes are longer than the
+// roots, in code order -- touched only when such a code turns up (under 1 % of the symbols).
+constexpr uint32_t C_LSORT = 0;                            // 288
+constexpr uint32_t C_DSORT = 288;                          // 32
+constexpr uint32_t COLD_U16 = 320;
 
 constexpr uint16_t E_LONG = 0x8000;           // primary entry: the code is longer than the root
 // other entries: symbol << 4 | code length; 0 = no code here
@@ -68,12 +79,20 @@ struct Meta {                 // what a lane reports about its chunk
 
 template <int STRIDE>
 struct Mem {
-    uint16_t *base;           // the lane's first 16-bit unit
+    uint16_t *base;           // the lane's first 16-bit unit of hot memory
+    uint16_t *cold;           // the lane's cold memory (COLD_U16 units, not interleaved)
     TDG_GZ_HD uint16_t &h(uint32_t i) const { return base[((i >> 1) * STRIDE) * 2 + (i & 1u)]; }
     TDG_GZ_HD uint8_t &b(uint32_t off16, uint32_t i) const
     {
         const uint32_t byte = off16 * 2 + i;
         return ((uint8_t *)base)[((byte >> 2) * STRIDE) * 4 + (byte & 3u)];
+    }
+    // arrays of 4-bit code lengths
+    TDG_GZ_HD uint32_t nib(uint32_t off16, uint32_t i) const { return (b(off16, i >> 1) >> ((i & 1u) * 4)) & 15u; }
+    TDG_GZ_HD void set_nib(uint32_t off16, uint32_t i, uint32_t v) const
+    {
+        uint8_t &x = b(off16, i >> 1);
+        x = (uint8_t)((i & 1u) ? ((x & 0x0Fu) | (v << 4)) : ((x & 0xF0u) | v));
     }
 };
 
@@ -120,83 +139,91 @@ struct Bits {
     TDG_GZ_HD uint64_t pos() const { return w * 32 - (uint64_t)cnt; }
 };
 
+// the low `len` bits of c in reverse order
 TDG_GZ_HD uint32_t bitrev(uint32_t c, int len)
 {
+#if defined(__CUDA_ARCH__)
+    return __brev(c) >> (32 - len);
+#else
     uint32_t r = 0;
     for (int b = 0; b < len; b++) r |= ((c >> b) & 1u) << (len - 1 - b);
     return r;
+#endif
 }
 
 // Builds the decoding structures of one canonical code from the n code lengths that start at
-// byte `first` of the lane's byte array at 16-bit offset o_lens.  Acceptance as in zlib's inflate_table: over-subscribed and incomplete sets
-// are refused, except the incomplete set that is a single 1-bit code (allow_single); a set
-// without any code is accepted and decodes nothing.
+// nibble `first` of the lane's array of 4-bit lengths at 16-bit offset o_lens; o_sort: where in
+// the lane's cold memory the symbols with codes longer than the root are listed.  Acceptance as in zlib's
+// inflate_table: over-subscribed and incomplete sets are refused, except the incomplete set that
+// is a single 1-bit code (allow_single); a set without any code is accepted and decodes nothing.
+// o_scr: 32 16-bit units of lane memory that are free while the code is built (the next code
+// value and the next slot in the long-code list, per length): one pass over the symbols.
 template <int STRIDE>
 TDG_GZ_FN bool build_code(const Mem<STRIDE> m, uint32_t o_lens, uint32_t first, uint32_t n, int root, uint32_t o_tab,
-                          uint32_t o_sort, uint32_t o_cnt, bool allow_single)
+                          uint32_t o_sort, uint32_t o_cnt, uint32_t o_scr, bool allow_single)
 {
     for (uint32_t l = 0; l < 16; l++) m.h(o_cnt + l) = 0;
-    for (uint32_t i = 0; i < n; i++) m.h(o_cnt + m.b(o_lens, first + i))++;
+    for (uint32_t i = 0; i < n; i++) m.h(o_cnt + m.nib(o_lens, first + i))++;
     m.h(o_cnt) = 0;
     int max = 15;
     while (max >= 1 && !m.h(o_cnt + max)) max--;
     const uint32_t psize = 1u << root;
-    for (uint32_t j = 0; j < psize; j++) m.h(o_tab + j) = 0;
-    if (max == 0) return true;
     int left = 1;
     for (int len = 1; len <= 15; len++) {
         left <<= 1;
         left -= (int)m.h(o_cnt + len);
         if (left < 0) return false;
     }
-    if (left > 0 && !(allow_single && max == 1)) return false;
-    // codes of at most `root` bits: every table index that ends in the (bit-reversed) code
-    uint32_t code = 0;
-    for (int len = 1; len <= root && len <= max; len++) {
-        code = (code + m.h(o_cnt + len - 1)) << 1;          // first code of this length
-        if (!m.h(o_cnt + len)) continue;
-        uint32_t c = code;
-        for (uint32_t s = 0; s < n; s++) {
-            if (m.b(o_lens, first + s) != len) continue;
-            const uint32_t rev = bitrev(c++, len);
-            const uint16_t e = (uint16_t)(s << 4 | (uint32_t)len);
-            for (uint32_t j = rev; j < psize; j += 1u << len) m.h(o_tab + j) = e;
+    if (max > 0 && left > 0 && !(allow_single && max == 1)) return false;
+    if (left > 0)                                            // an incomplete (or empty) set leaves holes: "no code here"
+        for (uint32_t j = 0; j < psize; j++) m.h(o_tab + j) = 0;
+    if (max == 0) return true;
+    {
+        uint32_t code = 0, slot = 0, first_long = 0;
+        for (int len = 1; len <= 15; len++) {
+            code = (code + m.h(o_cnt + len - 1)) << 1;      // first code of this length
+            m.h(o_scr + len) = (uint16_t)code;
+            m.h(o_scr + 16 + len) = (uint16_t)slot;
+            if (len > root) slot += m.h(o_cnt + len);
+            if (len == root + 1) first_long = code;
         }
+        m.h(o_cnt) = (uint16_t)first_long;                  // (the count of unused symbols is of no use: decode_long starts here)
     }
-    // longer codes: mark their root-bit prefixes, list the symbols in code order
-    uint32_t at = 0;
-    for (int len = root + 1; len <= max; len++) {
-        code = (code + m.h(o_cnt + len - 1)) << 1;
-        if (!m.h(o_cnt + len)) continue;
-        uint32_t c = code;
-        for (uint32_t s = 0; s < n; s++) {
-            if (m.b(o_lens, first + s) != len) continue;
-            m.h(o_tab + (bitrev(c >> (len - root), root))) = E_LONG;
-            c++;
-            m.h(o_sort + at++) = (uint16_t)s;
+    for (uint32_t s = 0; s < n; s++) {
+        const int len = (int)m.nib(o_lens, first + s);
+        if (!len) continue;
+        const uint32_t c = m.h(o_scr + len);
+        m.h(o_scr + len) = (uint16_t)(c + 1);
+        if (len <= root) {
+            // every table index that ends in the (bit-reversed) code
+            const uint16_t e = (uint16_t)(s << 4 | (uint32_t)len);
+            for (uint32_t j = bitrev(c, len); j < psize; j += 1u << len) m.h(o_tab + j) = e;
+        } else {
+            // a longer code: mark its root-bit prefix, list the symbol in code order
+            m.h(o_tab + bitrev(c >> (len - root), root)) = E_LONG;
+            const uint32_t at = m.h(o_scr + 16 + len);
+            m.h(o_scr + 16 + len) = (uint16_t)(at + 1);
+            m.cold[o_sort + at] = (uint16_t)s;
         }
     }
     return true;
 }
 
-// A code longer than the root, bit by bit (canonical order: the first code of each length follows
-// from the counts).  Returns symbol << 4 | length, 0 when the bits are no code.
+// A code longer than the root: its first `root` bits are the table index that led here; the
+// rest is read bit by bit (canonical order: the first code of each length follows from the
+// counts).  Returns symbol << 4 | length, 0 when the bits are no code.
 template <int STRIDE>
 TDG_GZ_FN uint32_t decode_long(const Mem<STRIDE> m, uint64_t buf, int root, uint32_t o_sort, uint32_t o_cnt)
 {
-    uint32_t code = 0, first = 0;
-    for (int len = 1; len <= root; len++) {
-        code |= (uint32_t)(buf & 1u);
-        buf >>= 1;
-        first = (first + m.h(o_cnt + len)) << 1;
-        code <<= 1;
-    }
+    uint32_t code = bitrev((uint32_t)buf & ((1u << root) - 1u), root) << 1;
+    uint32_t first = m.h(o_cnt);                             // first code of length root + 1
+    buf >>= root;
     uint32_t index = 0;
     for (int len = root + 1; len <= 15; len++) {
         code |= (uint32_t)(buf & 1u);
         buf >>= 1;
         const uint32_t count = m.h(o_cnt + len);
-        if (code < first + count) return (uint32_t)m.h(o_sort + index + (code - first)) << 4 | (uint32_t)len;
+        if (code < first + count) return (uint32_t)m.cold[o_sort + index + (code - first)] << 4 | (uint32_t)len;
         index += count;
         first = (first + count) << 1;
         code <<= 1;
@@ -300,13 +327,13 @@ struct Lane {
 
     TDG_GZ_FN bool load_fixed()
     {
-        for (uint32_t i = 0; i < 144; i++) m.b(O_LENS, i) = 8;
-        for (uint32_t i = 144; i < 256; i++) m.b(O_LENS, i) = 9;
-        for (uint32_t i = 256; i < 280; i++) m.b(O_LENS, i) = 7;
-        for (uint32_t i = 280; i < 288; i++) m.b(O_LENS, i) = 8;
-        if (!build_code<STRIDE>(m, O_LENS, 0, 288, LIT_ROOT, O_LIT, O_LSORT, O_LCNT, true)) return false;
-        for (uint32_t i = 0; i < 32; i++) m.b(O_LENS, i) = 5;
-        return build_code<STRIDE>(m, O_LENS, 0, 32, DIST_ROOT, O_DIST, O_DSORT, O_DCNT, true);
+        for (uint32_t i = 0; i < 144; i++) m.set_nib(O_LENS, i, 8);
+        for (uint32_t i = 144; i < 256; i++) m.set_nib(O_LENS, i, 9);
+        for (uint32_t i = 256; i < 280; i++) m.set_nib(O_LENS, i, 7);
+        for (uint32_t i = 280; i < 288; i++) m.set_nib(O_LENS, i, 8);
+        if (!build_code<STRIDE>(m, O_LENS, 0, 288, LIT_ROOT, O_LIT, C_LSORT, O_LCNT, O_DIST, true)) return false;
+        for (uint32_t i = 0; i < 32; i++) m.set_nib(O_LENS, i, 5);
+        return build_code<STRIDE>(m, O_LENS, 0, 32, DIST_ROOT, O_DIST, C_DSORT, O_DCNT, O_LENS + 32, true);
     }
 
     // dynamic block header at the reader's position (behind the three block bits)
@@ -320,14 +347,14 @@ struct Lane {
                               10ull << 40 | 5ull << 45 | 11ull << 50 | 4ull << 55;
         const uint64_t ord1 = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
         // the code-length code: its lengths sit in the (still unused) distance table, its decoding
-        // structures borrow the literal/length regions -- both are rebuilt below
-        for (uint32_t i = 0; i < 19; i++) m.b(O_DIST, i) = 0;
+        // table borrows the literal/length region -- both are rebuilt below
+        for (uint32_t i = 0; i < 10; i++) m.b(O_DIST, i) = 0;
         for (uint32_t i = 0; i < hclen; i++) {
             bits.fill();
             const uint32_t sym = (uint32_t)((i < 12 ? ord0 >> (5 * i) : ord1 >> (5 * (i - 12))) & 31u);
-            m.b(O_DIST, sym) = (uint8_t)bits.take(3);
+            m.set_nib(O_DIST, sym, bits.take(3));
         }
-        if (!build_code<STRIDE>(m, O_DIST, 0, 19, PRE_ROOT, O_LIT, O_LSORT, O_LCNT, false)) return false;
+        if (!build_code<STRIDE>(m, O_DIST, 0, 19, PRE_ROOT, O_LIT, C_LSORT, O_LCNT, O_DIST + 32, false)) return false;
         const uint32_t total = hlit + hdist;
         uint32_t i = 0;
         uint32_t prev = 0;
@@ -338,7 +365,7 @@ struct Lane {
             bits.drop((int)(e & 15u));
             const uint32_t sym = e >> 4;
             if (sym < 16) {
-                m.b(O_LENS, i) = (uint8_t)sym;
+                m.set_nib(O_LENS, i, sym);
                 prev = sym;
                 i++;
                 continue;
@@ -354,13 +381,13 @@ struct Lane {
                 rep = 11 + bits.take(7);
             }
             if (i + rep > total) return false;
-            while (rep--) m.b(O_LENS, i++) = (uint8_t)val;
+            while (rep--) m.set_nib(O_LENS, i++, val);
             prev = val;
         }
         if (exhausted()) return false;
-        if (m.b(O_LENS, 256) == 0) return false;            // no end-of-block code
-        if (!build_code<STRIDE>(m, O_LENS, 0, hlit, LIT_ROOT, O_LIT, O_LSORT, O_LCNT, true)) return false;
-        if (!build_code<STRIDE>(m, O_LENS, hlit, hdist, DIST_ROOT, O_DIST, O_DSORT, O_DCNT, true)) return false;
+        if (m.nib(O_LENS, 256) == 0) return false;          // no end-of-block code
+        if (!build_code<STRIDE>(m, O_LENS, 0, hlit, LIT_ROOT, O_LIT, C_LSORT, O_LCNT, O_DIST, true)) return false;
+        if (!build_code<STRIDE>(m, O_LENS, hlit, hdist, DIST_ROOT, O_DIST, C_DSORT, O_DCNT, O_LENS, true)) return false;
         fixed_loaded = false;
         return true;
     }
@@ -505,7 +532,7 @@ struct Lane {
         }
         bits.fill();
         uint32_t e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << LIT_ROOT) - 1u)));
-        if (e & E_LONG) e = decode_long<STRIDE>(m, bits.buf, LIT_ROOT, O_LSORT, O_LCNT);
+        if (e & E_LONG) e = decode_long<STRIDE>(m, bits.buf, LIT_ROOT, C_LSORT, O_LCNT);
         if (e == 0) {
             fail(F_ERROR);
             return;
@@ -541,7 +568,7 @@ struct Lane {
         }
         bits.fill();
         uint32_t f = m.h(O_DIST + ((uint32_t)bits.buf & ((1u << DIST_ROOT) - 1u)));
-        if (f & E_LONG) f = decode_long<STRIDE>(m, bits.buf, DIST_ROOT, O_DSORT, O_DCNT);
+        if (f & E_LONG) f = decode_long<STRIDE>(m, bits.buf, DIST_ROOT, C_DSORT, O_DCNT);
         if (f == 0) {
             fail(F_ERROR);
             return;
@@ -579,24 +606,36 @@ struct Lane {
         int32_t j = (int32_t)o - (int32_t)d;
         uint16_t *q = out + o;
         o += len;
-        if (d >= 8) {
+        if (d >= 8 && j >= 0) {
+            // the common case: the source is text this lane has written, eight symbols and more back
+            const uint16_t *p = out + j;
             while (len >= 8) {
-                const uint16_t a0 = sym_at(j), a1 = sym_at(j + 1), a2 = sym_at(j + 2), a3 = sym_at(j + 3), a4 = sym_at(j + 4),
-                               a5 = sym_at(j + 5), a6 = sym_at(j + 6), a7 = sym_at(j + 7);
+                const uint16_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4], a5 = p[5], a6 = p[6], a7 = p[7];
                 q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3; q[4] = a4; q[5] = a5; q[6] = a6; q[7] = a7;
                 q += 8;
-                j += 8;
+                p += 8;
                 len -= 8;
             }
-            uint16_t a[7];
-#pragma unroll
-            for (uint32_t k = 0; k < 7; k++) a[k] = k < len ? sym_at(j + (int32_t)k) : (uint16_t)0;
-#pragma unroll
-            for (uint32_t k = 0; k < 7; k++)
-                if (k < len) q[k] = a[k];
+            if (len >= 4) {
+                const uint16_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+                q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3;
+                q += 4;
+                p += 4;
+                len -= 4;
+            }
+            if (len) {
+                const uint16_t a0 = p[0], a1 = len > 1 ? p[1] : (uint16_t)0, a2 = len > 2 ? p[2] : (uint16_t)0;
+                q[0] = a0;
+                if (len > 1) q[1] = a1;
+                if (len > 2) q[2] = a2;
+            }
             return;
         }
-        // the d symbols of the pattern, packed 16 bits each
+        if (d >= 8) {
+            for (uint32_t k = 0; k < len; k++) q[k] = sym_at(j + (int32_t)k);      // (d >= len or not: sources lie 8+ back, in order)
+            return;
+        }
+        // a short distance repeats a pattern: its d symbols, packed 16 bits each
         uint64_t lo = 0, hi = 0;
 #pragma unroll
         for (uint32_t k = 0; k < 7; k++) {

@@ -16,7 +16,7 @@ namespace {
 // candidates of chunk k: bit offsets from `from` (relative to the buffer) that pass quick_test and
 // whose dynamic block header parses; the search stops at the first max_cand of them
 void scan(const std::vector<uint8_t> &buf, uint64_t nwords, uint64_t in_bits, uint64_t from, uint64_t to, const uint8_t *kraft3,
-          uint16_t *mem, std::vector<uint32_t> &cand, size_t max_cand)
+          uint16_t *mem, uint16_t *cold, std::vector<uint32_t> &cand, size_t max_cand)
 {
     cand.clear();
     for (uint64_t p = from; p < to && cand.size() < max_cand; p++) {
@@ -29,7 +29,7 @@ void scan(const std::vector<uint8_t> &buf, uint64_t nwords, uint64_t in_bits, ui
         const uint64_t lo = sh ? (a >> sh | b << (64 - sh)) : a;
         const uint32_t hi = (uint32_t)(b >> sh);
         if (!gzl::quick_test(lo, hi, kraft3)) continue;
-        if (gzl::header_parses<1>(gzl::Mem<1>{mem}, (const uint32_t *)buf.data(), nwords, in_bits, p)) cand.push_back((uint32_t)(p - from));
+        if (gzl::header_parses<1>(gzl::Mem<1>{mem, cold}, (const uint32_t *)buf.data(), nwords, in_bits, p)) cand.push_back((uint32_t)(p - from));
     }
 }
 
@@ -52,7 +52,7 @@ long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_ch
     uint8_t kraft3[512];
     gzl::make_kraft3(kraft3);
     std::vector<uint8_t> window(gzl::WIN, 0);
-    std::vector<uint16_t> mem(gzl::LANE_U16);
+    std::vector<uint16_t> mem(gzl::LANE_U16), cold(gzl::COLD_U16);
     std::vector<std::vector<uint16_t>> syms;
     std::vector<gzl::Meta> meta;
     std::vector<uint32_t> cand;
@@ -69,7 +69,7 @@ long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_ch
         meta.assign(r.nchunks, gzl::Meta());
         for (uint32_t k = 0; k < r.nchunks; k++) {
             syms[k].resize(symcap);
-            gzl::Mem<1> m{mem.data()};
+            gzl::Mem<1> m{mem.data(), cold.data()};
             const uint64_t stop = r.nominal(k + 1, n) - base_bit;
             if (k == 0) {
                 gzl::run_chunk<1>(m, (const uint32_t *)buf.data(), nwords, (uint64_t)nb * 8, true, r.pos_bit - base_bit, nullptr, 0,
@@ -77,7 +77,7 @@ long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_ch
             } else {
                 const uint64_t from = r.nominal(k, n) - base_bit;
                 const uint64_t to = std::min<uint64_t>(from + (uint64_t)search_bytes * 8, stop);
-                scan(buf, nwords, (uint64_t)nb * 8, from, to, kraft3, mem.data(), cand, 2);
+                scan(buf, nwords, (uint64_t)nb * 8, from, to, kraft3, mem.data(), cold.data(), cand, 2);
                 gzl::run_chunk<1>(m, (const uint32_t *)buf.data(), nwords, (uint64_t)nb * 8, false, from, cand.data(),
                                   (uint32_t)cand.size(), stop, 0, syms[k].data(), symcap, meta[k]);
             }
@@ -91,7 +91,7 @@ long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_ch
         // resolve the accepted chunks against the window handed from chunk to chunk
         const size_t text_at = total;
         for (uint32_t k = 0; k < o.accepted; k++) {
-            const uint32_t len = meta[k].out_len;
+            const uint32_t len = o.lens[k];
             if (total + len > cap) return -100;
             for (uint32_t i = 0; i < len; i++) {
                 const uint16_t s = syms[k][i];
@@ -106,7 +106,7 @@ long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_ch
         }
         const uint64_t text_len = total - text_at;
         const uint32_t text_crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), out + text_at, (uInt)text_len);
-        if (!st.advance(r, o, meta.data(), text_len, text_crc)) return -2;
+        if (!st.advance(r, o, text_len, text_crc)) return -2;
     }
     if (st.handover) {
         if (why && why_cap) {
