@@ -119,9 +119,10 @@ struct tdg_ctx {
     size_t file_buf_cap = 0;
 
     // device-side gzip feed (tdg_gzdev.cuh): growable buffers, kept between files
-    Grow gz_comp, gz_syms, gz_meta, gz_cand, gz_ncand, gz_windows, gz_text, gz_crc, gz_lens, gz_offs, gz_tabs, gz_carry, gz_cold;   // device
+    Grow gz_comp, gz_comp2, gz_syms, gz_sym2, gz_ntok, gz_meta, gz_cand, gz_ncand, gz_windows, gz_text, gz_crc, gz_lens, gz_offs, gz_tabs, gz_carry, gz_cold;   // device
     Grow gz_hmeta, gz_hcrc, gz_htail;                                                                                       // pinned host
     cudaEvent_t gz_up[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t gz_pre = nullptr;
     bool gz_tables = false;
     uint32_t gz_op[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -620,7 +621,9 @@ int gz_tables(tdg_ctx *ctx)
     CK(cudaMemcpy(ctx->gz_tabs.p, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     for (int j = 0; j < 8; j++) ctx->gz_op[j] = (uint32_t)crc32_combine_gen((z_off_t)(tdg::gzd::SUB << j));
     for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&ctx->gz_up[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->gz_pre, cudaEventDisableTiming));
     CK(cudaFuncSetAttribute(tdg::gzd::gz_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tdg::gzd::DEC_SMEM));
+    CK(cudaFuncSetAttribute(tdg::gzd::gz_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tdg::gzd::SCAN_SMEM));
     ctx->gz_tables = true;
     return TDG_OK;
 }
@@ -683,27 +686,45 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         return std::chrono::duration<double, std::milli>(b - a).count();
     };
 
+    int up_i = 0;
+    // file bytes [off, end) -> compressed buffer `which`, through the three pinned buffers, on `stream`
+    auto upload = [&](int which, size_t off, size_t end, cudaStream_t stream) -> int {
+        tdg_ctx::Grow &g = which ? ctx->gz_comp2 : ctx->gz_comp;
+        const size_t nb = end - off, padded = (nb + 3) / 4 * 4 + 256;
+        int rc = grow(ctx, g, padded, false);
+        if (rc) return rc;
+        const size_t piece = ctx->file_buf_cap;
+        for (size_t at = 0; at < nb; at += piece, up_i = (up_i + 1) % 3) {
+            const size_t m = std::min(piece, nb - at);
+            CK(cudaEventSynchronize(ctx->gz_up[up_i]));
+            if (!gz_pread_parallel(map.fd, ctx->file_buf[up_i], m, off + at, threads))
+                return fail(ctx, TDG_ERR_IO, std::string("read error on ") + path);
+            CK(cudaMemcpyAsync((uint8_t *)g.p + at, ctx->file_buf[up_i], m, cudaMemcpyHostToDevice, stream));
+            CK(cudaEventRecord(ctx->gz_up[up_i], stream));
+        }
+        CK(cudaMemsetAsync((uint8_t *)g.p + nb, 0, padded - nb, stream));
+        return TDG_OK;
+    };
+    int cur = 0;                                             // which compressed buffer the round reads
+    bool pre_valid = false;                                  // the other one holds [pre_off, pre_end) of the file
+    size_t pre_off = 0, pre_end = 0;
+
     while (!st.eof && !st.handover) {
         const gzc::Round r = st.plan(chunk, max_chunks);
         const size_t nb = r.buf_end - r.buf_off;
         const size_t nwords = (nb + 3) / 4;
-        // ---- the round's compressed bytes: file -> pinned pieces -> device
+        // ---- the round's compressed bytes: file -> pinned pieces -> device (or already there: see below)
         auto t0 = now();
-        rc = grow(ctx, ctx->gz_comp, nwords * 4 + 256, false);
-        if (rc) return rc;
-        {
-            const size_t piece = ctx->file_buf_cap;
-            int bi = 0;
-            for (size_t at = 0; at < nb; at += piece, bi = (bi + 1) % 3) {
-                const size_t m = std::min(piece, nb - at);
-                CK(cudaEventSynchronize(ctx->gz_up[bi]));
-                if (!gz_pread_parallel(map.fd, ctx->file_buf[bi], m, r.buf_off + at, threads))
-                    return fail(ctx, TDG_ERR_IO, std::string("read error on ") + path);
-                CK(cudaMemcpyAsync((uint8_t *)ctx->gz_comp.p + at, ctx->file_buf[bi], m, cudaMemcpyHostToDevice, ctx->stream));
-                CK(cudaEventRecord(ctx->gz_up[bi], ctx->stream));
-            }
-            CK(cudaMemsetAsync((uint8_t *)ctx->gz_comp.p + nb, 0, nwords * 4 + 256 - nb, ctx->stream));
+        const bool prefetched = pre_valid && pre_off == r.buf_off && pre_end >= r.buf_end;
+        if (prefetched) {
+            cur ^= 1;                                        // the bytes sit in the other buffer: wait for their copies
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->gz_pre, 0));
+        } else {
+            rc = upload(cur, r.buf_off, r.buf_end, ctx->stream);
+            if (rc) return rc;
         }
+        pre_valid = false;
+        tdg_ctx::Grow &comp = cur ? ctx->gz_comp2 : ctx->gz_comp;
         if ((rc = grow(ctx, ctx->gz_syms, (size_t)r.nchunks * symcap * 2, false))) return rc;
         if ((rc = grow(ctx, ctx->gz_meta, (size_t)r.nchunks * sizeof(gzl::Meta), false))) return rc;
         if ((rc = grow(ctx, ctx->gz_cand, (size_t)r.nchunks * gzd::MAXC * 4, false))) return rc;
@@ -714,7 +735,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         auto t1 = now();
         // ---- scan + decode
         gzd::RoundArgs a;
-        a.in = (const uint32_t *)ctx->gz_comp.p;
+        a.in = (const uint32_t *)comp.p;
         a.nwords = nwords;
         a.in_bits = (uint64_t)nb * 8;
         a.nchunks = r.nchunks;
@@ -744,6 +765,17 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         ctx->launches++;
         gzl::Meta *meta = (gzl::Meta *)ctx->gz_hmeta.p;
         CK(cudaMemcpyAsync(meta, ctx->gz_meta.p, (size_t)r.nchunks * sizeof(gzl::Meta), cudaMemcpyDeviceToHost, ctx->stream));
+        // While the lanes inflate, this thread reads the bytes the NEXT round will most likely ask
+        // for (every chunk accepted: its grid starts where this one's ends) and sends them to the
+        // other buffer on the copy stream.
+        if (r.grid + (size_t)r.nchunks * chunk < map.n && r.nchunks == max_chunks) {
+            pre_off = r.grid + (size_t)r.nchunks * chunk;
+            pre_end = std::min(map.n, pre_off + ((size_t)max_chunks + 1) * chunk);
+            rc = upload(cur ^ 1, pre_off, pre_end, ctx->copy_stream);
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->gz_pre, ctx->copy_stream));
+            pre_valid = true;
+        }
         CK(cudaStreamSynchronize(ctx->stream));
         auto t3 = now();
         // ---- which chunks continue the stream
@@ -769,9 +801,31 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
                 if (carry) CK(cudaMemcpyAsync(ctx->gz_text.p, ctx->gz_carry.p, carry, cudaMemcpyDeviceToDevice, ctx->stream));
             }
             CK(cudaMemcpyAsync(ctx->gz_lens.p, o.lens.data(), o.lens.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            // tokens -> symbols (accepted chunks only)
+            if ((rc = grow(ctx, ctx->gz_sym2, (size_t)r.nchunks * symcap * 2, false))) return rc;
+            if ((rc = grow(ctx, ctx->gz_ntok, (size_t)o.accepted * 4, false))) return rc;
+            {
+                std::vector<uint32_t> ntok(o.accepted);
+                for (uint32_t k = 0; k < o.accepted; k++) ntok[k] = o.lens[k] ? meta[k].ntok : 0u;
+                CK(cudaMemcpyAsync(ctx->gz_ntok.p, ntok.data(), ntok.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));      // (ntok is a local)
+                gzd::ExpandArgs ea;
+                ea.tok = a.syms;
+                ea.syms = (uint16_t *)ctx->gz_sym2.p;
+                ea.symcap = symcap;
+                ea.ntok = (const uint32_t *)ctx->gz_ntok.p;
+                ea.accepted = o.accepted;
+                gzd::gz_expand<<<(o.accepted + gzd::EXP_WARPS - 1) / gzd::EXP_WARPS, gzd::EXP_WARPS * 32, 0, ctx->stream>>>(ea);
+                CK(cudaGetLastError());
+                ctx->launches++;
+                if (debug) {
+                    CK(cudaStreamSynchronize(ctx->stream));
+                    fprintf(stderr, "gzdev expand: %.1f ms\n", ms(t3, now()));
+                }
+            }
             CK(cudaMemcpyAsync(ctx->gz_offs.p, o.text_off.data(), o.text_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
             gzd::WinArgs w;
-            w.syms = a.syms;
+            w.syms = (const uint16_t *)ctx->gz_sym2.p;
             w.symcap = symcap;
             w.out_len = (const uint32_t *)ctx->gz_lens.p;
             w.accepted = o.accepted;
@@ -793,7 +847,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             uint32_t *d_flag = (uint32_t *)ctx->gz_crc.p + pieces;
             CK(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
             gzd::ResArgs ra;
-            ra.syms = a.syms;
+            ra.syms = (const uint16_t *)ctx->gz_sym2.p;
             ra.symcap = symcap;
             ra.text_off = (const uint64_t *)ctx->gz_offs.p;
             ra.accepted = o.accepted;
@@ -1020,13 +1074,14 @@ void tdg_destroy(tdg_ctx *ctx)
             if (g->p) cudaFree(g->p);
         for (tdg_ctx::Grow *g : {&ctx->sp_hout, &ctx->sp_hflags, &ctx->sp_hbase})
             if (g->p) cudaFreeHost(g->p);
-        for (tdg_ctx::Grow *g : {&ctx->gz_comp, &ctx->gz_syms, &ctx->gz_meta, &ctx->gz_cand, &ctx->gz_ncand, &ctx->gz_windows,
+        for (tdg_ctx::Grow *g : {&ctx->gz_comp, &ctx->gz_comp2, &ctx->gz_syms, &ctx->gz_sym2, &ctx->gz_ntok, &ctx->gz_meta, &ctx->gz_cand, &ctx->gz_ncand, &ctx->gz_windows,
                                  &ctx->gz_text, &ctx->gz_crc, &ctx->gz_lens, &ctx->gz_offs, &ctx->gz_tabs, &ctx->gz_carry, &ctx->gz_cold})
             if (g->p) cudaFree(g->p);
         for (tdg_ctx::Grow *g : {&ctx->gz_hmeta, &ctx->gz_hcrc, &ctx->gz_htail})
             if (g->p) cudaFreeHost(g->p);
         for (int i = 0; i < 3; i++)
             if (ctx->gz_up[i]) cudaEventDestroy(ctx->gz_up[i]);
+        if (ctx->gz_pre) cudaEventDestroy(ctx->gz_pre);
         if (ctx->d_replicas) cudaFree(ctx->d_replicas);
         for (int i = 0; i < 3; i++)
             if (ctx->file_buf[i]) cudaFreeHost(ctx->file_buf[i]);

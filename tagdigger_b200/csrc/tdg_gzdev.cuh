@@ -8,14 +8,17 @@
 //   gz_scan     one WARP per chunk looks for the first dynamic block header behind the chunk's
 //               nominal offset: 32 bit positions per step pass the cheap test (block bits, HLIT /
 //               HDIST, code-length code exactly complete -- a table of Kraft sums for three
-//               lengths at a time); a position that passes has its header parsed by its lane;
-//   gz_decode   one LANE per chunk inflates from there (tdg_gzlane.h) into 16-bit symbols, up to
-//               the block boundary at or behind the next chunk's nominal offset, and reports
-//               where it started and stopped.  A lane is a state machine and the 32 lanes of a
+//               lengths at a time); positions that pass are queued and their headers parsed 32 at a
+//               time, one per lane;
+//   gz_decode   one LANE per chunk inflates from there (tdg_gzlane.h) into TOKENS (literals and
+//               length / distance pairs), up to the block boundary at or behind the next chunk's
+//               nominal offset, and reports where it started and stopped.  A lane is a state machine and the 32 lanes of a
 //               warp take their steps together behind a vote, so they stay converged on the
 //               symbol path however their blocks are cut.  Four warps per SM: a lane's hot tables take
 //               1.7 KB of shared memory, interleaved with those of the other lanes of its warp;
 //   (host)      the chain decides which chunks continue the stream (tdg_gzchain.h);
+//   gz_expand   one WARP per accepted chunk turns its tokens into 16-bit symbols: a byte, or -- for
+//               a reference into the unknown 32 KiB before the chunk -- the marker 256 + index;
 //   gz_ptr_*    the 32 KiB in front of every accepted chunk, all chunks at once: every entry is a
 //               byte or a pointer into the window before, and log2(chunks) passes of pointer
 //               jumping leave bytes only;
@@ -40,8 +43,8 @@ namespace gzd {
 constexpr int DEC_THREADS = 32 * TDG_GZ_WARPS;       // lanes (= chunks) per CTA of gz_decode, one CTA per SM
 constexpr size_t DEC_SMEM = (size_t)DEC_THREADS * gzl::LANE_U16 * 2;
 constexpr int SCAN_WARPS = 8;
-constexpr size_t SCAN_SMEM = (size_t)SCAN_WARPS * gzl::LANE_U16 * 2;
-constexpr uint32_t MAXC = 2;                         // block starts the scan keeps per chunk
+constexpr size_t SCAN_SMEM = (size_t)SCAN_WARPS * 32 * gzl::VAL_U16 * 2;     // 32 validator slices per warp
+constexpr uint32_t MAXC = 1;                         // block starts the scan keeps per chunk (a second one would cost a second block's worth of scanning)
 constexpr uint32_t PIECE = 16384;                    // bytes of text per CTA of gz_resolve
 constexpr int RES_THREADS = 256;
 constexpr uint32_t SUB = PIECE / RES_THREADS;        // bytes per thread in the CRC
@@ -59,7 +62,7 @@ struct RoundArgs {
     uint32_t hist;
     uint32_t symcap;
     uint32_t *cand, *ncand;      // [nchunks][MAXC], [nchunks]
-    uint16_t *syms;              // [nchunks][symcap]
+    uint16_t *syms;              // [nchunks][symcap] token slots
     gzl::Meta *meta;
     const uint8_t *kraft3;
     uint16_t *cold;              // [nchunks][COLD_U16]: a lane's list of long-code symbols (the scan's warps use it first)
@@ -73,35 +76,54 @@ __device__ __forceinline__ uint64_t nominal_rel(const RoundArgs &a, uint64_t k)
 
 __global__ void __launch_bounds__(SCAN_WARPS * 32) gz_scan(const RoundArgs a)
 {
-    extern __shared__ uint16_t s_lane[];
+    extern __shared__ uint16_t s_lane[];                         // per warp: 32 interleaved validator slices
     __shared__ uint8_t s_kraft[512];
+    __shared__ uint32_t s_queue[SCAN_WARPS][64];                 // positions that passed the cheap test, in order
     for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) s_kraft[i] = a.kraft3[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t k = blockIdx.x * SCAN_WARPS + warp + 1;       // chunk 0 starts at a known bit
     if (k >= a.nchunks) return;
     const uint64_t from = nominal_rel(a, k), to = nominal_rel(a, k + 1);
-    const gzl::Mem<1> m{s_lane + warp * gzl::LANE_U16, a.cold + ((size_t)blockIdx.x * SCAN_WARPS + warp) * gzl::COLD_U16};
-    uint32_t n = 0;
-    for (uint64_t base = from; base < to && n < MAXC; base += 32) {
-        const uint64_t idx = base >> 5;                          // `from` is a multiple of 128 bits
-        const uint32_t w0 = a.in[idx], w1 = a.in[idx + 1], w2 = a.in[idx + 2], w3 = a.in[idx + 3];
-        const uint64_t lo64 = (uint64_t)w1 << 32 | w0, hi64 = (uint64_t)w3 << 32 | w2;
-        const uint64_t lo = lane ? (lo64 >> lane | hi64 << (64 - lane)) : lo64;
-        const uint32_t hi = (uint32_t)(hi64 >> lane);
-        const uint64_t p = base + lane;
-        const bool ok = p < to && gzl::quick_test(lo, hi, s_kraft);
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, ok);
-        while (mask && n < MAXC) {
-            const uint32_t l = (uint32_t)__ffs((int)mask) - 1u;
-            mask &= mask - 1u;
+    const gzl::Mem<32> m{s_lane + (size_t)warp * gzl::VAL_U16 * 32 + lane * 2, nullptr};
+    uint32_t *queue = s_queue[warp];
+    uint32_t qn = 0, n = 0;
+    // About one position in 300 passes the cheap test and a full look at one costs a lane ~2,000
+    // instructions: the positions are queued and looked at 32 at a time, one per lane.
+    for (uint64_t base = from; n < MAXC; base += 32) {
+        const bool more = base < to;
+        if (more) {
+            const uint64_t idx = base >> 5;                      // `from` is a multiple of 128 bits
+            const uint32_t w0 = a.in[idx], w1 = a.in[idx + 1], w2 = a.in[idx + 2], w3 = a.in[idx + 3];
+            const uint64_t lo64 = (uint64_t)w1 << 32 | w0, hi64 = (uint64_t)w3 << 32 | w2;
+            const uint64_t lo = lane ? (lo64 >> lane | hi64 << (64 - lane)) : lo64;
+            const uint32_t hi = (uint32_t)(hi64 >> lane);
+            const bool ok = base + lane < to && gzl::quick_test(lo, hi, s_kraft);
+            const uint32_t mask = __ballot_sync(0xFFFFFFFFu, ok);
+            if (ok) queue[qn + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(base + lane - from);
+            qn += __popc(mask);
+            __syncwarp();
+        }
+        if (qn >= 32 || (!more && qn)) {
+            const uint32_t take = qn < 32 ? qn : 32;
             bool v = false;
-            if (lane == l) v = gzl::header_parses<1>(m, a.in, a.nwords, a.in_bits, p);
-            if (__ballot_sync(0xFFFFFFFFu, v)) {
-                if (lane == 0) a.cand[(size_t)k * MAXC + n] = (uint32_t)(base + l - from);
+            if (lane < take) v = gzl::header_check<32>(m, a.in, a.nwords, a.in_bits, from + queue[lane]);
+            uint32_t good = __ballot_sync(0xFFFFFFFFu, v);
+            while (good && n < MAXC) {
+                const uint32_t l = (uint32_t)__ffs((int)good) - 1u;
+                good &= good - 1u;
+                if (lane == 0) a.cand[(size_t)k * MAXC + n] = queue[l];
                 n++;
             }
+            // drop the positions looked at
+            const uint32_t rest = qn - take;
+            const uint32_t moved = lane < rest ? queue[take + lane] : 0u;
+            __syncwarp();
+            if (lane < rest) queue[lane] = moved;
+            qn = rest;
+            __syncwarp();
         }
+        if (!more && qn == 0) break;
     }
     if (lane == 0) a.ncand[k] = n;
 }
@@ -128,6 +150,63 @@ __global__ void __launch_bounds__(DEC_THREADS) gz_decode(const RoundArgs a)
         r.start_bit += a.base_bit;
         r.end_bit += a.base_bit;
         a.meta[k] = r;
+    }
+}
+
+// Tokens -> symbols, one WARP per accepted chunk.  32 token slots per step: a prefix sum of the
+// lengths places every token; literals are stored at once; the step's matches are copied one after
+// the other, each by the whole warp -- symbol k of a match is the symbol (k mod distance) of the
+// distance symbols in front of it, all of which are written before the match begins, so the 32
+// lanes never wait for each other inside a match (and overlapping matches need no special case).
+struct ExpandArgs {
+    const uint16_t *tok;         // [nchunks][symcap]
+    uint16_t *syms;              // [nchunks][symcap]
+    uint32_t symcap;
+    const uint32_t *ntok;        // [accepted] token slots of each accepted chunk (0: nothing to do)
+    uint32_t accepted;
+};
+constexpr int EXP_WARPS = 8;
+
+__global__ void __launch_bounds__(EXP_WARPS * 32) gz_expand(const ExpandArgs a)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t k = blockIdx.x * EXP_WARPS + (threadIdx.x >> 5);
+    if (k >= a.accepted) return;
+    const uint32_t ntok = a.ntok[k];
+    const uint16_t *tok = a.tok + (size_t)k * a.symcap;
+    uint16_t *sym = a.syms + (size_t)k * a.symcap;
+    uint32_t o = 0;
+    for (uint32_t base = 0; base < ntok; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t s = i < ntok ? tok[i] : (uint32_t)gzl::T_DIST;           // beyond the end: a slot of no length
+        const uint32_t nx = i + 1 < ntok ? tok[i + 1] : 0u;
+        const bool lit = s < 256u, head = (s & 0xC000u) == gzl::T_LEN;
+        const uint32_t len = lit ? 1u : (head ? (s & 0x1FFu) : 0u);
+        uint32_t off = len;                                                     // inclusive prefix sum
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, off, d);
+            if ((int)lane >= d) off += v;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, off, 31);
+        off = o + off - len;
+        if (lit) sym[off] = (uint16_t)s;
+        uint32_t mm = __ballot_sync(0xFFFFFFFFu, head);
+        while (mm) {
+            const int src = __ffs((int)mm) - 1;
+            mm &= mm - 1u;
+            const uint32_t mlen = __shfl_sync(0xFFFFFFFFu, len, src);
+            const uint32_t dist = (__shfl_sync(0xFFFFFFFFu, nx, src) & 0x7FFFu) + 1u;
+            const uint32_t dst = __shfl_sync(0xFFFFFFFFu, off, src);
+            __syncwarp();                                                       // what the lanes stored so far is visible
+            const int32_t from = (int32_t)dst - (int32_t)dist;
+            for (uint32_t kk = lane; kk < mlen; kk += 32) {
+                const int32_t j = from + (int32_t)(kk < dist ? kk : kk % dist);
+                sym[dst + kk] = j < 0 ? (uint16_t)(256 + gzl::WIN + j) : sym[j];
+            }
+        }
+        __syncwarp();
+        o += total;
     }
 }
 

@@ -57,6 +57,13 @@ constexpr uint32_t C_LSORT = 0;                            // 288
 constexpr uint32_t C_DSORT = 288;                          // 32
 constexpr uint32_t COLD_U16 = 320;
 
+// What a lane writes: TOKENS, 16 bits each -- a literal (0..255), or a match as two slots,
+// T_LEN | length (3..258) followed by T_DIST | (distance - 1).  A lane never reads what it has
+// produced, so its steps cost instruction latency only; copying the matches (whose sources are
+// mostly out of L2: thousands of lanes times 32 KiB of history each) is left to gz_expand, where a
+// warp per chunk has all the memory-level parallelism a lane lacks.
+constexpr uint16_t T_LEN = 0x4000, T_DIST = 0x8000;
+
 constexpr uint16_t E_LONG = 0x8000;           // primary entry: the code is longer than the root
 // other entries: symbol << 4 | code length; 0 = no code here
 
@@ -74,7 +81,7 @@ struct Meta {                 // what a lane reports about its chunk
     uint32_t out_len;
     uint32_t flags;
     uint32_t min_pre;         // smallest index into the 32 KiB before the chunk that a match named directly (WIN: none)
-    uint32_t tried;           // candidates looked at (diagnostics)
+    uint32_t ntok;            // token slots that hold those out_len symbols (expand_tokens)
 };
 
 template <int STRIDE>
@@ -160,7 +167,7 @@ TDG_GZ_HD uint32_t bitrev(uint32_t c, int len)
 // value and the next slot in the long-code list, per length): one pass over the symbols.
 template <int STRIDE>
 TDG_GZ_FN bool build_code(const Mem<STRIDE> m, uint32_t o_lens, uint32_t first, uint32_t n, int root, uint32_t o_tab,
-                          uint32_t o_sort, uint32_t o_cnt, uint32_t o_scr, bool allow_single)
+                          uint32_t o_sort, uint32_t o_cnt, uint32_t o_scr, bool allow_single, bool check_only = false)
 {
     for (uint32_t l = 0; l < 16; l++) m.h(o_cnt + l) = 0;
     for (uint32_t i = 0; i < n; i++) m.h(o_cnt + m.nib(o_lens, first + i))++;
@@ -175,6 +182,7 @@ TDG_GZ_FN bool build_code(const Mem<STRIDE> m, uint32_t o_lens, uint32_t first, 
         if (left < 0) return false;
     }
     if (max > 0 && left > 0 && !(allow_single && max == 1)) return false;
+    if (check_only) return true;                             // (the scan only asks whether the header is one)
     if (left > 0)                                            // an incomplete (or empty) set leaves holes: "no code here"
         for (uint32_t j = 0; j < psize; j++) m.h(o_tab + j) = 0;
     if (max == 0) return true;
@@ -245,9 +253,10 @@ struct Lane {
     Bits bits;
     uint64_t in_bits;         // valid bits of the buffer
     uint64_t wmax;            // a word index beyond this means the input is exhausted for sure
-    uint16_t *out;
-    uint32_t cap;             // symbols `out` can hold
+    uint16_t *out;            // token slots
+    uint32_t cap;             // symbols the chunk may produce (token slots never outnumber symbols)
     uint32_t o;               // symbols produced
+    uint32_t t;               // token slots written
     uint32_t hist;            // how far back a distance may reach beyond o (WIN: unknown prehistory)
     uint32_t min_pre;
     bool fixed_loaded;
@@ -263,7 +272,7 @@ struct Lane {
     bool final_block;
     uint32_t stored_left, blocks_done;
     uint64_t start, last_bit;
-    uint32_t last_o;
+    uint32_t last_o, last_t;
     Meta *r;
 
     TDG_GZ_HD bool exhausted() const { return bits.pos() > in_bits; }
@@ -284,6 +293,7 @@ struct Lane {
         out = dst;
         cap = dst_cap;
         o = 0;
+        t = 0;
         hist = WIN;
         min_pre = WIN;
         fixed_loaded = false;
@@ -299,14 +309,14 @@ struct Lane {
         final_block = false;
         stored_left = blocks_done = 0;
         start = last_bit = base;
-        last_o = 0;
+        last_o = last_t = 0;
         r = report;
         r->start_bit = base;
         r->end_bit = base;
         r->out_len = 0;
         r->flags = 0;
         r->min_pre = WIN;
-        r->tried = 0;
+        r->ntok = 0;
     }
 
     TDG_GZ_FN void finish(uint32_t flags)
@@ -314,6 +324,7 @@ struct Lane {
         r->start_bit = start;
         r->end_bit = last_bit;
         r->out_len = last_o;
+        r->ntok = last_t;
         r->flags = F_FOUND | flags;
         r->min_pre = min_pre;
         state = S_DONE;
@@ -337,7 +348,7 @@ struct Lane {
     }
 
     // dynamic block header at the reader's position (behind the three block bits)
-    TDG_GZ_FN bool read_dynamic()
+    TDG_GZ_FN bool read_dynamic(bool check_only = false)
     {
         bits.fill();
         const uint32_t hlit = bits.take(5) + 257, hdist = bits.take(5) + 1, hclen = bits.take(4) + 4;
@@ -358,6 +369,9 @@ struct Lane {
         const uint32_t total = hlit + hdist;
         uint32_t i = 0;
         uint32_t prev = 0;
+        // Kraft sums of the two codes as their lengths arrive (in units of 2^-15): random bits
+        // over-subscribe a code within a few dozen lengths, long before the header has been read
+        uint32_t kraft_l = 0, kraft_d = 0;
         while (i < total) {
             bits.fill();
             const uint32_t e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << PRE_ROOT) - 1u)));
@@ -366,6 +380,11 @@ struct Lane {
             const uint32_t sym = e >> 4;
             if (sym < 16) {
                 m.set_nib(O_LENS, i, sym);
+                if (sym) {
+                    if (i < hlit) kraft_l += 32768u >> sym;
+                    else kraft_d += 32768u >> sym;
+                    if (kraft_l > 32768u || kraft_d > 32768u) return false;
+                }
                 prev = sym;
                 i++;
                 continue;
@@ -381,13 +400,20 @@ struct Lane {
                 rep = 11 + bits.take(7);
             }
             if (i + rep > total) return false;
-            while (rep--) m.set_nib(O_LENS, i++, val);
+            while (rep--) {
+                if (val) {
+                    if (i < hlit) kraft_l += 32768u >> val;
+                    else kraft_d += 32768u >> val;
+                }
+                m.set_nib(O_LENS, i++, val);
+            }
+            if (kraft_l > 32768u || kraft_d > 32768u) return false;
             prev = val;
         }
         if (exhausted()) return false;
         if (m.nib(O_LENS, 256) == 0) return false;          // no end-of-block code
-        if (!build_code<STRIDE>(m, O_LENS, 0, hlit, LIT_ROOT, O_LIT, C_LSORT, O_LCNT, O_DIST, true)) return false;
-        if (!build_code<STRIDE>(m, O_LENS, hlit, hdist, DIST_ROOT, O_DIST, C_DSORT, O_DCNT, O_LENS, true)) return false;
+        if (!build_code<STRIDE>(m, O_LENS, 0, hlit, LIT_ROOT, O_LIT, C_LSORT, O_LCNT, O_DIST, true, check_only)) return false;
+        if (!build_code<STRIDE>(m, O_LENS, hlit, hdist, DIST_ROOT, O_DIST, C_DSORT, O_DCNT, O_LENS, true, check_only)) return false;
         fixed_loaded = false;
         return true;
     }
@@ -402,6 +428,7 @@ struct Lane {
         if (final_block) {
             last_bit = bits.pos();
             last_o = o;
+            last_t = t;
             finish(F_FINAL);
             return;
         }
@@ -425,12 +452,12 @@ struct Lane {
                 return;
             }
             start = search_base + cand[c++];
-            r->tried = c;
             hist = WIN;
             probation = true;
         }
         bits.seek(start);
         o = 0;
+        t = 0;
         min_pre = WIN;
         fixed_loaded = false;
         blocks_done = 0;
@@ -444,6 +471,7 @@ struct Lane {
         const uint64_t bp = bits.pos();
         last_bit = bp;
         last_o = o;
+        last_t = t;
         if (bp + 3 > in_bits) {
             fail(F_INPUT);
             return;
@@ -514,7 +542,8 @@ struct Lane {
         stored_left -= n;
         while (n--) {
             bits.fill();
-            out[o++] = (uint16_t)bits.take(8);
+            out[t++] = (uint16_t)bits.take(8);
+            o++;
         }
         if (stored_left == 0) block_end();
     }
@@ -540,12 +569,14 @@ struct Lane {
         bits.drop((int)(e & 15u));
         const uint32_t sym = e >> 4;
         if (sym < 256) {
-            out[o++] = (uint16_t)sym;
+            out[t++] = (uint16_t)sym;
+            o++;
             // a second literal without another fill (at least 17 bits are left)
             e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << LIT_ROOT) - 1u)));
             if (e == 0 || e >= (256u << 4)) return;          // not a short literal code: the next step looks again
             bits.drop((int)(e & 15u));
-            out[o++] = (uint16_t)(e >> 4);
+            out[t++] = (uint16_t)(e >> 4);
+            o++;
             return;
         }
         if (sym == 256) {
@@ -593,63 +624,10 @@ struct Lane {
             const uint32_t pre = WIN - (d - o);
             if (pre < min_pre) min_pre = pre;
         }
-        copy_match(len, d);
-    }
-
-    // out[o .. o + len) = the len symbols that start d symbols back.  Symbol j of the stream seen
-    // from this chunk: j < 0 is prehistory -> marker 256 + (WIN + j).  Sources are read eight at a
-    // time before anything is written (a lane's load-store-load chain through L2 is what a
-    // symbol-by-symbol copy costs); a distance below eight repeats a pattern held in registers.
-    TDG_GZ_HD uint16_t sym_at(int32_t j) const { return j < 0 ? (uint16_t)(256 + WIN + j) : out[j]; }
-    TDG_GZ_FN void copy_match(uint32_t len, uint32_t d)
-    {
-        int32_t j = (int32_t)o - (int32_t)d;
-        uint16_t *q = out + o;
+        out[t] = (uint16_t)(T_LEN | len);
+        out[t + 1] = (uint16_t)(T_DIST | (d - 1));
+        t += 2;
         o += len;
-        if (d >= 8 && j >= 0) {
-            // the common case: the source is text this lane has written, eight symbols and more back
-            const uint16_t *p = out + j;
-            while (len >= 8) {
-                const uint16_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4], a5 = p[5], a6 = p[6], a7 = p[7];
-                q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3; q[4] = a4; q[5] = a5; q[6] = a6; q[7] = a7;
-                q += 8;
-                p += 8;
-                len -= 8;
-            }
-            if (len >= 4) {
-                const uint16_t a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
-                q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3;
-                q += 4;
-                p += 4;
-                len -= 4;
-            }
-            if (len) {
-                const uint16_t a0 = p[0], a1 = len > 1 ? p[1] : (uint16_t)0, a2 = len > 2 ? p[2] : (uint16_t)0;
-                q[0] = a0;
-                if (len > 1) q[1] = a1;
-                if (len > 2) q[2] = a2;
-            }
-            return;
-        }
-        if (d >= 8) {
-            for (uint32_t k = 0; k < len; k++) q[k] = sym_at(j + (int32_t)k);      // (d >= len or not: sources lie 8+ back, in order)
-            return;
-        }
-        // a short distance repeats a pattern: its d symbols, packed 16 bits each
-        uint64_t lo = 0, hi = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < 7; k++) {
-            if (k < d) {
-                const uint64_t v = sym_at(j + (int32_t)k);
-                if (k < 4) lo |= v << (16 * k);
-                else hi |= v << (16 * (k - 4));
-            }
-        }
-        uint32_t t = 0;
-        for (uint32_t k = 0; k < len; k++) {
-            q[k] = (uint16_t)(t < 4 ? lo >> (16 * t) : hi >> (16 * (t - 4)));
-            if (++t == d) t = 0;
-        }
     }
 
     TDG_GZ_FN void step()
@@ -690,6 +668,25 @@ inline void make_kraft3(uint8_t *t)
     }
 }
 
+// Tokens -> symbols, one after the other (the CPU harness; on the device gz_expand does this with
+// a warp per chunk).  sym[j] for j < 0 is the unknown text before the chunk: marker 256 + (WIN + j).
+TDG_GZ_FN inline uint32_t expand_tokens(const uint16_t *tok, uint32_t ntok, uint16_t *sym)
+{
+    uint32_t o = 0;
+    for (uint32_t i = 0; i < ntok; i++) {
+        const uint16_t s = tok[i];
+        if (s < 256) {
+            sym[o++] = s;
+            continue;
+        }
+        const uint32_t len = s & 0x1FFu, d = (uint32_t)(tok[++i] & 0x7FFFu) + 1u;
+        int32_t j = (int32_t)o - (int32_t)d;
+        for (uint32_t k = 0; k < len; k++, j++) sym[o + k] = j < 0 ? (uint16_t)(256 + WIN + j) : sym[j];
+        o += len;
+    }
+    return o;
+}
+
 // Does a dynamic block header parse at `bit` (both Huffman codes valid, an end-of-block code
 // present)?  The scan's second test for a position that passed quick_test.
 template <int STRIDE>
@@ -701,7 +698,86 @@ TDG_GZ_FN bool header_parses(Mem<STRIDE> m, const uint32_t *in, uint64_t nwords,
     z.bits.seek(bit);
     z.bits.fill();
     z.bits.drop(3);
-    return z.read_dynamic();
+    return z.read_dynamic(true);
+}
+
+// The scan's second test, lean enough for 32 candidates at a time (one per lane, 384 bytes of
+// interleaved shared memory each): does a dynamic block header parse at `bit`?  Same verdict as
+// Lane::read_dynamic, but nothing is kept -- the code-length code gets its table, the lengths it
+// decodes are only summed up (Kraft sums of the two codes as they arrive: random bits
+// over-subscribe a code within a few dozen lengths), and the end-of-block code must exist.
+constexpr uint32_t V_TAB = 0;                 // 128: table of the code-length code
+constexpr uint32_t V_CNT = 128;               // 16
+constexpr uint32_t V_LENS = 144;              // 19 x 4 bits (10 units), padded to 16
+constexpr uint32_t V_SCR = 160;               // 32
+constexpr uint32_t VAL_U16 = 192;
+
+template <int STRIDE>
+TDG_GZ_FN bool header_check(const Mem<STRIDE> m, const uint32_t *in, uint64_t nwords, uint64_t in_bits, uint64_t bit)
+{
+    Bits bits;
+    bits.in = in;
+    bits.nwords = nwords;
+    bits.seek(bit);
+    bits.fill();
+    bits.drop(3);
+    bits.fill();
+    const uint32_t hlit = bits.take(5) + 257, hdist = bits.take(5) + 1, hclen = bits.take(4) + 4;
+    if (hlit > 286 || hdist > 30) return false;
+    const uint64_t ord0 = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 | 6ull << 35 |
+                          10ull << 40 | 5ull << 45 | 11ull << 50 | 4ull << 55;
+    const uint64_t ord1 = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
+    for (uint32_t i = 0; i < 10; i++) m.b(V_LENS, i) = 0;
+    for (uint32_t i = 0; i < hclen; i++) {
+        bits.fill();
+        const uint32_t sym = (uint32_t)((i < 12 ? ord0 >> (5 * i) : ord1 >> (5 * (i - 12))) & 31u);
+        m.set_nib(V_LENS, sym, bits.take(3));
+    }
+    if (!build_code<STRIDE>(m, V_LENS, 0, 19, PRE_ROOT, V_TAB, 0, V_CNT, V_SCR, false)) return false;
+    const uint32_t total = hlit + hdist;
+    uint32_t i = 0, prev = 0, eob = 0;
+    uint32_t kraft_l = 0, kraft_d = 0, codes_l = 0, codes_d = 0, max_l = 0, max_d = 0;
+    while (i < total) {
+        bits.fill();
+        const uint32_t e = m.h(V_TAB + ((uint32_t)bits.buf & ((1u << PRE_ROOT) - 1u)));
+        if (e == 0 || (e & E_LONG)) return false;
+        bits.drop((int)(e & 15u));
+        const uint32_t sym = e >> 4;
+        uint32_t rep = 1, val = sym;
+        if (sym >= 16) {
+            val = 0;
+            if (sym == 16) {
+                if (i == 0) return false;
+                val = prev;
+                rep = 3 + bits.take(2);
+            } else if (sym == 17) {
+                rep = 3 + bits.take(3);
+            } else {
+                rep = 11 + bits.take(7);
+            }
+            if (i + rep > total) return false;
+        }
+        prev = val;
+        if (val) {
+            // how many of the rep lengths fall to the literal/length code
+            const uint32_t to_l = i >= hlit ? 0u : (i + rep <= hlit ? rep : hlit - i);
+            kraft_l += to_l * (32768u >> val);
+            kraft_d += (rep - to_l) * (32768u >> val);
+            if (kraft_l > 32768u || kraft_d > 32768u) return false;
+            codes_l += to_l;
+            codes_d += rep - to_l;
+            if (to_l && val > max_l) max_l = val;
+            if (rep > to_l && val > max_d) max_d = val;
+            if (i <= 256 && 256 < i + rep) eob = val;
+        }
+        i += rep;
+    }
+    if (bits.pos() > in_bits) return false;
+    if (eob == 0) return false;
+    // an incomplete code is accepted only when it is a single 1-bit code (zlib's inflate_table)
+    if (kraft_l < 32768u && max_l != 1) return false;
+    if (codes_d && kraft_d < 32768u && max_d != 1) return false;
+    return true;
 }
 
 // A lane's whole job for its chunk, one call (the CPU harness; the kernel steps its lanes itself):

@@ -29,7 +29,7 @@ void scan(const std::vector<uint8_t> &buf, uint64_t nwords, uint64_t in_bits, ui
         const uint64_t lo = sh ? (a >> sh | b << (64 - sh)) : a;
         const uint32_t hi = (uint32_t)(b >> sh);
         if (!gzl::quick_test(lo, hi, kraft3)) continue;
-        if (gzl::header_parses<1>(gzl::Mem<1>{mem, cold}, (const uint32_t *)buf.data(), nwords, in_bits, p)) cand.push_back((uint32_t)(p - from));
+        if (gzl::header_check<1>(gzl::Mem<1>{mem, cold}, (const uint32_t *)buf.data(), nwords, in_bits, p)) cand.push_back((uint32_t)(p - from));
     }
 }
 
@@ -54,6 +54,7 @@ long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_ch
     std::vector<uint8_t> window(gzl::WIN, 0);
     std::vector<uint16_t> mem(gzl::LANE_U16), cold(gzl::COLD_U16);
     std::vector<std::vector<uint16_t>> syms;
+    std::vector<uint16_t> toks;
     std::vector<gzl::Meta> meta;
     std::vector<uint32_t> cand;
     size_t total = 0;
@@ -69,21 +70,23 @@ long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_ch
         meta.assign(r.nchunks, gzl::Meta());
         for (uint32_t k = 0; k < r.nchunks; k++) {
             syms[k].resize(symcap);
+            toks.resize(symcap);
             gzl::Mem<1> m{mem.data(), cold.data()};
             const uint64_t stop = r.nominal(k + 1, n) - base_bit;
             if (k == 0) {
                 gzl::run_chunk<1>(m, (const uint32_t *)buf.data(), nwords, (uint64_t)nb * 8, true, r.pos_bit - base_bit, nullptr, 0,
-                                  stop, r.hist, syms[k].data(), symcap, meta[k]);
+                                  stop, r.hist, toks.data(), symcap, meta[k]);
             } else {
                 const uint64_t from = r.nominal(k, n) - base_bit;
                 const uint64_t to = std::min<uint64_t>(from + (uint64_t)search_bytes * 8, stop);
                 scan(buf, nwords, (uint64_t)nb * 8, from, to, kraft3, mem.data(), cold.data(), cand, 2);
                 gzl::run_chunk<1>(m, (const uint32_t *)buf.data(), nwords, (uint64_t)nb * 8, false, from, cand.data(),
-                                  (uint32_t)cand.size(), stop, 0, syms[k].data(), symcap, meta[k]);
+                                  (uint32_t)cand.size(), stop, 0, toks.data(), symcap, meta[k]);
             }
+            if (gzl::expand_tokens(toks.data(), meta[k].ntok, syms[k].data()) != meta[k].out_len) return -50;
             meta[k].start_bit += base_bit;
             meta[k].end_bit += base_bit;
-            info[3] += meta[k].tried;
+            info[3] += meta[k].ntok;
             info[5]++;
         }
         const gzc::Outcome o = st.chain(r, meta.data());
