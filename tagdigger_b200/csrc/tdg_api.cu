@@ -779,7 +779,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         CK(cudaStreamSynchronize(ctx->stream));
         auto t3 = now();
         // ---- which chunks continue the stream
-        const gzc::Outcome o = st.chain(r, meta);
+        const gzc::Outcome o = st.chain(r, meta, symcap);
         uint64_t text_len = o.text_off.back();
         uint32_t text_crc = 0;
         auto t4 = t3, t5 = t3;
@@ -807,6 +807,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             {
                 std::vector<uint32_t> ntok(o.accepted);
                 for (uint32_t k = 0; k < o.accepted; k++) ntok[k] = o.lens[k] ? meta[k].ntok : 0u;
+                for (const gzc::Repair &rp : o.repairs) ntok[rp.chunk] = 0;          // the host made these chunks' symbols
                 CK(cudaMemcpyAsync(ctx->gz_ntok.p, ntok.data(), ntok.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));      // (ntok is a local)
                 gzd::ExpandArgs ea;
@@ -818,9 +819,13 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
                 gzd::gz_expand<<<(o.accepted + gzd::EXP_WARPS - 1) / gzd::EXP_WARPS, gzd::EXP_WARPS * 32, 0, ctx->stream>>>(ea);
                 CK(cudaGetLastError());
                 ctx->launches++;
+                for (const gzc::Repair &rp : o.repairs)
+                    if (!rp.syms.empty())
+                        CK(cudaMemcpyAsync((uint16_t *)ctx->gz_sym2.p + (size_t)rp.chunk * symcap, rp.syms.data(), rp.syms.size() * 2,
+                                           cudaMemcpyHostToDevice, ctx->stream));
                 if (debug) {
                     CK(cudaStreamSynchronize(ctx->stream));
-                    fprintf(stderr, "gzdev expand: %.1f ms\n", ms(t3, now()));
+                    fprintf(stderr, "gzdev expand: %.1f ms, %zu chunks made by the host\n", ms(t3, now()), o.repairs.size());
                 }
             }
             CK(cudaMemcpyAsync(ctx->gz_offs.p, o.text_off.data(), o.text_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "tdg_gzlane.h"
@@ -27,6 +28,58 @@
 
 namespace tdg {
 namespace gzc {
+
+// A chunk the lanes could not deliver (no block start confirmed in it, or one that was not the
+// stream's) does not end the round: the HOST inflates it -- one chunk is half a millisecond of
+// zlib-class work here, and a lane's worth of waiting (tens of milliseconds) on the device --
+// into the same 16-bit symbols, from the bit the lane before it stopped at to the boundary the
+// next lane must have started from.
+struct Repair {
+    uint32_t chunk;
+    std::vector<uint16_t> syms;
+};
+constexpr size_t MAX_REPAIRS = 16;
+
+// symbols of the blocks from pos_bit up to the first boundary at or behind stop_bit that stands in
+// front of a non-final dynamic block (the lanes' stopping rule); false when that cannot be done
+// here (invalid data, the end of a member, the end of the input)
+inline bool host_gap(const uint8_t *in, size_t size, uint64_t pos_bit, uint64_t stop_bit, uint64_t hist, std::vector<uint16_t> &syms,
+                     uint64_t &end_bit)
+{
+    std::unique_ptr<pgz::Inflater> z(new pgz::Inflater());
+    pgz::Chunk c;
+    z->in = in;
+    z->in_size = size;
+    c.prepare(pgz::WIN + ((size_t)1 << 20), true);
+    c.unknown_window();
+    z->out = c.buf.data();
+    z->cap = c.buf.size();
+    z->seek(pos_bit);
+    z->o = pgz::WIN;
+    z->member_start = pgz::WIN - (size_t)std::min<uint64_t>(pgz::WIN, hist);
+    uint64_t stop = stop_bit;
+    for (;;) {
+        const pgz::Status st = z->run(stop);
+        if (st == pgz::ST_SPACE) {
+            if (c.buf.size() > ((size_t)64 << 20)) return false;
+            c.buf.resize(c.buf.size() * 2);
+            z->out = c.buf.data();
+            z->cap = c.buf.size();
+            continue;
+        }
+        if (st != pgz::ST_STOP) return false;
+        // at a boundary: is the next block one a lane's scan accepts?
+        const uint64_t bp = z->bitpos();
+        if (bp + 3 > (uint64_t)size * 8) return false;
+        const uint32_t h = (uint32_t)((in[bp >> 3] | (uint32_t)in[(bp >> 3) + 1 < size ? (bp >> 3) + 1 : (bp >> 3)] << 8) >> (bp & 7)) & 7u;
+        if (h == 4u) {
+            end_bit = bp;
+            syms.assign(c.buf.data() + pgz::WIN, c.buf.data() + z->o);
+            return true;
+        }
+        stop = bp + 1;                                       // run through this block as well
+    }
+}
 
 struct Round {
     size_t chunk = 0;          // nominal chunk size in bytes (multiple of 16)
@@ -44,6 +97,7 @@ struct Outcome {
     std::vector<uint64_t> text_off;    // [accepted + 1] offsets of their bytes in the round's text
     std::vector<uint32_t> lens;        // [accepted] symbols each of them contributes (0: the lane before ran through the whole chunk)
     uint64_t end_bit = 0;              // where the last of them stopped
+    std::vector<Repair> repairs;       // chunks whose symbols the host made (their lens entry says how many)
     bool member_end = false;           // the last accepted chunk ends a member (trailer follows at end_bit)
     bool handover = false;             // the host reader must take over behind the accepted chunks
     const char *why = "";
@@ -91,7 +145,7 @@ struct Stream {
     }
 
     // meta[k]: lane k's report with ABSOLUTE bit positions
-    Outcome chain(const Round &r, const gzl::Meta *meta) const
+    Outcome chain(const Round &r, const gzl::Meta *meta, size_t sym_cap) const
     {
         Outcome o;
         o.text_off.push_back(0);
@@ -107,8 +161,23 @@ struct Stream {
                 o.lens.push_back(0);
                 continue;
             }
-            if (!(c.flags & gzl::F_FOUND)) break;
-            if (c.start_bit != pos) break;
+            if (!(c.flags & gzl::F_FOUND) || c.start_bit != pos) {
+                // the lane of this chunk did not start where the stream is: the host fills in
+                if (o.repairs.size() >= MAX_REPAIRS || k == 0) break;
+                Repair rp;
+                rp.chunk = k;
+                uint64_t e = 0;
+                if (!host_gap(in, size, pos, r.nominal(k + 1, size), h, rp.syms, e)) break;
+                if (rp.syms.size() > sym_cap) break;
+                o.accepted = k + 1;
+                o.text_off.push_back(o.text_off.back() + rp.syms.size());
+                o.lens.push_back((uint32_t)rp.syms.size());
+                h += rp.syms.size();
+                pos = e;
+                o.end_bit = pos;
+                o.repairs.push_back(std::move(rp));
+                continue;
+            }
             if (k > 0 && c.min_pre < gzl::WIN - std::min<uint64_t>(gzl::WIN, h)) {
                 // a distance reaches in front of its member: zlib calls that invalid
                 o.handover = true;

@@ -20,19 +20,19 @@ def build(force=False):
     return _LIB
 
 
-def inflate(blob, chunk=1 << 16, max_chunks=64, search_bytes=1 << 15, symcap=None, cap=None):
+def inflate(blob, chunk=1 << 16, max_chunks=64, search_bytes=1 << 15, symcap=None, cap=None, blind_every=0):
     """(bytes or None, code, info dict).  code >= 0: everything was inflated."""
     L = ctypes.CDLL(build())
     L.gzl_inflate.restype = ctypes.c_longlong
     L.gzl_inflate.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint32,
-                              ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+                              ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32]
     symcap = symcap or 8 * chunk
     cap = cap or max(1 << 20, 40 * len(blob) + (1 << 20))
     out = np.empty(cap, dtype=np.uint8)
     info = np.zeros(6, dtype=np.int64)
     why = ctypes.create_string_buffer(128)
-    n = L.gzl_inflate(blob, len(blob), chunk, max_chunks, search_bytes, symcap, out.ctypes.data, cap, info.ctypes.data, why, 128)
-    d = {"rounds": int(info[0]), "accepted": int(info[1]), "handover": int(info[2]), "tried": int(info[3]),
+    n = L.gzl_inflate(blob, len(blob), chunk, max_chunks, search_bytes, symcap, out.ctypes.data, cap, info.ctypes.data, why, 128, blind_every)
+    d = {"rounds": int(info[0]), "accepted": int(info[1]), "handover": int(info[2]), "repairs": int(info[3]),
          "delivered": int(info[4]), "chunks": int(info[5]), "why": why.value.decode()}
     if n >= 0:
         return out[:n].tobytes(), int(n), d

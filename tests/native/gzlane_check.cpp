@@ -41,9 +41,9 @@ extern "C" {
 // written to out, or: -10 first header not handled, -2 CRC / length mismatch, -1 the stream needs
 // zlib (out holds the bytes delivered so far: info[4]), -100 out too small.
 // info: [0] rounds, [1] chunks accepted, [2] handover (0 none, 1 resumed by tdg_pgz, 2 straight to zlib),
-//       [3] candidates tried, [4] bytes delivered before zlib was asked for, [5] chunks run
+//       [3] chunks the host inflated in place of a lane, [4] bytes delivered before zlib was asked for, [5] chunks run
 long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_chunks, size_t search_bytes, uint32_t symcap,
-                      uint8_t *out, size_t cap, long long *info, char *why, size_t why_cap)
+                      uint8_t *out, size_t cap, long long *info, char *why, size_t why_cap, uint32_t blind_every)
 {
     for (int i = 0; i < 6; i++) info[i] = 0;
     if (why && why_cap) why[0] = 0;
@@ -80,16 +80,20 @@ long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_ch
                 const uint64_t from = r.nominal(k, n) - base_bit;
                 const uint64_t to = std::min<uint64_t>(from + (uint64_t)search_bytes * 8, stop);
                 scan(buf, nwords, (uint64_t)nb * 8, from, to, kraft3, mem.data(), cold.data(), cand, 2);
+                if (blind_every && k % blind_every == 0) cand.clear();          // (test: a lane that finds no start; the host fills in)
                 gzl::run_chunk<1>(m, (const uint32_t *)buf.data(), nwords, (uint64_t)nb * 8, false, from, cand.data(),
                                   (uint32_t)cand.size(), stop, 0, toks.data(), symcap, meta[k]);
             }
             if (gzl::expand_tokens(toks.data(), meta[k].ntok, syms[k].data()) != meta[k].out_len) return -50;
             meta[k].start_bit += base_bit;
             meta[k].end_bit += base_bit;
-            info[3] += meta[k].ntok;
             info[5]++;
         }
-        const gzc::Outcome o = st.chain(r, meta.data());
+        const gzc::Outcome o = st.chain(r, meta.data(), symcap);
+        for (const gzc::Repair &rp : o.repairs) {
+            std::copy(rp.syms.begin(), rp.syms.end(), syms[rp.chunk].begin());
+            info[2]++;
+        }
         info[1] += o.accepted;
         // resolve the accepted chunks against the window handed from chunk to chunk
         const size_t text_at = total;
@@ -111,6 +115,9 @@ long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_ch
         const uint32_t text_crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), out + text_at, (uInt)text_len);
         if (!st.advance(r, o, text_len, text_crc)) return -2;
     }
+    const long long repairs = info[2];
+    info[2] = 0;
+    info[3] = repairs;
     if (st.handover) {
         if (why && why_cap) {
             strncpy(why, st.why, why_cap - 1);

@@ -182,3 +182,15 @@ def test_lane_inflater_random_streams():
         out, n, info = inflate(blob, chunk=chunk, max_chunks=r.randint(1, 40), search_bytes=r.choice((2048, 1 << 15)),
                                cap=len(data) + 100)
         assert n == len(data) and out == data, (case, info)
+
+
+def test_chunks_without_a_confirmed_start_are_inflated_by_the_host():
+    """A lane that finds no block start (or a false one) does not end the round: the host inflates that
+    chunk into the same symbols and the chain goes on."""
+    data = _fastq_like(21, 8 << 20)
+    for level in (1, 6):
+        blob = gzip.compress(data, level)
+        ref = inflate(blob, chunk=1 << 16, max_chunks=200)
+        out, n, info = inflate(blob, chunk=1 << 16, max_chunks=200, blind_every=7)
+        assert n == len(data) and out == data
+        assert info["repairs"] >= 5 and info["rounds"] == ref[2]["rounds"] and info["handover"] == 0, info
