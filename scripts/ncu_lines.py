@@ -47,7 +47,7 @@ def main():
     rep = sys.argv[1]
     ksub = sys.argv[2] if len(sys.argv) > 2 else "count_kernelILb1"
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE,
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + ksub], stdout=subprocess.PIPE,
                          stderr=subprocess.DEVNULL, universal_newlines=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")

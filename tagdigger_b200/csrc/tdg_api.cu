@@ -917,6 +917,24 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
                     r.nchunks, o.accepted, (unsigned long long)text_len, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5),
                     ms(t5, t6), st.handover ? "  -> host reader: " : "", st.handover ? st.why : "");
     }
+    // Large rounds hold tens of GB (16-bit tokens and symbols for 8 x the compressed bytes of up to
+    // 18,944 chunks, the windows, the text): those buffers go back when the file is done; what a
+    // small file needed stays for the next one.
+    {
+        tdg_ctx::Grow *big[] = {&ctx->gz_syms, &ctx->gz_sym2, &ctx->gz_windows, &ctx->gz_text, &ctx->gz_comp, &ctx->gz_comp2};
+        size_t held = 0;
+        for (tdg_ctx::Grow *g : big) held += g->cap;
+        if (held > ((size_t)4 << 30)) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaStreamSynchronize(ctx->copy_stream));
+            for (tdg_ctx::Grow *g : big) {
+                if (g == &ctx->gz_text && carry) continue;                  // the caller still copies the carried bytes out of it
+                if (g->p) cudaFree(g->p);
+                g->p = nullptr;
+                g->cap = 0;
+            }
+        }
+    }
     if (st.handover) {
         ho.active = true;
         ho.to_zlib = st.to_zlib;

@@ -571,12 +571,17 @@ struct Lane {
         if (sym < 256) {
             out[t++] = (uint16_t)sym;
             o++;
-            // a second literal without another fill (at least 17 bits are left)
-            e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << LIT_ROOT) - 1u)));
-            if (e == 0 || e >= (256u << 4)) return;          // not a short literal code: the next step looks again
-            bits.drop((int)(e & 15u));
-            out[t++] = (uint16_t)(e >> 4);
-            o++;
+            // more literals without another fill, while the bits left cover a table index (a code
+            // that is not longer than the root is decided by those bits alone)
+#pragma unroll
+            for (int more = 0; more < 2; more++) {
+                if (bits.cnt < LIT_ROOT) return;
+                e = m.h(O_LIT + ((uint32_t)bits.buf & ((1u << LIT_ROOT) - 1u)));
+                if (e == 0 || e >= (256u << 4)) return;      // not a short literal code: the next step looks again
+                bits.drop((int)(e & 15u));
+                out[t++] = (uint16_t)(e >> 4);
+                o++;
+            }
             return;
         }
         if (sym == 256) {
