@@ -155,6 +155,10 @@ int         tdg_count_lines_device(tdg_ctx *ctx, const void *dev_bytes, size_t n
 int         tdg_count_file(tdg_ctx *ctx, const char *path, int gz,
                            uint64_t reads_limit, uint64_t totals[4]);
 
+/* Frees the working buffers of the device-side gzip feed (tokens, symbols, windows, text: about ten
+ * times the compressed bytes of a round, at most ~12 GB); they are kept between files otherwise. */
+int         tdg_release_scratch(tdg_ctx *ctx);
+
 /* The gzip feed of tdg_count_file by itself (tests, profiling): inflates `path` into the host
  * buffer dst[0..cap) -- rounds on the device, the rest, if any, through the host feeder -- and
  * reports the number of bytes in *n.  info: [0] device rounds, [1] chunks run, [2] chunks accepted,

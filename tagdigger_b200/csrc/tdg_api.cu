@@ -672,8 +672,12 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
     size_t chunk = round_up((map.n + max_chunks - 1) / max_chunks, (size_t)16 << 10);
     chunk = std::min<size_t>(std::max<size_t>(chunk, (size_t)32 << 10), (size_t)128 << 10);
     if (const char *e = getenv("TDG_GZDEV_CHUNK")) chunk = std::max<size_t>(4096, strtoull(e, nullptr, 10) / 16 * 16);
-    uint32_t symcap = (uint32_t)std::max<size_t>(8 * chunk, (size_t)256 << 10);     // symbols a lane may write: 8 x its chunk, and room for a large block
-    if (const char *e = getenv("TDG_GZDEV_SYMCAP")) symcap = (uint32_t)std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
+    // what a lane may produce: symbols up to 8 x its chunk (and room for a large block), token slots up to
+    // 3 x its chunk (literal codes of 4 bits and more: two slots per compressed byte); a chunk that needs more
+    // ends the device feed (the host reader takes over)
+    uint32_t symcap = (uint32_t)std::max<size_t>(8 * chunk, (size_t)256 << 10);
+    uint32_t tokcap = (uint32_t)std::max<size_t>(3 * chunk, (size_t)128 << 10);
+    if (const char *e = getenv("TDG_GZDEV_SYMCAP")) symcap = tokcap = (uint32_t)std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
     const bool debug = getenv("TDG_GZDEV_DEBUG") != nullptr;
     const int threads = gz_io_threads();
     uint8_t *d_tabs = (uint8_t *)ctx->gz_tabs.p;
@@ -725,7 +729,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         }
         pre_valid = false;
         tdg_ctx::Grow &comp = cur ? ctx->gz_comp2 : ctx->gz_comp;
-        if ((rc = grow(ctx, ctx->gz_syms, (size_t)r.nchunks * symcap * 2, false))) return rc;
+        if ((rc = grow(ctx, ctx->gz_syms, (size_t)r.nchunks * tokcap * 2, false))) return rc;
         if ((rc = grow(ctx, ctx->gz_meta, (size_t)r.nchunks * sizeof(gzl::Meta), false))) return rc;
         if ((rc = grow(ctx, ctx->gz_cand, (size_t)r.nchunks * gzd::MAXC * 4, false))) return rc;
         if ((rc = grow(ctx, ctx->gz_ncand, (size_t)r.nchunks * 4, false))) return rc;
@@ -745,6 +749,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         a.base_bit = (uint64_t)r.grid * 8;
         a.hist = r.hist;
         a.symcap = symcap;
+        a.tokcap = tokcap;
         a.cand = (uint32_t *)ctx->gz_cand.p;
         a.ncand = (uint32_t *)ctx->gz_ncand.p;
         a.syms = (uint16_t *)ctx->gz_syms.p;
@@ -768,6 +773,8 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         // While the lanes inflate, this thread reads the bytes the NEXT round will most likely ask
         // for (every chunk accepted: its grid starts where this one's ends) and sends them to the
         // other buffer on the copy stream.
+        double ms_prefetch = 0;
+        const auto tp0 = now();
         if (r.grid + (size_t)r.nchunks * chunk < map.n && r.nchunks == max_chunks) {
             pre_off = r.grid + (size_t)r.nchunks * chunk;
             pre_end = std::min(map.n, pre_off + ((size_t)max_chunks + 1) * chunk);
@@ -775,6 +782,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             if (rc) return rc;
             CK(cudaEventRecord(ctx->gz_pre, ctx->copy_stream));
             pre_valid = true;
+            ms_prefetch = ms(tp0, now());
         }
         CK(cudaStreamSynchronize(ctx->stream));
         auto t3 = now();
@@ -802,7 +810,11 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             }
             CK(cudaMemcpyAsync(ctx->gz_lens.p, o.lens.data(), o.lens.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
             // tokens -> symbols (accepted chunks only)
-            if ((rc = grow(ctx, ctx->gz_sym2, (size_t)r.nchunks * symcap * 2, false))) return rc;
+            // the symbols: as many per chunk as the largest accepted chunk has
+            uint32_t stride = 64;
+            for (uint32_t len : o.lens) stride = std::max(stride, len);
+            stride = (stride + 63u) & ~63u;
+            if ((rc = grow(ctx, ctx->gz_sym2, (size_t)o.accepted * stride * 2, false))) return rc;
             if ((rc = grow(ctx, ctx->gz_ntok, (size_t)o.accepted * 4, false))) return rc;
             {
                 std::vector<uint32_t> ntok(o.accepted);
@@ -813,7 +825,8 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
                 gzd::ExpandArgs ea;
                 ea.tok = a.syms;
                 ea.syms = (uint16_t *)ctx->gz_sym2.p;
-                ea.symcap = symcap;
+                ea.tokcap = tokcap;
+                ea.symcap = stride;
                 ea.ntok = (const uint32_t *)ctx->gz_ntok.p;
                 ea.accepted = o.accepted;
                 gzd::gz_expand<<<(o.accepted + gzd::EXP_WARPS - 1) / gzd::EXP_WARPS, gzd::EXP_WARPS * 32, 0, ctx->stream>>>(ea);
@@ -821,7 +834,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
                 ctx->launches++;
                 for (const gzc::Repair &rp : o.repairs)
                     if (!rp.syms.empty())
-                        CK(cudaMemcpyAsync((uint16_t *)ctx->gz_sym2.p + (size_t)rp.chunk * symcap, rp.syms.data(), rp.syms.size() * 2,
+                        CK(cudaMemcpyAsync((uint16_t *)ctx->gz_sym2.p + (size_t)rp.chunk * stride, rp.syms.data(), rp.syms.size() * 2,
                                            cudaMemcpyHostToDevice, ctx->stream));
                 if (debug) {
                     CK(cudaStreamSynchronize(ctx->stream));
@@ -831,7 +844,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             CK(cudaMemcpyAsync(ctx->gz_offs.p, o.text_off.data(), o.text_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
             gzd::WinArgs w;
             w.syms = (const uint16_t *)ctx->gz_sym2.p;
-            w.symcap = symcap;
+            w.symcap = stride;
             w.out_len = (const uint32_t *)ctx->gz_lens.p;
             w.accepted = o.accepted;
             w.window_in = d_window;
@@ -853,7 +866,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             CK(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
             gzd::ResArgs ra;
             ra.syms = (const uint16_t *)ctx->gz_sym2.p;
-            ra.symcap = symcap;
+            ra.symcap = stride;
             ra.text_off = (const uint64_t *)ctx->gz_offs.p;
             ra.accepted = o.accepted;
             ra.ptrs = (const uint32_t *)ctx->gz_windows.p;
@@ -912,28 +925,11 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             stats->ms_sink += ms(t5, t6);
         }
         if (debug)
-            fprintf(stderr, "gzdev round: %u chunks, %u accepted, %llu bytes of text; upload %.1f scan %.1f decode %.1f windows+resolve %.1f "
-                            "crc/utf8 %.1f sink %.1f ms%s%s\n",
-                    r.nchunks, o.accepted, (unsigned long long)text_len, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, t5),
+            fprintf(stderr, "gzdev round: %u chunks of %zu KiB, %u accepted, %llu bytes of text; upload %.1f%s scan %.1f decode %.1f "
+                            "(host read the next round's bytes meanwhile: %.1f) expand+windows+resolve %.1f crc/utf8 %.1f sink %.1f ms%s%s\n",
+                    r.nchunks, chunk >> 10, o.accepted, (unsigned long long)text_len, ms(t0, t1), prefetched ? " (prefetched)" : "", ms(t1, t2),
+                    ms(t2, t3), ms_prefetch, ms(t3, t4), ms(t4, t5),
                     ms(t5, t6), st.handover ? "  -> host reader: " : "", st.handover ? st.why : "");
-    }
-    // Large rounds hold tens of GB (16-bit tokens and symbols for 8 x the compressed bytes of up to
-    // 18,944 chunks, the windows, the text): those buffers go back when the file is done; what a
-    // small file needed stays for the next one.
-    {
-        tdg_ctx::Grow *big[] = {&ctx->gz_syms, &ctx->gz_sym2, &ctx->gz_windows, &ctx->gz_text, &ctx->gz_comp, &ctx->gz_comp2};
-        size_t held = 0;
-        for (tdg_ctx::Grow *g : big) held += g->cap;
-        if (held > ((size_t)4 << 30)) {
-            CK(cudaStreamSynchronize(ctx->stream));
-            CK(cudaStreamSynchronize(ctx->copy_stream));
-            for (tdg_ctx::Grow *g : big) {
-                if (g == &ctx->gz_text && carry) continue;                  // the caller still copies the carried bytes out of it
-                if (g->p) cudaFree(g->p);
-                g->p = nullptr;
-                g->cap = 0;
-            }
-        }
     }
     if (st.handover) {
         ho.active = true;
@@ -1696,6 +1692,25 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     cudaStreamSynchronize(ctx->stream);
     if (result == TDG_OK && totals) result = tdg_file_totals(ctx, totals);
     return result;
+}
+
+// Gives the working buffers of the device-side gzip feed back (a 1.2 GB round holds about 12 GB:
+// tokens, symbols, windows, text).  They are kept between files otherwise.
+int tdg_release_scratch(tdg_ctx *ctx)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    for (tdg_ctx::Grow *g : {&ctx->gz_comp, &ctx->gz_comp2, &ctx->gz_syms, &ctx->gz_sym2, &ctx->gz_ntok, &ctx->gz_meta, &ctx->gz_cand,
+                             &ctx->gz_ncand, &ctx->gz_windows, &ctx->gz_text, &ctx->gz_crc, &ctx->gz_lens, &ctx->gz_offs, &ctx->gz_carry,
+                             &ctx->gz_cold}) {
+        if (g->p) cudaFree(g->p);
+        g->p = nullptr;
+        g->cap = 0;
+    }
+    return TDG_OK;
 }
 
 // The device-side gzip feed by itself: inflates `path` into dst (host memory) the way

@@ -60,9 +60,9 @@ struct RoundArgs {
     uint64_t pos_rel;            // exact start of chunk 0, in bits from the grid
     uint64_t base_bit;           // bit position of the grid in the file
     uint32_t hist;
-    uint32_t symcap;
+    uint32_t symcap, tokcap;     // symbols a chunk may produce; token slots per chunk in `syms`
     uint32_t *cand, *ncand;      // [nchunks][MAXC], [nchunks]
-    uint16_t *syms;              // [nchunks][symcap] token slots
+    uint16_t *syms;              // [nchunks][tokcap] token slots
     gzl::Meta *meta;
     const uint8_t *kraft3;
     uint16_t *cold;              // [nchunks][COLD_U16]: a lane's list of long-code symbols (the scan's warps use it first)
@@ -140,9 +140,9 @@ __global__ void __launch_bounds__(DEC_THREADS) gz_decode(const RoundArgs a)
     if (mine) {
         const gzl::Mem<32> m{s_lane + (size_t)warp * gzl::LANE_U16 * 32 + lane * 2, a.cold + (size_t)k * gzl::COLD_U16};
         const uint64_t stop = nominal_rel(a, k + 1);
-        uint16_t *out = a.syms + (size_t)k * a.symcap;
-        if (k == 0) z.init(m, a.in, a.nwords, a.in_bits, true, a.pos_rel, nullptr, 0, stop, a.hist, out, a.symcap, &r);
-        else z.init(m, a.in, a.nwords, a.in_bits, false, nominal_rel(a, k), a.cand + (size_t)k * MAXC, a.ncand[k], stop, 0, out, a.symcap, &r);
+        uint16_t *out = a.syms + (size_t)k * a.tokcap;
+        if (k == 0) z.init(m, a.in, a.nwords, a.in_bits, true, a.pos_rel, nullptr, 0, stop, a.hist, out, a.tokcap, a.symcap, &r);
+        else z.init(m, a.in, a.nwords, a.in_bits, false, nominal_rel(a, k), a.cand + (size_t)k * MAXC, a.ncand[k], stop, 0, out, a.tokcap, a.symcap, &r);
     }
     // every lane of the warp takes every step together: the vote is the point of reconvergence
     while (__any_sync(0xFFFFFFFFu, z.state != gzl::S_DONE)) z.step();
@@ -159,9 +159,9 @@ __global__ void __launch_bounds__(DEC_THREADS) gz_decode(const RoundArgs a)
 // distance symbols in front of it, all of which are written before the match begins, so the 32
 // lanes never wait for each other inside a match (and overlapping matches need no special case).
 struct ExpandArgs {
-    const uint16_t *tok;         // [nchunks][symcap]
-    uint16_t *syms;              // [nchunks][symcap]
-    uint32_t symcap;
+    const uint16_t *tok;         // [nchunks][tokcap]
+    uint16_t *syms;              // [accepted][symcap]
+    uint32_t tokcap, symcap;
     const uint32_t *ntok;        // [accepted] token slots of each accepted chunk (0: nothing to do)
     uint32_t accepted;
 };
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(EXP_WARPS * 32) gz_expand(const ExpandArgs a)
     const uint32_t k = blockIdx.x * EXP_WARPS + (threadIdx.x >> 5);
     if (k >= a.accepted) return;
     const uint32_t ntok = a.ntok[k];
-    const uint16_t *tok = a.tok + (size_t)k * a.symcap;
+    const uint16_t *tok = a.tok + (size_t)k * a.tokcap;
     uint16_t *sym = a.syms + (size_t)k * a.symcap;
     uint32_t o = 0;
     for (uint32_t base = 0; base < ntok; base += 32) {

@@ -254,7 +254,8 @@ struct Lane {
     uint64_t in_bits;         // valid bits of the buffer
     uint64_t wmax;            // a word index beyond this means the input is exhausted for sure
     uint16_t *out;            // token slots
-    uint32_t cap;             // symbols the chunk may produce (token slots never outnumber symbols)
+    uint32_t cap;             // symbols the chunk may produce
+    uint32_t tokcap;          // token slots `out` holds (literal-heavy data needs about two per compressed byte)
     uint32_t o;               // symbols produced
     uint32_t t;               // token slots written
     uint32_t hist;            // how far back a distance may reach beyond o (WIN: unknown prehistory)
@@ -279,7 +280,7 @@ struct Lane {
 
     TDG_GZ_FN void init(Mem<STRIDE> mem, const uint32_t *in, uint64_t nwords, uint64_t inbits, bool known_start, uint64_t base,
                         const uint32_t *cands, uint32_t ncands, uint64_t stop, uint32_t history, uint16_t *dst, uint32_t dst_cap,
-                        Meta *report)
+                        uint32_t sym_cap, Meta *report)
     {
         m = mem;
         bits.in = in;
@@ -291,7 +292,8 @@ struct Lane {
         in_bits = inbits;
         wmax = (inbits + 31) / 32 + 2;
         out = dst;
-        cap = dst_cap;
+        tokcap = dst_cap;
+        cap = sym_cap;
         o = 0;
         t = 0;
         hist = WIN;
@@ -527,7 +529,7 @@ struct Lane {
             fail(F_INPUT);
             return;
         }
-        if (o + len + 260 > cap) {
+        if (o + len + 260 > cap || t + len + 8 > tokcap) {
             fail(F_SPACE);
             return;
         }
@@ -551,7 +553,7 @@ struct Lane {
     // S_HUFF: one literal/length symbol (and a second literal when it is there for the taking), or a whole match
     TDG_GZ_FN void step_huff()
     {
-        if (o + 260 > cap) {
+        if (o + 260 > cap || t + 8 > tokcap) {
             fail(F_SPACE);
             return;
         }
@@ -699,7 +701,7 @@ TDG_GZ_FN bool header_parses(Mem<STRIDE> m, const uint32_t *in, uint64_t nwords,
 {
     Lane<STRIDE> z;
     Meta dummy;
-    z.init(m, in, nwords, in_bits, true, bit, nullptr, 0, 0, 0, nullptr, 0, &dummy);
+    z.init(m, in, nwords, in_bits, true, bit, nullptr, 0, 0, 0, nullptr, 0, 0, &dummy);
     z.bits.seek(bit);
     z.bits.fill();
     z.bits.drop(3);
@@ -794,11 +796,11 @@ TDG_GZ_FN bool header_check(const Mem<STRIDE> m, const uint32_t *in, uint64_t nw
 // every defect is real.  Bit positions are relative to the buffer (`in`).
 template <int STRIDE>
 TDG_GZ_FN void run_chunk(Mem<STRIDE> m, const uint32_t *in, uint64_t nwords, uint64_t in_bits, bool known, uint64_t search_base,
-                         const uint32_t *cand, uint32_t ncand, uint64_t stop_bit, uint32_t hist, uint16_t *out, uint32_t cap,
-                         Meta &r)
+                         const uint32_t *cand, uint32_t ncand, uint64_t stop_bit, uint32_t hist, uint16_t *out, uint32_t tokcap,
+                         uint32_t symcap, Meta &r)
 {
     Lane<STRIDE> z;
-    z.init(m, in, nwords, in_bits, known, search_base, cand, ncand, stop_bit, hist, out, cap, &r);
+    z.init(m, in, nwords, in_bits, known, search_base, cand, ncand, stop_bit, hist, out, tokcap, symcap, &r);
     while (z.state != S_DONE) z.step();
 }
 

@@ -75,14 +75,14 @@ long long gzl_inflate(const uint8_t *gz, size_t n, size_t chunk, uint32_t max_ch
             const uint64_t stop = r.nominal(k + 1, n) - base_bit;
             if (k == 0) {
                 gzl::run_chunk<1>(m, (const uint32_t *)buf.data(), nwords, (uint64_t)nb * 8, true, r.pos_bit - base_bit, nullptr, 0,
-                                  stop, r.hist, toks.data(), symcap, meta[k]);
+                                  stop, r.hist, toks.data(), symcap, symcap, meta[k]);
             } else {
                 const uint64_t from = r.nominal(k, n) - base_bit;
                 const uint64_t to = std::min<uint64_t>(from + (uint64_t)search_bytes * 8, stop);
                 scan(buf, nwords, (uint64_t)nb * 8, from, to, kraft3, mem.data(), cold.data(), cand, 2);
                 if (blind_every && k % blind_every == 0) cand.clear();          // (test: a lane that finds no start; the host fills in)
                 gzl::run_chunk<1>(m, (const uint32_t *)buf.data(), nwords, (uint64_t)nb * 8, false, from, cand.data(),
-                                  (uint32_t)cand.size(), stop, 0, toks.data(), symcap, meta[k]);
+                                  (uint32_t)cand.size(), stop, 0, toks.data(), symcap, symcap, meta[k]);
             }
             if (gzl::expand_tokens(toks.data(), meta[k].ntok, syms[k].data()) != meta[k].out_len) return -50;
             meta[k].start_bit += base_bit;
