@@ -667,17 +667,15 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
     uint32_t max_chunks = (uint32_t)ctx->sm_count * gzd::DEC_THREADS;          // one lane per chunk, one CTA per SM
     if (const char *e = getenv("TDG_GZDEV_MAXCHUNKS")) max_chunks = (uint32_t)std::max(1, atoi(e));
     max_chunks = std::min<uint32_t>(max_chunks, 65000);             // gz_ptr_*: a chunk index has 16 bits
-    // chunk size: every lane gets work when the file is large enough, in steps of 16 KiB between 32 and 128 KiB
-    // (a chunk should hold a block start: zlib's blocks are 10 - 30 KB of compressed data)
-    size_t chunk = round_up((map.n + max_chunks - 1) / max_chunks, (size_t)16 << 10);
-    chunk = std::min<size_t>(std::max<size_t>(chunk, (size_t)32 << 10), (size_t)128 << 10);
-    if (const char *e = getenv("TDG_GZDEV_CHUNK")) chunk = std::max<size_t>(4096, strtoull(e, nullptr, 10) / 16 * 16);
-    // what a lane may produce: symbols up to 8 x its chunk (and room for a large block), token slots up to
-    // 3 x its chunk (literal codes of 4 bits and more: two slots per compressed byte); a chunk that needs more
-    // ends the device feed (the host reader takes over)
-    uint32_t symcap = (uint32_t)std::max<size_t>(8 * chunk, (size_t)256 << 10);
-    uint32_t tokcap = (uint32_t)std::max<size_t>(3 * chunk, (size_t)128 << 10);
-    if (const char *e = getenv("TDG_GZDEV_SYMCAP")) symcap = tokcap = (uint32_t)std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
+    // Chunk size, chosen per round from what is left of the file: every lane gets work when there is enough of
+    // it, in steps of 16 KiB between 32 and 128 KiB (a chunk should hold a block start: zlib's blocks are
+    // 10 - 30 KB of compressed data).  What a lane may produce: symbols up to 8 x its chunk (and room for a
+    // large block), token slots up to 3 x its chunk (literal codes of 4 bits and more: two slots per compressed
+    // byte); a chunk that needs more ends the device feed (the host reader takes over).
+    size_t fixed_chunk = 0;
+    if (const char *e = getenv("TDG_GZDEV_CHUNK")) fixed_chunk = std::max<size_t>(4096, strtoull(e, nullptr, 10) / 16 * 16);
+    uint32_t fixed_cap = 0;
+    if (const char *e = getenv("TDG_GZDEV_SYMCAP")) fixed_cap = (uint32_t)std::max<unsigned long long>(1024, strtoull(e, nullptr, 10));
     const bool debug = getenv("TDG_GZDEV_DEBUG") != nullptr;
     const int threads = gz_io_threads();
     uint8_t *d_tabs = (uint8_t *)ctx->gz_tabs.p;
@@ -714,14 +712,24 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
     size_t pre_off = 0, pre_end = 0;
 
     while (!st.eof && !st.handover) {
+        size_t chunk = fixed_chunk;
+        if (!chunk) {
+            const size_t left = map.n - (size_t)(st.pos_bit >> 3);
+            chunk = round_up((left + max_chunks - 1) / max_chunks, (size_t)16 << 10);
+            chunk = std::min<size_t>(std::max<size_t>(chunk, (size_t)32 << 10), (size_t)128 << 10);
+        }
+        const uint32_t symcap = fixed_cap ? fixed_cap : (uint32_t)std::max<size_t>(8 * chunk, (size_t)256 << 10);
+        const uint32_t tokcap = fixed_cap ? fixed_cap : (uint32_t)std::max<size_t>(3 * chunk, (size_t)128 << 10);
         const gzc::Round r = st.plan(chunk, max_chunks);
         const size_t nb = r.buf_end - r.buf_off;
         const size_t nwords = (nb + 3) / 4;
         // ---- the round's compressed bytes: file -> pinned pieces -> device (or already there: see below)
         auto t0 = now();
-        const bool prefetched = pre_valid && pre_off == r.buf_off && pre_end >= r.buf_end;
+        const bool prefetched = pre_valid && pre_off <= r.buf_off && pre_end >= r.buf_end && (r.buf_off - pre_off) % 16 == 0;
+        size_t comp_skip = 0;                                // where the round's bytes begin in the buffer
         if (prefetched) {
             cur ^= 1;                                        // the bytes sit in the other buffer: wait for their copies
+            comp_skip = r.buf_off - pre_off;
             CK(cudaStreamWaitEvent(ctx->stream, ctx->gz_pre, 0));
         } else {
             rc = upload(cur, r.buf_off, r.buf_end, ctx->stream);
@@ -739,7 +747,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         auto t1 = now();
         // ---- scan + decode
         gzd::RoundArgs a;
-        a.in = (const uint32_t *)comp.p;
+        a.in = (const uint32_t *)((const uint8_t *)comp.p + comp_skip);
         a.nwords = nwords;
         a.in_bits = (uint64_t)nb * 8;
         a.nchunks = r.nchunks;
@@ -776,8 +784,8 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         double ms_prefetch = 0;
         const auto tp0 = now();
         if (r.grid + (size_t)r.nchunks * chunk < map.n && r.nchunks == max_chunks) {
-            pre_off = r.grid + (size_t)r.nchunks * chunk;
-            pre_end = std::min(map.n, pre_off + ((size_t)max_chunks + 1) * chunk);
+            pre_off = r.grid + (size_t)r.nchunks * chunk;    // (the next round's grid starts here or, with smaller chunks, a little further on)
+            pre_end = std::min(map.n, pre_off + ((size_t)max_chunks + 2) * chunk);
             rc = upload(cur ^ 1, pre_off, pre_end, ctx->copy_stream);
             if (rc) return rc;
             CK(cudaEventRecord(ctx->gz_pre, ctx->copy_stream));
