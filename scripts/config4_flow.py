@@ -47,6 +47,9 @@ def main():
     eng.set_tags(plan.tags.patterns, plan.tags.index, any_base=plan.tags.any_base)
     eng.bind_matrix(matrix.data_ptr(), plan.barnum, plan.ntags)
     eng.begin_file(plan.bar.patterns, plan.bar.index, plan.bar_tag_off, any_base=plan.bar.any_base)
+    if world > 1:
+        eng.allreduce_matrix()             # (the matrix is still all zeros: NCCL sets up its channels on the first call)
+        eng.sync()
     gen = _synth_native.Generator(bcs, tags, site, readlen=readlen, seed=4, **mix)
     mine = total // world
     first = rank * mine
