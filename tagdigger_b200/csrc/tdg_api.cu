@@ -595,10 +595,7 @@ bool gz_pread_parallel(int fd, uint8_t *dst, size_t n, uint64_t off, int threads
             lo += (size_t)r;
         }
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-    work(0);
-    for (auto &x : th) x.join();
+    tdg::Pool::get().run(nt, work);
     for (char c : ok)
         if (!c) return false;
     return true;

@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "tdg_pgz.h"
+#include "tdg_pool.h"
 
 namespace tdg {
 
@@ -219,10 +220,7 @@ private:
             }
             got[t] = (long long)(done - lo);
         };
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-        work(0);
-        for (auto &x : th) x.join();
+        Pool::get().run(nt, work);
         size_t total = 0;
         for (int t = 0; t < nt; t++) {
             if (got[t] < 0) return fail(-3, "read error on " + path_);

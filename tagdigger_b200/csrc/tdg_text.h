@@ -14,6 +14,8 @@
 #include <thread>
 #include <vector>
 
+#include "tdg_pool.h"
+
 namespace tdg {
 
 // Does p[0..n) hold a byte >= 0x80?  (FASTQ text almost never does: then there is nothing to validate.)
@@ -39,10 +41,7 @@ inline bool has_high_bit_mt(const uint8_t *p, size_t n, int threads)
         size_t lo = n / nt * t, hi = t == nt - 1 ? n : n / nt * (t + 1);
         hit[t] = has_high_bit(p + lo, hi - lo) ? 1 : 0;
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
-    work(0);
-    for (auto &x : th) x.join();
+    Pool::get().run(nt, work);
     for (char h : hit)
         if (h) return true;
     return false;

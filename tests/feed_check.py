@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "native", "feed_check.cpp")
 _LIB = os.path.join(_HERE, "native", "libfeed_check.so")
-_DEPS = [os.path.join(os.path.dirname(_HERE), "tagdigger_b200", "csrc", h) for h in ("tdg_feed.h", "tdg_pgz.h", "tdg_text.h")]
+_DEPS = [os.path.join(os.path.dirname(_HERE), "tagdigger_b200", "csrc", h) for h in ("tdg_feed.h", "tdg_pgz.h", "tdg_text.h", "tdg_pool.h")]
 
 
 def build(force=False):

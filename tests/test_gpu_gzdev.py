@@ -260,3 +260,14 @@ def test_count_gzip_members_and_utf8_on_the_device(tmp_path, monkeypatch):
     monkeypatch.setenv("TDG_GZDEV", "0")
     host = np.asarray(counting.find_tags_fastq(p, bcs, tags))
     assert (host == want).all()
+
+
+def test_release_scratch_and_inflate_again(tmp_path):
+    """tdg_release_scratch gives the feed's working buffers back; the next file allocates them again."""
+    data = _fastq_like(12, 6 << 20)
+    eng = counting.get_engine(0)
+    out, info, ms = _inflate(tmp_path, gzip.compress(data, 6), len(data) + 100)
+    assert out == data
+    eng.release_scratch()
+    out, info, ms = _inflate(tmp_path, gzip.compress(data, 1), len(data) + 100)
+    assert out == data and info["mode"] == 0
