@@ -159,17 +159,17 @@ int grow(tdg_ctx *ctx, tdg_ctx::Grow &g, size_t need, bool host)
 {
     if (need <= g.cap) return TDG_OK;
     CK(cudaStreamSynchronize(ctx->stream));
-    if (g.p) {
-        if (g.host) cudaFreeHost(g.p); else cudaFree(g.p);
-        g.p = nullptr;
-        g.cap = 0;
-    }
     const size_t cap = need + need / 4 + 4096;
-    cudaError_t e = host ? cudaHostAlloc(&g.p, cap, cudaHostAllocDefault) : cudaMalloc(&g.p, cap);
+    void *fresh = nullptr;
+    cudaError_t e = host ? cudaHostAlloc(&fresh, cap, cudaHostAllocDefault) : cudaMalloc(&fresh, cap);
     if (e != cudaSuccess) {
-        g.p = nullptr;
+        cudaGetLastError();                                  // (the failed allocation must not show up as the next launch's error)
         return fail(ctx, TDG_ERR_NOMEM, std::string("buffer of ") + std::to_string(cap) + " bytes: " + cudaGetErrorString(e));
     }
+    if (g.p) {
+        if (g.host) cudaFreeHost(g.p); else cudaFree(g.p);   // (the old buffer stays whole when the new one cannot be had)
+    }
+    g.p = fresh;
     g.cap = cap;
     g.host = host;
     return TDG_OK;
@@ -708,7 +708,12 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
     bool pre_valid = false;                                  // the other one holds [pre_off, pre_end) of the file
     size_t pre_off = 0, pre_end = 0;
 
-    while (!st.eof && !st.handover) {
+    // One round.  TDG_ERR_NOMEM from a buffer that cannot be had is not the file's fault: nothing of the round
+    // has been delivered then, and the host reader takes over at the state the round began in.
+    int round_no = 0;
+    const int oom_round = getenv("TDG_GZDEV_OOM_ROUND") ? atoi(getenv("TDG_GZDEV_OOM_ROUND")) : -1;      // test hook
+    auto one_round = [&]() -> int {
+        if (round_no++ == oom_round) return fail(ctx, TDG_ERR_NOMEM, "buffer of 0 bytes: simulated (TDG_GZDEV_OOM_ROUND)");
         size_t chunk = fixed_chunk;
         if (!chunk) {
             const size_t left = map.n - (size_t)(st.pos_bit >> 3);
@@ -935,6 +940,17 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
                     r.nchunks, chunk >> 10, o.accepted, (unsigned long long)text_len, ms(t0, t1), prefetched ? " (prefetched)" : "", ms(t1, t2),
                     ms(t2, t3), ms_prefetch, ms(t3, t4), ms(t4, t5),
                     ms(t5, t6), st.handover ? "  -> host reader: " : "", st.handover ? st.why : "");
+            return TDG_OK;
+    };
+    while (!st.eof && !st.handover) {
+        rc = one_round();
+        if (rc == TDG_ERR_NOMEM) {
+            st.handover = true;
+            st.why = "device memory";
+            pre_valid = false;
+            break;
+        }
+        if (rc) return rc;
     }
     if (st.handover) {
         ho.active = true;

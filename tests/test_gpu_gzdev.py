@@ -271,3 +271,33 @@ def test_release_scratch_and_inflate_again(tmp_path):
     eng.release_scratch()
     out, info, ms = _inflate(tmp_path, gzip.compress(data, 1), len(data) + 100)
     assert out == data and info["mode"] == 0
+
+
+def test_device_memory_shortage_hands_over_to_the_host(tmp_path, monkeypatch):
+    """A buffer that cannot be had (simulated) is not the file's fault: the host reader finishes it."""
+    data = _fastq_like(13, 8 << 20)
+    blob = gzip.compress(data, 6)
+    monkeypatch.setenv("TDG_GZDEV_CHUNK", "65536")
+    monkeypatch.setenv("TDG_GZDEV_MAXCHUNKS", "16")
+    for at in (0, 2):
+        monkeypatch.setenv("TDG_GZDEV_OOM_ROUND", str(at))
+        out, info, ms = _inflate(tmp_path, blob, len(data) + 100)
+        assert out == data and info["mode"] == 1 and info["rounds"] == at, (at, info)
+
+
+@pytest.mark.parametrize("max_chunks", [37, 5])
+def test_count_gzip_file_in_many_rounds(tmp_path, monkeypatch, max_chunks):
+    """Rounds of a few chunks: the next round's bytes are prefetched, lines are carried from round to round."""
+    monkeypatch.setenv("TDG_GZDEV_CHUNK", "65536")
+    monkeypatch.setenv("TDG_GZDEV_MAXCHUNKS", str(max_chunks))
+    rng, bcs, tags = _tables(5)
+    fq, _ = synth.make_fastq(150000, bcs, tags, rng)
+    p = str(tmp_path / "reads.fq.gz")
+    with open(p, "wb") as fh:
+        fh.write(gzip.compress(fq, 1))
+    want, wtot = c_oracle.Counter(bcs, tags).count(fq)
+    tot = []
+    got = np.asarray(counting.find_tags_fastq(p, bcs, tags, totals=tot))
+    assert tot[:3] == wtot and (got == want).all()
+    info = counting.get_engine(0).gz_inflate_host(p, len(fq) + 100)[1]
+    assert info["mode"] == 0 and info["rounds"] > 3
