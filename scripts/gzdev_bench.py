@@ -3,7 +3,7 @@
 tables) as ONE ordinary gzip member, (a) inflated by tdg_gz_inflate_host with the time per stage,
 (b) counted by tdg_count_file with the device feed (default) and with TDG_GZDEV=0 (host threads).
 
-    python scripts/gzdev_bench.py [reads] [level]
+    python scripts/gzdev_bench.py [reads] [level] [bgzf]      # bgzf: the file as BGZF members (bgzip's format) instead
 """
 import json
 import os
@@ -15,6 +15,26 @@ import time
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 import numpy as np  # noqa: E402
+
+
+def _bgzf_piece(job):
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from feed_check import bgzf_compress
+    path, a, b, last, level = job
+    with open(path, "rb") as fh:
+        fh.seek(a)
+        data = fh.read(b - a)
+    return bgzf_compress(data, eof_marker=last, level=level)
+
+
+def write_bgzf_parallel(src, dst, level=6, piece=65280 * 256):
+    import multiprocessing as mp
+    size = os.path.getsize(src)
+    cuts = list(range(0, size, piece)) + [size]
+    jobs = [(src, a, b, b == size, level) for a, b in zip(cuts[:-1], cuts[1:])]
+    with mp.get_context("fork").Pool(min(len(jobs), os.cpu_count() or 1)) as pool, open(dst, "wb") as out:
+        for blob in pool.imap(_bgzf_piece, jobs):
+            out.write(blob)
 
 
 def main():
@@ -40,7 +60,11 @@ def main():
         img.tofile(plain)
         want, wtot = c_oracle.count_sharded(img, c_oracle.Counter(bcs, tags, bench.CUTSITE))
         gz = plain + ".gz"
-        bench.write_gzip_parallel(plain, gz, level=level)
+        if len(sys.argv) > 3 and sys.argv[3] == "bgzf":
+            write_bgzf_parallel(plain, gz, level=level)
+            res["format"] = "BGZF"
+        else:
+            bench.write_gzip_parallel(plain, gz, level=level)
         res["text_bytes"] = int(nbytes)
         res["gzip_bytes"] = os.path.getsize(gz)
         runs = []

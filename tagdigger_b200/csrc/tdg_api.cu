@@ -554,6 +554,8 @@ int end_file_impl(tdg_ctx *ctx, uint64_t reads_limit)
 struct GzHandover {              // how the host feeder continues when the device feed stops early
     bool active = false;
     bool to_zlib = false;
+    bool bgzf = false;           // BGZF: the host feeder continues at the member at file offset bgzf_off
+    uint64_t bgzf_off = 0;
     uint64_t pos_bit = 0, member_len = 0, delivered = 0;
     uint32_t hist = 0, crc = 0;
     std::vector<uint8_t> window;
@@ -625,6 +627,250 @@ int gz_tables(tdg_ctx *ctx)
     return TDG_OK;
 }
 
+// A mapped file (the device feeds parse headers and trailers in it; the bytes themselves go through pread)
+struct GzMap {
+    int fd = -1;
+    const uint8_t *p = nullptr;
+    size_t n = 0;
+    ~GzMap()
+    {
+        if (p) munmap(const_cast<uint8_t *>(p), n);
+        if (fd >= 0) ::close(fd);
+    }
+};
+
+// file bytes [off, end) -> compressed buffer `which` (zero padded), through the three pinned buffers, on `stream`
+int gz_upload(tdg_ctx *ctx, const GzMap &map, const char *path, int threads, int &up_i, int which, size_t off, size_t end,
+              cudaStream_t stream)
+{
+    tdg_ctx::Grow &g = which ? ctx->gz_comp2 : ctx->gz_comp;
+    const size_t nb = end - off, padded = (nb + 3) / 4 * 4 + 256;
+    int rc = grow(ctx, g, padded, false);
+    if (rc) return rc;
+    const size_t piece = ctx->file_buf_cap;
+    for (size_t at = 0; at < nb; at += piece, up_i = (up_i + 1) % 3) {
+        const size_t m = std::min(piece, nb - at);
+        CK(cudaEventSynchronize(ctx->gz_up[up_i]));
+        if (!gz_pread_parallel(map.fd, ctx->file_buf[up_i], m, off + at, threads))
+            return fail(ctx, TDG_ERR_IO, std::string("read error on ") + path);
+        CK(cudaMemcpyAsync((uint8_t *)g.p + at, ctx->file_buf[up_i], m, cudaMemcpyHostToDevice, stream));
+        CK(cudaEventRecord(ctx->gz_up[up_i], stream));
+    }
+    CK(cudaMemsetAsync((uint8_t *)g.p + nb, 0, padded - nb, stream));
+    return TDG_OK;
+}
+
+// BGZF (bgzip): gzip members of at most 64 KiB of text that carry their compressed size in a 'BC'
+// extra field -- every member is its own deflate stream, so nothing is speculative here: the host
+// walks the member headers, one lane inflates one member from its first bit to its final block
+// (gz_decode in member mode), gz_expand and gz_resolve lay the text out, gz_member_crc takes every
+// member's CRC-32, and the host holds length, end position and CRC against the member's trailer.
+// A member that fails any of that is what the host feeder calls a corrupt BGZF member; a member
+// header that is not BGZF (or a truncated one) ends the device feed, the host feeder continues there.
+int gz_device_feed_bgzf(tdg_ctx *ctx, const char *path, const GzMap &map, GzSink &sink, GzHandover &ho, size_t &carry, GzStats *stats,
+                        tdg::Utf8State *u8)
+{
+    using namespace tdg;
+    struct Member {
+        size_t off;
+        uint32_t hlen, csize, isize, crc;
+    };
+    int rc = gz_tables(ctx);
+    if (rc) return rc;
+    rc = ensure_slots(ctx);
+    if (rc) return rc;
+    uint32_t max_chunks = (uint32_t)ctx->sm_count * gzd::DEC_THREADS;
+    if (const char *e = getenv("TDG_GZDEV_MAXCHUNKS")) max_chunks = (uint32_t)std::max(1, atoi(e));
+    const bool debug = getenv("TDG_GZDEV_DEBUG") != nullptr;
+    const int threads = gz_io_threads();
+    const uint32_t symcap = 65536 + 512, tokcap = 65536 + 64;
+    uint8_t *d_tabs = (uint8_t *)ctx->gz_tabs.p;
+    uint32_t op[5];
+    for (int j = 0; j < 5; j++) op[j] = (uint32_t)crc32_combine_gen((z_off_t)(2048u << j));
+    int up_i = 0;
+    carry = 0;
+    size_t off = 0;
+    uint64_t delivered = 0;
+    bool foreign = false;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    while (off < map.n && !foreign) {
+        // ---- the members of this round
+        auto t0 = now();
+        std::vector<Member> mem;
+        size_t end = off;
+        while (end < map.n && mem.size() < max_chunks && end - off < ((size_t)1 << 30)) {
+            uint32_t csize = 0, hlen = 0;
+            if (!Feeder::bgzf_member(map.p + end, std::min<size_t>(map.n - end, 1024), csize, hlen) || end + csize > map.n) {
+                foreign = true;
+                break;
+            }
+            Member m;
+            m.off = end;
+            m.hlen = hlen;
+            m.csize = csize;
+            memcpy(&m.crc, map.p + end + csize - 8, 4);
+            memcpy(&m.isize, map.p + end + csize - 4, 4);
+            if (m.isize > 65536) {
+                foreign = true;
+                break;
+            }
+            mem.push_back(m);
+            end += csize;
+        }
+        if (mem.empty()) break;
+        const uint32_t n = (uint32_t)mem.size();
+        const size_t nb = end - off, nwords = (nb + 3) / 4;
+        if ((rc = gz_upload(ctx, map, path, threads, up_i, 0, off, end, ctx->stream))) return rc;
+        if ((rc = grow(ctx, ctx->gz_syms, (size_t)n * tokcap * 2, false))) return rc;
+        if ((rc = grow(ctx, ctx->gz_sym2, (size_t)n * symcap * 2, false))) return rc;
+        if ((rc = grow(ctx, ctx->gz_meta, (size_t)n * sizeof(gzl::Meta), false))) return rc;
+        if ((rc = grow(ctx, ctx->gz_hmeta, (size_t)n * sizeof(gzl::Meta), true))) return rc;
+        if ((rc = grow(ctx, ctx->gz_cold, (size_t)(n + 8) * gzl::COLD_U16 * 2, false))) return rc;
+        if ((rc = grow(ctx, ctx->gz_offs, ((size_t)n * 3 + 1) * 8, false))) return rc;       // [n] start bits, [n] end bits, [n + 1] text offsets
+        if ((rc = grow(ctx, ctx->gz_lens, (size_t)n * 4, false))) return rc;
+        if ((rc = grow(ctx, ctx->gz_ntok, (size_t)n * 4, false))) return rc;
+        std::vector<uint64_t> bits(2 * (size_t)n), text_off(n + 1, 0);
+        std::vector<uint32_t> lens(n);
+        for (uint32_t k = 0; k < n; k++) {
+            bits[k] = (uint64_t)(mem[k].off + mem[k].hlen - off) * 8;
+            bits[n + k] = (uint64_t)(mem[k].off + mem[k].csize - 8 - off) * 8;
+            lens[k] = mem[k].isize;
+            text_off[k + 1] = text_off[k] + mem[k].isize;
+        }
+        const uint64_t text_len = text_off[n];
+        uint64_t *d_bits = (uint64_t *)ctx->gz_offs.p;
+        uint64_t *d_toff = d_bits + 2 * (size_t)n;
+        CK(cudaMemcpyAsync(d_bits, bits.data(), bits.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_toff, text_off.data(), text_off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->gz_lens.p, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        gzd::RoundArgs a;
+        memset(&a, 0, sizeof(a));
+        a.in = (const uint32_t *)ctx->gz_comp.p;
+        a.nwords = nwords;
+        a.in_bits = (uint64_t)nb * 8;
+        a.nchunks = n;
+        a.symcap = symcap;
+        a.tokcap = tokcap;
+        a.syms = (uint16_t *)ctx->gz_syms.p;
+        a.meta = (gzl::Meta *)ctx->gz_meta.p;
+        a.cold = (uint16_t *)ctx->gz_cold.p;
+        a.m_start = d_bits;
+        a.m_end = d_bits + n;
+        gzd::gz_decode<<<(n + gzd::DEC_THREADS - 1) / gzd::DEC_THREADS, gzd::DEC_THREADS, gzd::DEC_SMEM, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        gzl::Meta *meta = (gzl::Meta *)ctx->gz_hmeta.p;
+        CK(cudaMemcpyAsync(meta, ctx->gz_meta.p, (size_t)n * sizeof(gzl::Meta), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        auto t1 = now();
+        // ---- every member must have ended with its final block, right in front of its trailer, at its length
+        std::vector<uint32_t> ntok(n);
+        for (uint32_t k = 0; k < n; k++) {
+            const gzl::Meta &c = meta[k];
+            const bool good = c.flags == (gzl::F_FOUND | gzl::F_FINAL) && c.out_len == mem[k].isize && (c.end_bit + 7) / 8 * 8 == bits[n + k];
+            if (!good) return fail(ctx, TDG_ERR_GZIP, std::string("gzip error in ") + path + ": corrupt BGZF member");
+            ntok[k] = c.ntok;
+        }
+        if (text_len) {
+            const uint32_t pieces = (uint32_t)((text_len + gzd::PIECE - 1) / gzd::PIECE);
+            if ((rc = grow(ctx, ctx->gz_crc, ((size_t)pieces + n) * 4 + 16, false))) return rc;
+            if ((rc = grow(ctx, ctx->gz_hcrc, ((size_t)n + 1) * 4 + 16, true))) return rc;
+            if ((rc = grow(ctx, ctx->gz_windows, gzl::WIN * 4, false))) return rc;          // (never read: a member has no history before it)
+            const size_t need = round_up(carry + text_len, TDG_TILE_BYTES) + TDG_HALO_BYTES + 64;
+            if (need > ctx->gz_text.cap) {
+                if (carry) {
+                    if ((rc = grow(ctx, ctx->gz_carry, carry, false))) return rc;
+                    CK(cudaMemcpyAsync(ctx->gz_carry.p, ctx->gz_text.p, carry, cudaMemcpyDeviceToDevice, ctx->stream));
+                }
+                if ((rc = grow(ctx, ctx->gz_text, need, false))) return rc;
+                if (carry) CK(cudaMemcpyAsync(ctx->gz_text.p, ctx->gz_carry.p, carry, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+            CK(cudaMemcpyAsync(ctx->gz_ntok.p, ntok.data(), ntok.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            gzd::ExpandArgs ea;
+            ea.tok = a.syms;
+            ea.syms = (uint16_t *)ctx->gz_sym2.p;
+            ea.tokcap = tokcap;
+            ea.symcap = symcap;
+            ea.ntok = (const uint32_t *)ctx->gz_ntok.p;
+            ea.accepted = n;
+            gzd::gz_expand<<<(n + gzd::EXP_WARPS - 1) / gzd::EXP_WARPS, gzd::EXP_WARPS * 32, 0, ctx->stream>>>(ea);
+            CK(cudaGetLastError());
+            uint32_t *d_piece_crc = (uint32_t *)ctx->gz_crc.p;
+            uint32_t *d_flag = d_piece_crc + pieces;
+            uint32_t *d_mcrc = d_flag + 1;
+            CK(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
+            gzd::ResArgs ra;
+            ra.syms = (const uint16_t *)ctx->gz_sym2.p;
+            ra.symcap = symcap;
+            ra.text_off = d_toff;
+            ra.accepted = n;
+            ra.ptrs = (const uint32_t *)ctx->gz_windows.p;
+            ra.text = (uint8_t *)ctx->gz_text.p + carry;
+            ra.text_len = text_len;
+            ra.crc = d_piece_crc;
+            ra.flag = d_flag;
+            ra.table = (const uint32_t *)(d_tabs + 512);
+            for (int j = 0; j < 8; j++) ra.op[j] = ctx->gz_op[j];
+            gzd::gz_resolve<<<pieces, gzd::RES_THREADS, 0, ctx->stream>>>(ra);
+            CK(cudaGetLastError());
+            gzd::MemberCrcArgs ca;
+            ca.syms = (const uint16_t *)ctx->gz_sym2.p;
+            ca.stride = symcap;
+            ca.lens = (const uint32_t *)ctx->gz_lens.p;
+            ca.n = n;
+            ca.crc = d_mcrc;
+            ca.table = (const uint32_t *)(d_tabs + 512);
+            for (int j = 0; j < 5; j++) ca.op[j] = op[j];
+            gzd::gz_member_crc<<<(n + 7) / 8, 256, 0, ctx->stream>>>(ca);
+            CK(cudaGetLastError());
+            ctx->launches += 4;
+            uint32_t *h = (uint32_t *)ctx->gz_hcrc.p;                                       // [0] the high-bit flag, [1..n] the members' CRCs
+            CK(cudaMemcpyAsync(h, d_flag, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (uint32_t k = 0; k < n; k++)
+                if (h[1 + k] != mem[k].crc) return fail(ctx, TDG_ERR_GZIP, std::string("gzip error in ") + path + ": corrupt BGZF member");
+            if (u8) {
+                if ((h[0] & 0x80u) || u8->need) {
+                    std::vector<uint8_t> host(text_len);
+                    CK(cudaMemcpy(host.data(), (uint8_t *)ctx->gz_text.p + carry, text_len, cudaMemcpyDeviceToHost));
+                    long long bad = tdg::utf8_feed(*u8, host.data(), host.size());
+                    if (bad >= 0) return fail(ctx, TDG_ERR_UTF8, "position " + std::to_string(bad) + ": invalid UTF-8 in " + path);
+                } else {
+                    u8->offset += text_len;
+                }
+            }
+            rc = sink.text(ctx, (uint8_t *)ctx->gz_text.p, carry, (size_t)text_len);
+            if (rc) return rc;
+        } else {
+            ctx->launches += 1;
+        }
+        delivered += text_len;
+        off = end;
+        if (stats) {
+            stats->rounds++;
+            stats->chunks += n;
+            stats->accepted += n;
+            stats->ms_decode += ms(t0, t1);
+            stats->ms_resolve += ms(t1, now());
+        }
+        if (debug)
+            fprintf(stderr, "gzdev BGZF round: %u members, %zu compressed bytes, %llu bytes of text; upload + decode %.1f, rest %.1f ms\n", n, nb,
+                    (unsigned long long)text_len, ms(t0, t1), ms(t1, now()));
+    }
+    if (foreign || off < map.n) {
+        // something that is not a BGZF member follows (or the file stops inside one): the host feeder's to judge
+        ho.active = true;
+        ho.bgzf = true;
+        ho.bgzf_off = off;
+        ho.delivered = delivered;
+        ho.why = "not a BGZF member";
+    }
+    return TDG_OK;
+}
+
 // Inflates `path` (an ordinary gzip file) on the device round by round and hands every round's
 // text to `sink`.  handled = false: nothing was done (a header this feed does not take: the host
 // feeder starts from the beginning).  Otherwise the text went to the sink up to the end of the
@@ -635,16 +881,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
     using namespace tdg;
     handled = false;
     ho = GzHandover();
-    struct Map {
-        int fd = -1;
-        const uint8_t *p = nullptr;
-        size_t n = 0;
-        ~Map()
-        {
-            if (p) munmap(const_cast<uint8_t *>(p), n);
-            if (fd >= 0) ::close(fd);
-        }
-    } map;
+    GzMap map;
     map.fd = ::open(path, O_RDONLY);
     if (map.fd < 0) return TDG_OK;                       // the host feeder reports it
     struct stat sb;
@@ -653,7 +890,19 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
     void *mp = mmap(nullptr, map.n, PROT_READ, MAP_PRIVATE, map.fd, 0);
     if (mp == MAP_FAILED) return TDG_OK;
     map.p = (const uint8_t *)mp;
-    if (tdg::Feeder::is_bgzf(map.p, std::min<size_t>(map.n, 1024))) return TDG_OK;     // BGZF: members inflate in parallel on the host
+    if (tdg::Feeder::is_bgzf(map.p, std::min<size_t>(map.n, 1024))) {
+        handled = true;
+        int brc = gz_device_feed_bgzf(ctx, path, map, sink, ho, carry, stats, u8);
+        if (brc == TDG_ERR_NOMEM) {
+            // (a buffer that cannot be had: nothing sensible to resume from in the middle of a round -- only
+            // when nothing has been delivered yet does the host feeder simply start over)
+            if (!ho.active && carry == 0 && (!stats || stats->rounds == 0)) {
+                handled = false;
+                return TDG_OK;
+            }
+        }
+        return brc;
+    }
     gzc::Stream st;
     if (!st.open(map.p, map.n)) return TDG_OK;
     int rc = gz_tables(ctx);
@@ -686,23 +935,8 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
     };
 
     int up_i = 0;
-    // file bytes [off, end) -> compressed buffer `which`, through the three pinned buffers, on `stream`
     auto upload = [&](int which, size_t off, size_t end, cudaStream_t stream) -> int {
-        tdg_ctx::Grow &g = which ? ctx->gz_comp2 : ctx->gz_comp;
-        const size_t nb = end - off, padded = (nb + 3) / 4 * 4 + 256;
-        int rc = grow(ctx, g, padded, false);
-        if (rc) return rc;
-        const size_t piece = ctx->file_buf_cap;
-        for (size_t at = 0; at < nb; at += piece, up_i = (up_i + 1) % 3) {
-            const size_t m = std::min(piece, nb - at);
-            CK(cudaEventSynchronize(ctx->gz_up[up_i]));
-            if (!gz_pread_parallel(map.fd, ctx->file_buf[up_i], m, off + at, threads))
-                return fail(ctx, TDG_ERR_IO, std::string("read error on ") + path);
-            CK(cudaMemcpyAsync((uint8_t *)g.p + at, ctx->file_buf[up_i], m, cudaMemcpyHostToDevice, stream));
-            CK(cudaEventRecord(ctx->gz_up[up_i], stream));
-        }
-        CK(cudaMemsetAsync((uint8_t *)g.p + nb, 0, padded - nb, stream));
-        return TDG_OK;
+        return gz_upload(ctx, map, path, threads, up_i, which, off, end, stream);
     };
     int cur = 0;                                             // which compressed buffer the round reads
     bool pre_valid = false;                                  // the other one holds [pre_off, pre_end) of the file
@@ -749,6 +983,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         auto t1 = now();
         // ---- scan + decode
         gzd::RoundArgs a;
+        memset(&a, 0, sizeof(a));                            // (m_start / m_end stay null: this is one stream, not BGZF members)
         a.in = (const uint32_t *)((const uint8_t *)comp.p + comp_skip);
         a.nwords = nwords;
         a.in_bits = (uint64_t)nb * 8;
@@ -1632,9 +1867,10 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     std::thread reader([&]() {
         // host feed: parallel pread / parallel BGZF inflate / zlib, see tdg_feed.h
         tdg::Feeder feed;
-        int orc = ho.active ? feed.open_resume(path, ho.pos_bit, ho.to_zlib ? nullptr : ho.window.data(), ho.hist, ho.crc, ho.member_len,
-                                               ho.delivered)
-                            : feed.open(path, gz != 0);
+        int orc = !ho.active ? feed.open(path, gz != 0)
+                  : ho.bgzf  ? feed.open_resume_bgzf(path, ho.bgzf_off, ho.delivered)
+                             : feed.open_resume(path, ho.pos_bit, ho.to_zlib ? nullptr : ho.window.data(), ho.hist, ho.crc, ho.member_len,
+                                                ho.delivered);
         int bi = 0;
         for (;;) {
             Buf &b = bufs[bi];
@@ -1780,9 +2016,10 @@ int tdg_gz_inflate_host(tdg_ctx *ctx, const char *path, void *dst, size_t cap, u
     size_t used = sink.used;
     if (!handled || ho.active) {
         tdg::Feeder feed;
-        int orc = ho.active ? feed.open_resume(path, ho.pos_bit, ho.to_zlib ? nullptr : ho.window.data(), ho.hist, ho.crc, ho.member_len,
-                                               ho.delivered)
-                            : feed.open(path, true);
+        int orc = !ho.active ? feed.open(path, true)
+                  : ho.bgzf  ? feed.open_resume_bgzf(path, ho.bgzf_off, ho.delivered)
+                             : feed.open_resume(path, ho.pos_bit, ho.to_zlib ? nullptr : ho.window.data(), ho.hist, ho.crc, ho.member_len,
+                                                ho.delivered);
         if (orc) return fail(ctx, orc, feed.error());
         for (;;) {
             if (used == cap) return fail(ctx, TDG_ERR_ARG, "output buffer too small");

@@ -120,6 +120,33 @@ public:
         return rc;
     }
 
+    // BGZF member at h: its size and the length of its header (public form of bgzf_header)
+    static bool bgzf_member(const uint8_t *h, size_t n, uint32_t &csize, uint32_t &hlen) { return bgzf_header(h, n, csize, hlen); }
+
+    // Continue a BGZF file at the member that starts at file offset `off` (`delivered`
+    // uncompressed bytes went out already: the device feed's, tdg_gzdev.cuh).
+    int open_resume_bgzf(const char *path, uint64_t off, uint64_t delivered)
+    {
+        int rc = open(path, true);
+        if (rc) return rc;
+        if (off == 0) return 0;
+        if (mode_ != BGZF) {
+            // (one thread, or a first header that is not BGZF after all): zlib from the uncompressed offset
+            close();
+            fd_ = ::open(path, O_RDONLY);
+            if (fd_ < 0) return fail(-3, std::string("cannot open ") + path);
+            mode_ = GZ;
+            rc = open_gz(delivered);
+            gz_first_ = false;
+            return rc;
+        }
+        cbuf_.clear();
+        cused_ = 0;
+        cpos_ = off;
+        delivered_ = delivered;
+        return 0;
+    }
+
     // does the file image start with a BGZF member?
     static bool is_bgzf(const uint8_t *h, size_t n)
     {

@@ -66,6 +66,8 @@ struct RoundArgs {
     gzl::Meta *meta;
     const uint8_t *kraft3;
     uint16_t *cold;              // [nchunks][COLD_U16]: a lane's list of long-code symbols (the scan's warps use it first)
+    // BGZF: every chunk is a whole member -- lane k inflates [m_start[k], m_end[k]) (bits from `in`) to its final block
+    const uint64_t *m_start, *m_end;
 };
 
 __device__ __forceinline__ uint64_t nominal_rel(const RoundArgs &a, uint64_t k)
@@ -141,7 +143,8 @@ __global__ void __launch_bounds__(DEC_THREADS) gz_decode(const RoundArgs a)
         const gzl::Mem<32> m{s_lane + (size_t)warp * gzl::LANE_U16 * 32 + lane * 2, a.cold + (size_t)k * gzl::COLD_U16};
         const uint64_t stop = nominal_rel(a, k + 1);
         uint16_t *out = a.syms + (size_t)k * a.tokcap;
-        if (k == 0) z.init(m, a.in, a.nwords, a.in_bits, true, a.pos_rel, nullptr, 0, stop, a.hist, out, a.tokcap, a.symcap, &r);
+        if (a.m_start) z.init(m, a.in, a.nwords, a.m_end[k], true, a.m_start[k], nullptr, 0, ~0ull, 0, out, a.tokcap, a.symcap, &r);
+        else if (k == 0) z.init(m, a.in, a.nwords, a.in_bits, true, a.pos_rel, nullptr, 0, stop, a.hist, out, a.tokcap, a.symcap, &r);
         else z.init(m, a.in, a.nwords, a.in_bits, false, nominal_rel(a, k), a.cand + (size_t)k * MAXC, a.ncand[k], stop, 0, out, a.tokcap, a.symcap, &r);
     }
     // every lane of the warp takes every step together: the vote is the point of reconvergence
@@ -359,6 +362,48 @@ __global__ void __launch_bounds__(RES_THREADS) gz_resolve(const ResArgs a)
     if (tid == 0) a.crc[blockIdx.x] = s_part[0];
     any = __reduce_or_sync(0xFFFFFFFFu, any);
     if ((tid & 31u) == 0 && (any & 0x80u)) atomicOr(a.flag, 0x80u);
+}
+
+// BGZF: the CRC-32 of every member's bytes (at most 64 KiB each), one warp per member.  Lane l takes
+// the l-th 2 KiB of the member laid against the END of a 64 KiB frame (the lanes in front of a short
+// member have nothing: a register that is still zero stays zero under the shifts); the lane that
+// holds the member's first byte starts from 0xFFFFFFFF as the CRC asks.
+struct MemberCrcArgs {
+    const uint16_t *syms;        // [n][stride] the members' bytes as 16-bit symbols
+    uint32_t stride;
+    const uint32_t *lens;
+    uint32_t n;
+    uint32_t *crc;
+    const uint32_t *table;
+    uint32_t op[5];              // x^(8 * 2048 * 2^j) modulo the polynomial
+};
+
+__global__ void __launch_bounds__(256) gz_member_crc(const MemberCrcArgs a)
+{
+    __shared__ uint32_t s_tab[256];
+    s_tab[threadIdx.x] = a.table[threadIdx.x];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= a.n) return;
+    const uint32_t len = a.lens[k] < 65536u ? a.lens[k] : 65536u;
+    const uint32_t shift = 65536u - len;
+    const uint16_t *src = a.syms + (size_t)k * a.stride;
+    uint32_t reg = 0;
+    const uint32_t u0 = lane * 2048u;
+    for (uint32_t j = 0; j < 2048u; j++) {
+        const uint32_t u = u0 + j;
+        if (u < shift) continue;
+        const uint32_t i = u - shift;
+        if (i == 0) reg = 0xFFFFFFFFu;
+        reg = s_tab[(reg ^ src[i]) & 0xFFu] ^ (reg >> 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const uint32_t other = __shfl_down_sync(0xFFFFFFFFu, reg, 1u << j);
+        if ((lane & ((2u << j) - 1u)) == 0) reg = gf_mul(a.op[j], reg) ^ other;
+    }
+    if (lane == 0) a.crc[k] = len ? reg ^ 0xFFFFFFFFu : 0u;
 }
 
 }  // namespace gzd

@@ -301,3 +301,64 @@ def test_count_gzip_file_in_many_rounds(tmp_path, monkeypatch, max_chunks):
     assert tot[:3] == wtot and (got == want).all()
     info = counting.get_engine(0).gz_inflate_host(p, len(fq) + 100)[1]
     assert info["mode"] == 0 and info["rounds"] > 3
+
+
+# ---------------------------------------------------------------------------------------------
+# BGZF: every member is its own stream -- one lane per member, nothing speculative
+
+def test_device_feed_bgzf(tmp_path, monkeypatch):
+    from feed_check import bgzf_block, bgzf_compress
+    data = _fastq_like(14, 12 << 20)
+    eng = counting.get_engine(0)
+    for blob, want in ((bgzf_compress(data), data),
+                       (bgzf_compress(data[:3000000], block=777, eof_marker=False), data[:3000000]),      # tiny members, no EOF marker
+                       (bgzf_compress(data[:1 << 20], level=1) + bgzf_compress(data[1 << 20:5 << 20], level=9), data[:5 << 20])):
+        out, info, ms = _inflate(tmp_path, blob, len(want) + 100, name="b.gz")
+        assert out == want and info["mode"] == 0 and info["accepted"] == info["chunks"] > 0, info
+    # few lanes per round
+    monkeypatch.setenv("TDG_GZDEV_MAXCHUNKS", "13")
+    out, info, ms = _inflate(tmp_path, bgzf_compress(data[:4 << 20]), (4 << 20) + 100, name="b.gz")
+    assert out == data[:4 << 20] and info["rounds"] > 4
+    monkeypatch.delenv("TDG_GZDEV_MAXCHUNKS")
+    # BGZF members followed by an ordinary member: the host feeder continues there
+    half = 3 << 20
+    blob = bgzf_compress(data[:half], eof_marker=False) + gzip.compress(data[half:2 * half])
+    out, info, ms = _inflate(tmp_path, blob, 2 * half + 100, name="b.gz")
+    assert out == data[:2 * half] and info["mode"] == 1
+    # a damaged member, a wrong CRC, a wrong length: a gzip error, as from the host feeder
+    good = bgzf_compress(data[:2 << 20])
+    for kind in ("flip", "crc", "isize"):
+        bad = bytearray(good)
+        first = struct.unpack("<H", good[16:18])[0] + 1                  # size of the first member
+        if kind == "flip":
+            bad[len(bad) // 2] ^= 0x55
+        elif kind == "crc":
+            bad[first - 8] ^= 1
+        else:
+            bad[first - 4] ^= 1
+        p = str(tmp_path / "bad.gz")
+        with open(p, "wb") as fh:
+            fh.write(bytes(bad))
+        with pytest.raises(_native.TdgError) as e:
+            eng.gz_inflate_host(p, (2 << 20) + 100)
+        assert e.value.code == _native.TDG_ERR_GZIP, kind
+        with pytest.raises(Exception):
+            gzip.open(p, "rb").read()
+
+
+def test_count_bgzf_file_on_the_device(tmp_path, monkeypatch):
+    from feed_check import bgzf_compress
+    monkeypatch.setenv("TDG_GZDEV_MIN", "0")
+    rng, bcs, tags = _tables(6)
+    fq, _ = synth.make_fastq(60000, bcs, tags, rng)
+    fq = fq[:-1]                                                         # no final newline
+    p = str(tmp_path / "reads.fq.gz")
+    with open(p, "wb") as fh:
+        fh.write(bgzf_compress(fq))
+    want, wtot = c_oracle.Counter(bcs, tags).count(fq)
+    eng = counting.get_engine(0)
+    before = eng.launch_count()
+    tot = []
+    got = np.asarray(counting.find_tags_fastq(p, bcs, tags, totals=tot))
+    assert tot[:3] == wtot and (got == want).all()
+    assert eng.gz_inflate_host(p, len(fq) + 100)[1]["mode"] == 0 and eng.launch_count() > before
