@@ -144,8 +144,9 @@ int         tdg_count_lines_device(tdg_ctx *ctx, const void *dev_bytes, size_t n
  * binding passes that decision.  Plain files are read by host threads into pinned buffers and
  * copied to the device piece by piece.  Ordinary gzip files of 8 MiB and more are inflated ON THE
  * DEVICE (csrc/tdg_gzdev.cuh: the compressed bytes cross PCIe, thousands of lanes enter the one
- * deflate stream speculatively at block starts, the text is born in HBM and counted there); BGZF
- * files, small files, reads behind a `reads_limit`, and the rest of any stream that holds something
+ * deflate stream speculatively at block starts -- or, for BGZF files, inflate one member each --,
+ * the text is born in HBM and counted there); small files, reads behind a `reads_limit`, and the
+ * rest of any stream that holds something
  * the device feed does not judge (stored data it cannot enter, a damaged or truncated stream, a
  * header with unusual flags) are inflated by host threads (csrc/tdg_pgz.h, csrc/tdg_feed.h), which
  * resume at exactly the bit the device feed reached -- so every error is raised by one code path:
