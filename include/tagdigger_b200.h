@@ -156,6 +156,14 @@ int         tdg_count_lines_device(tdg_ctx *ctx, const void *dev_bytes, size_t n
 int         tdg_count_file(tdg_ctx *ctx, const char *path, int gz,
                            uint64_t reads_limit, uint64_t totals[4]);
 
+/* tdg_count_file with a look at what comes next: `next_path` (may be null) names the file the caller
+ * will count after this one; its reading thread is started now, into a second set of pinned
+ * buffers, so that a key of many small files (config 3; the counting stage of config 5) never
+ * waits for a read.  Files the device gzip feed takes are not read ahead.  Nothing is lost when the
+ * next call names another file: the reader is dropped. */
+int         tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit, uint64_t totals[4],
+                            const char *next_path, int next_gz);
+
 /* Frees the working buffers of the device-side gzip feed (tokens, symbols, windows, text: about ten
  * times the compressed bytes of a round, at most ~12 GB); they are kept between files otherwise. */
 int         tdg_release_scratch(tdg_ctx *ctx);

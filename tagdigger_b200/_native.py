@@ -34,7 +34,7 @@ NO_LIMIT = (1 << 63)
 
 EXPORTS = """tdg_abi_version tdg_create tdg_destroy tdg_last_error tdg_set_tags tdg_set_matrix
 tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end_file tdg_count_device
-tdg_count_lines_device tdg_count_file tdg_gz_inflate_host tdg_release_scratch tdg_sync tdg_file_totals tdg_read_matrix tdg_matrix_min tdg_comm_unique_id tdg_comm_init tdg_allreduce_matrix tdg_finish
+tdg_count_lines_device tdg_count_file tdg_count_file2 tdg_gz_inflate_host tdg_release_scratch tdg_sync tdg_file_totals tdg_read_matrix tdg_matrix_min tdg_comm_unique_id tdg_comm_init tdg_allreduce_matrix tdg_finish
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
 tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch tdg_split_begin tdg_split_block tdg_feed_open tdg_feed_read tdg_feed_close tdg_match_batch tdg_write_counts_csv tdg_write_geno_csv""".split()
@@ -111,6 +111,7 @@ def lib():
         "tdg_count_device": (i32, [vp, vp, sz, u64, i32, u64]),
         "tdg_count_lines_device": (i32, [vp, vp, sz, u64, i32, vp]),
         "tdg_count_file": (i32, [vp, ctypes.c_char_p, i32, u64, vp]),
+        "tdg_count_file2": (i32, [vp, ctypes.c_char_p, i32, u64, vp, ctypes.c_char_p, i32]),
         "tdg_gz_inflate_host": (i32, [vp, ctypes.c_char_p, vp, sz, vp, vp, vp]),
         "tdg_release_scratch": (i32, [vp]),
         "tdg_sync": (i32, [vp]),
@@ -317,9 +318,11 @@ class Engine(object):
         self._ck(self._L.tdg_count_lines_device(self._h, dev_ptr, n, line_base, prev_kind, st.ctypes.data))
         return int(st[0]), int(st[1])
 
-    def count_file(self, path, gz, reads_limit=NO_LIMIT):
+    def count_file(self, path, gz, reads_limit=NO_LIMIT, next_path=None, next_gz=False):
+        """next_path: the file that will be counted after this one (its reading starts now)."""
         tot = np.zeros(4, dtype=np.uint64)
-        self._ck(self._L.tdg_count_file(self._h, os.fsencode(path), 1 if gz else 0, reads_limit, tot.ctypes.data))
+        self._ck(self._L.tdg_count_file2(self._h, os.fsencode(path), 1 if gz else 0, reads_limit, tot.ctypes.data,
+                                         os.fsencode(next_path) if next_path else None, 1 if next_gz else 0))
         self.note_hits(int(tot[2]))
         return [int(x) for x in tot]
 

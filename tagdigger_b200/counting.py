@@ -57,13 +57,15 @@ def _is_gz(name):
     return name[-2:].lower() == "gz"            # tagdigger_fun.py:240
 
 
-def _run_file(eng, fqfile, limit):
+def _run_file(eng, fqfile, limit, next_file=None):
     """Stream one file; map library errors to the exceptions the reference's
-    open()/gzip.open() would raise."""
+    open()/gzip.open() would raise.  ``next_file``: the file that will be counted next (the
+    library starts reading it while this one is counted)."""
     with open(fqfile, "rb"):                    # FileNotFoundError / PermissionError / IsADirectoryError
         pass
     try:
-        return eng.count_file(fqfile, _is_gz(fqfile), limit)
+        return eng.count_file(fqfile, _is_gz(fqfile), limit, next_path=next_file,
+                              next_gz=_is_gz(next_file) if next_file else False)
     except _native.TdgError as e:
         if e.code == _native.TDG_ERR_GZIP:
             raise _gzip_exception(e.message)
@@ -239,10 +241,11 @@ def count_files(bckeys, tags, cutsite="TGCAG", maxreads=5e9, device=None, rank=0
         tot = count_file_range(eng, f, rank, world, limit, gather)
         if totals is not None:
             totals[f] = tot[:3]
-    for f in assign_files([f for f in files if f not in split], rank, world):
+    mine = assign_files([f for f in files if f not in split], rank, world)
+    for i, f in enumerate(mine):
         p = plans[f]
         load_plan(eng, p, row_of=rows[f], set_tags=False)
-        tot = _run_file(eng, f, limit)
+        tot = _run_file(eng, f, limit, next_file=mine[i + 1] if i + 1 < len(mine) else None)
         print("{0}: Reads: {1} With barcode and cut site: {2} With tag: {3}".format(f, tot[0], tot[1], tot[2]))
         if totals is not None:
             totals[f] = tot[:3]

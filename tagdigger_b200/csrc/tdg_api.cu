@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -45,6 +46,92 @@ struct Slot {
 };
 
 }  // namespace
+
+// how the host feeder continues when the device gzip feed stops early (tdg_gzdev.cuh)
+struct GzHandover {
+    bool active = false;
+    bool to_zlib = false;
+    bool bgzf = false;           // BGZF: the host feeder continues at the member at file offset bgzf_off
+    uint64_t bgzf_off = 0;
+    uint64_t pos_bit = 0, member_len = 0, delivered = 0;
+    uint32_t hist = 0, crc = 0;
+    std::vector<uint8_t> window;
+    std::string why;
+};
+
+// The host side of tdg_count_file for one file: a thread that reads (or inflates) the file through
+// tdg_feed.h into three pinned buffers, one ahead of the other.  It can be started BEFORE its
+// file's turn (the `next_path` of tdg_count_file2): a key of many small files then never waits for
+// a read -- the next file's bytes arrive while this file's are copied and counted.
+struct FileReader {
+    static constexpr int NBUF = 3;
+    struct Buf {
+        uint8_t *p = nullptr;
+        size_t n = 0;
+        int state = 0;          // 0 free, 1 full
+        bool high = false;      // some byte >= 0x80: the text needs UTF-8 validation
+        int err = 0;            // the read that should have filled this buffer failed
+        std::string msg;
+    } bufs[NBUF];
+    std::mutex mu;
+    std::condition_variable cv;
+    bool stop = false;
+    std::thread th;
+    std::string path;
+    bool gz = false;
+    size_t chunk = 0;
+    int set = 0;                // which of the context's two sets of pinned buffers it fills
+    GzHandover ho;
+
+    void start()
+    {
+        th = std::thread([this]() {
+            // host feed: parallel pread / parallel BGZF inflate / zlib, see tdg_feed.h
+            tdg::Feeder feed;
+            const char *p = path.c_str();
+            int orc = !ho.active ? feed.open(p, gz)
+                      : ho.bgzf  ? feed.open_resume_bgzf(p, ho.bgzf_off, ho.delivered)
+                                 : feed.open_resume(p, ho.pos_bit, ho.to_zlib ? nullptr : ho.window.data(), ho.hist, ho.crc, ho.member_len,
+                                                    ho.delivered);
+            int bi = 0;
+            for (;;) {
+                Buf &b = bufs[bi];
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return b.state == 0 || stop; });
+                    if (stop) break;
+                }
+                long long r = orc ? orc : feed.fill(b.p, chunk);
+                size_t got = 0;
+                int err = 0;
+                std::string msg;
+                if (r < 0) { err = (int)r; msg = feed.error(); }
+                else got = (size_t)r;
+                const bool high = got ? tdg::has_high_bit_mt(b.p, got, feed.threads()) : false;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    b.n = got;
+                    b.high = high;
+                    b.err = err;
+                    b.msg = msg;
+                    b.state = 1;
+                }
+                cv.notify_all();
+                if (got == 0 || err) break;           // end of file, or the defect: nothing comes after it
+                bi = (bi + 1) % NBUF;
+            }
+        });
+    }
+    ~FileReader()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+};
 
 struct tdg_ctx {
     int device = 0;
@@ -117,6 +204,9 @@ struct tdg_ctx {
     // pinned buffers of tdg_count_file (kept between files: pinning 192 MiB costs ~0.1 s)
     uint8_t *file_buf[3] = {nullptr, nullptr, nullptr};
     size_t file_buf_cap = 0;
+    uint8_t *file_buf2[3] = {nullptr, nullptr, nullptr};     // a second set: the reader that runs ahead for the next file
+    size_t file_buf2_cap = 0;
+    std::unique_ptr<FileReader> ahead;                        // started by tdg_count_file2's next_path
 
     // device-side gzip feed (tdg_gzdev.cuh): growable buffers, kept between files
     Grow gz_comp, gz_comp2, gz_syms, gz_sym2, gz_ntok, gz_meta, gz_cand, gz_ncand, gz_windows, gz_text, gz_crc, gz_lens, gz_offs, gz_tabs, gz_carry, gz_cold;   // device
@@ -550,17 +640,6 @@ int end_file_impl(tdg_ctx *ctx, uint64_t reads_limit)
 
 // ---------------------------------------------------------------------------
 // Device-side gzip feed (tdg_gzlane.h, tdg_gzchain.h, tdg_gzdev.cuh)
-
-struct GzHandover {              // how the host feeder continues when the device feed stops early
-    bool active = false;
-    bool to_zlib = false;
-    bool bgzf = false;           // BGZF: the host feeder continues at the member at file offset bgzf_off
-    uint64_t bgzf_off = 0;
-    uint64_t pos_bit = 0, member_len = 0, delivered = 0;
-    uint32_t hist = 0, crc = 0;
-    std::vector<uint8_t> window;
-    std::string why;
-};
 
 struct GzStats {
     uint32_t rounds = 0, chunks = 0, accepted = 0;
@@ -1358,8 +1437,11 @@ void tdg_destroy(tdg_ctx *ctx)
             if (ctx->gz_up[i]) cudaEventDestroy(ctx->gz_up[i]);
         if (ctx->gz_pre) cudaEventDestroy(ctx->gz_pre);
         if (ctx->d_replicas) cudaFree(ctx->d_replicas);
+        ctx->ahead.reset();
         for (int i = 0; i < 3; i++)
             if (ctx->file_buf[i]) cudaFreeHost(ctx->file_buf[i]);
+        for (int i = 0; i < 3; i++)
+            if (ctx->file_buf2[i]) cudaFreeHost(ctx->file_buf2[i]);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     }
@@ -1780,7 +1862,58 @@ int tdg_timing_end(tdg_ctx *ctx, double *kernel_ms, uint32_t *nlaunch)
 // Whole-file streaming: a reader thread (read() or zlib inflate) fills pinned
 // buffers; the calling thread feeds them to the GPU.
 
-int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit, uint64_t totals[4])
+namespace {
+
+int ensure_file_bufs(tdg_ctx *ctx, int set)
+{
+    uint8_t **buf = set ? ctx->file_buf2 : ctx->file_buf;
+    size_t &cap = set ? ctx->file_buf2_cap : ctx->file_buf_cap;
+    if (cap >= ctx->chunk_bytes) return TDG_OK;
+    for (int i = 0; i < 3; i++) {
+        if (buf[i]) cudaFreeHost(buf[i]);
+        buf[i] = nullptr;
+    }
+    cap = 0;
+    for (int i = 0; i < 3; i++) {
+        cudaError_t e = cudaHostAlloc(&buf[i], ctx->chunk_bytes, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            for (int k = 0; k <= i; k++) {
+                if (buf[k]) cudaFreeHost(buf[k]);
+                buf[k] = nullptr;
+            }
+            return fail(ctx, TDG_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+        }
+    }
+    cap = ctx->chunk_bytes;
+    return TDG_OK;
+}
+
+size_t file_chunk(const tdg_ctx *ctx, uint64_t reads_limit)
+{
+    // With a read limit the reference stops reading at the maxreads'th sequence line
+    // (tagdigger_fun.py:272-273): feed smaller pieces, so that little is read, inflated and copied
+    // beyond that point.
+    const bool limited = reads_limit < ((uint64_t)1 << 61);
+    return limited ? std::min<size_t>(ctx->chunk_bytes, (size_t)8 << 20) : ctx->chunk_bytes;
+}
+
+std::unique_ptr<FileReader> start_reader(tdg_ctx *ctx, const char *path, bool gz, size_t chunk, int set, const GzHandover *ho)
+{
+    std::unique_ptr<FileReader> r(new FileReader());
+    uint8_t **buf = set ? ctx->file_buf2 : ctx->file_buf;
+    for (int i = 0; i < FileReader::NBUF; i++) r->bufs[i].p = buf[i];
+    r->path = path;
+    r->gz = gz;
+    r->chunk = chunk;
+    r->set = set;
+    if (ho) r->ho = *ho;
+    r->start();
+    return r;
+}
+
+}  // namespace
+
+int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit, uint64_t totals[4], const char *next_path, int next_gz)
 {
     int rc = need_ready(ctx);
     if (rc) return rc;
@@ -1788,53 +1921,33 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     CK(cudaSetDevice(ctx->device));
     rc = ensure_slots(ctx);
     if (rc) return rc;
-
-    constexpr int NBUF = 3;
-    struct Buf {
-        uint8_t *p = nullptr;
-        size_t n = 0;
-        int state = 0;   // 0 free, 1 full
-        bool high = false;      // some byte >= 0x80: the text needs UTF-8 validation
-        int err = 0;            // the read that should have filled this buffer failed
-        std::string msg;
-    } bufs[NBUF];
-    static_assert(NBUF == 3, "tdg_ctx::file_buf holds three buffers");
-    if (ctx->file_buf_cap < ctx->chunk_bytes) {
-        for (int i = 0; i < NBUF; i++) {
-            if (ctx->file_buf[i]) cudaFreeHost(ctx->file_buf[i]);
-            ctx->file_buf[i] = nullptr;
-        }
-        ctx->file_buf_cap = 0;
-        for (int i = 0; i < NBUF; i++) {
-            cudaError_t e = cudaHostAlloc(&ctx->file_buf[i], ctx->chunk_bytes, cudaHostAllocDefault);
-            if (e != cudaSuccess) {
-                for (int k = 0; k <= i; k++) {
-                    if (ctx->file_buf[k]) cudaFreeHost(ctx->file_buf[k]);
-                    ctx->file_buf[k] = nullptr;
-                }
-                return fail(ctx, TDG_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
-            }
-        }
-        ctx->file_buf_cap = ctx->chunk_bytes;
-    }
-    for (int i = 0; i < NBUF; i++) bufs[i].p = ctx->file_buf[i];
-    std::mutex mu;
-    std::condition_variable cv;
-    bool stop = false;
-    // With a read limit the reference stops reading at the maxreads'th sequence line
-    // (tagdigger_fun.py:272-273): feed smaller pieces, so that little is read, inflated and copied
-    // beyond that point.
     const bool limited = reads_limit < ((uint64_t)1 << 61);
-    size_t chunk = ctx->chunk_bytes;
-    if (limited) chunk = std::min<size_t>(chunk, (size_t)8 << 20);
+    const size_t chunk = file_chunk(ctx, reads_limit);
+
+    // a reader that was started for this file while the one before it was counted
+    std::unique_ptr<FileReader> reader;
+    if (ctx->ahead && ctx->ahead->path == path && ctx->ahead->gz == (gz != 0) && ctx->ahead->chunk == chunk) reader = std::move(ctx->ahead);
+    ctx->ahead.reset();
+    const int set = reader ? reader->set : 0;
+    rc = ensure_file_bufs(ctx, set);
+    if (rc) return rc;
+    // ... and the one for the file that comes next (files the device gzip feed takes are not read ahead)
+    if (next_path && *next_path && std::string(next_path) != path && !(next_gz && gz_device_wanted(next_path, reads_limit))) {
+        struct stat sb;
+        if (stat(next_path, &sb) == 0 && S_ISREG(sb.st_mode)) {
+            rc = ensure_file_bufs(ctx, set ^ 1);
+            if (rc) return rc;
+            ctx->ahead = start_reader(ctx, next_path, next_gz != 0, chunk, set ^ 1, nullptr);
+        }
+    }
 
     // Ordinary gzip files are inflated on the DEVICE (tdg_gzdev.cuh): the compressed bytes cross
-    // PCIe, the text is born in HBM.  Whatever that feed does not take -- BGZF, small files, a read
+    // PCIe, the text is born in HBM.  Whatever that feed does not take -- small files, a read
     // limit, and the rest of any stream with something unusual in it -- goes through the host
     // feeder below, which resumes exactly where the device feed stopped.
     tdg::Utf8State u8;
     GzHandover ho;
-    if (gz && gz_device_wanted(path, reads_limit)) {
+    if (!reader && gz && gz_device_wanted(path, reads_limit)) {
         bool handled = false;
         size_t dcarry = 0;
         GzCountSink sink(reads_limit);
@@ -1863,43 +1976,9 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
             return drc;
         }
     }
+    if (!reader) reader = start_reader(ctx, path, gz != 0, chunk, set, ho.active ? &ho : nullptr);
 
-    std::thread reader([&]() {
-        // host feed: parallel pread / parallel BGZF inflate / zlib, see tdg_feed.h
-        tdg::Feeder feed;
-        int orc = !ho.active ? feed.open(path, gz != 0)
-                  : ho.bgzf  ? feed.open_resume_bgzf(path, ho.bgzf_off, ho.delivered)
-                             : feed.open_resume(path, ho.pos_bit, ho.to_zlib ? nullptr : ho.window.data(), ho.hist, ho.crc, ho.member_len,
-                                                ho.delivered);
-        int bi = 0;
-        for (;;) {
-            Buf &b = bufs[bi];
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return b.state == 0 || stop; });
-                if (stop) break;
-            }
-            long long r = orc ? orc : feed.fill(b.p, chunk);
-            size_t got = 0;
-            int err = 0;
-            std::string msg;
-            if (r < 0) { err = (int)r; msg = feed.error(); }
-            else got = (size_t)r;
-            const bool high = got ? tdg::has_high_bit_mt(b.p, got, feed.threads()) : false;
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                b.n = got;
-                b.high = high;
-                b.err = err;
-                b.msg = msg;
-                b.state = 1;
-            }
-            cv.notify_all();
-            if (got == 0 || err) break;           // end of file, or the defect: nothing comes after it
-            bi = (bi + 1) % NBUF;
-        }
-    });
-
+    FileReader &fr = *reader;
     int bi = 0;
     int result = TDG_OK;
     tdg::LineLimit ll;
@@ -1908,10 +1987,10 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     if (limited) ll.remaining = reads_limit ? 4 * reads_limit - 2 : 1;
     bool at_eof = false;
     for (;;) {
-        Buf &b = bufs[bi];
+        FileReader::Buf &b = fr.bufs[bi];
         {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return b.state == 1; });
+            std::unique_lock<std::mutex> lk(fr.mu);
+            fr.cv.wait(lk, [&] { return b.state == 1; });
         }
         if (b.err) { result = fail(ctx, b.err, b.msg); break; }
         if (b.n == 0) { at_eof = true; break; }
@@ -1928,19 +2007,14 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
         }
         if (use) result = submit_impl(ctx, b.p, use, reads_limit, true);
         {
-            std::lock_guard<std::mutex> lk(mu);
+            std::lock_guard<std::mutex> lk(fr.mu);
             b.state = 0;
         }
-        cv.notify_all();
+        fr.cv.notify_all();
         if (result || ll.reached) break;
-        bi = (bi + 1) % NBUF;
+        bi = (bi + 1) % FileReader::NBUF;
     }
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        stop = true;
-    }
-    cv.notify_all();
-    reader.join();
+    reader.reset();                                          // stops and joins the reading thread
     if (result == TDG_OK && at_eof && tdg::utf8_finish(u8) >= 0)
         result = fail(ctx, TDG_ERR_UTF8, "position " + std::to_string(tdg::utf8_finish(u8)) + ": unexpected end of data in " + path);
     if (result == TDG_OK) result = end_file_impl(ctx, reads_limit);
@@ -1949,6 +2023,11 @@ int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit,
     cudaStreamSynchronize(ctx->stream);
     if (result == TDG_OK && totals) result = tdg_file_totals(ctx, totals);
     return result;
+}
+
+int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit, uint64_t totals[4])
+{
+    return tdg_count_file2(ctx, path, gz, reads_limit, totals, nullptr, 0);
 }
 
 // Gives the working buffers of the device-side gzip feed back (a 1.2 GB round holds about 12 GB:
@@ -1983,15 +2062,9 @@ int tdg_gz_inflate_host(tdg_ctx *ctx, const char *path, void *dst, size_t cap, u
     CK(cudaSetDevice(ctx->device));
     rc = ensure_slots(ctx);
     if (rc) return rc;
-    if (ctx->file_buf_cap < ctx->chunk_bytes) {
-        for (int i = 0; i < 3; i++) {
-            if (ctx->file_buf[i]) cudaFreeHost(ctx->file_buf[i]);
-            ctx->file_buf[i] = nullptr;
-        }
-        ctx->file_buf_cap = 0;
-        for (int i = 0; i < 3; i++) CK(cudaHostAlloc(&ctx->file_buf[i], ctx->chunk_bytes, cudaHostAllocDefault));
-        ctx->file_buf_cap = ctx->chunk_bytes;
-    }
+    ctx->ahead.reset();
+    rc = ensure_file_bufs(ctx, 0);
+    if (rc) return rc;
     GzCopySink sink((uint8_t *)dst, cap);
     GzHandover ho;
     GzStats st;

@@ -234,7 +234,7 @@ private:
     {
         if (pos_ >= size_) return fill_seq_at(p, cap);      // the file may have grown: plain reads from here
         size_t n = (size_t)std::min<uint64_t>(cap, size_ - pos_);
-        int nt = (int)std::min<size_t>((size_t)threads_, std::max<size_t>(1, n >> 22));   // >= 4 MiB per thread
+        int nt = (int)std::min<size_t>((size_t)threads_, std::max<size_t>(1, n >> 20));   // >= 1 MiB per thread (pooled threads: a loop costs microseconds to start)
         std::vector<long long> got(nt, 0);
         auto work = [&](int t) {
             size_t lo = n / nt * t, hi = t == nt - 1 ? n : n / nt * (t + 1);

@@ -362,3 +362,34 @@ def test_count_bgzf_file_on_the_device(tmp_path, monkeypatch):
     got = np.asarray(counting.find_tags_fastq(p, bcs, tags, totals=tot))
     assert tot[:3] == wtot and (got == want).all()
     assert eng.gz_inflate_host(p, len(fq) + 100)[1]["mode"] == 0 and eng.launch_count() > before
+
+
+def test_count_files_reads_the_next_file_ahead(tmp_path):
+    """count_files names every file's successor to the library (tdg_count_file2): plain files, small gzip files,
+    an empty file and a file without a final newline in one key give the per-file oracle rows; a file that is
+    missing raises when its turn comes, not before."""
+    rng, bcs, tags = _tables(8)
+    bckeys, want_rows, names = {}, [], []
+    for i in range(9):
+        fq, _ = synth.make_fastq(4000 + 700 * i, bcs[:4], tags, rng)
+        if i == 3:
+            fq = b""
+        if i == 5:
+            fq = fq[:-1]
+        name = str(tmp_path / ("s%02d.fq%s" % (i, ".gz" if i % 3 == 1 else "")))
+        with open(name, "wb") as fh:
+            fh.write(gzip.compress(fq) if name.endswith("gz") else fq)
+        bckeys[name] = [list(bcs[:4]), ["S%d_%d" % (i, b) for b in range(4)]]
+        want_rows.append(c_oracle.Counter(bcs[:4], tags).count(fq)[0])
+        names.append(name)
+    samples, counts = counting.count_files(bckeys, tags, as_array=True)
+    assert len(samples) == 36 and (np.asarray(counts) == np.concatenate(want_rows)).all()
+    # twice in a row (the reader started for a file that never came is dropped), then with a hole in the key
+    samples, counts = counting.count_files(bckeys, tags, as_array=True)
+    assert (np.asarray(counts) == np.concatenate(want_rows)).all()
+    import os
+    os.remove(names[4])
+    with pytest.raises(FileNotFoundError):
+        counting.count_files(bckeys, tags)
+    got = np.asarray(counting.find_tags_fastq(names[5], bcs[:4], tags))
+    assert (got == want_rows[5]).all()
