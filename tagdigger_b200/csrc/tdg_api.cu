@@ -603,6 +603,8 @@ int submit_impl(tdg_ctx *ctx, const uint8_t *bytes, size_t n, uint64_t reads_lim
     if (rc) return rc;
     size_t pos = 0;
     int last = -1;
+    static const bool sdebug = getenv("TDG_FILE_DEBUG") != nullptr;
+    const auto s0 = std::chrono::steady_clock::now();
     while (pos < n) {
         size_t m = n - pos < ctx->chunk_bytes ? n - pos : ctx->chunk_bytes;
         size_t cut = line_cut(bytes + pos, m);
@@ -613,7 +615,12 @@ int submit_impl(tdg_ctx *ctx, const uint8_t *bytes, size_t n, uint64_t reads_lim
         if (rc) return rc;
         pos += m;
     }
+    const auto s1 = std::chrono::steady_clock::now();
     if (wait_copied && last >= 0) CK(cudaEventSynchronize(ctx->slot[last].copied));
+    if (sdebug)
+        fprintf(stderr, "  submit %zu bytes: enqueue %.2f ms, wait for the copy %.2f ms\n", n,
+                std::chrono::duration<double, std::milli>(s1 - s0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s1).count());
     return TDG_OK;
 }
 
@@ -641,10 +648,63 @@ int end_file_impl(tdg_ctx *ctx, uint64_t reads_limit)
 // ---------------------------------------------------------------------------
 // Device-side gzip feed (tdg_gzlane.h, tdg_gzchain.h, tdg_gzdev.cuh)
 
+constexpr int TDG_STOP_ROUND = -1000;       // (internal) the sink does not want this round
+
 struct GzStats {
     uint32_t rounds = 0, chunks = 0, accepted = 0;
     double ms_upload = 0, ms_scan = 0, ms_decode = 0, ms_host = 0, ms_resolve = 0, ms_sink = 0;
 };
+
+// The read limit of find_tags_fastq (maxreads, default 5e9: tagdigger_fun.py:192, :272-273) on the
+// host side of tdg_count_file.  The kernels apply the limit exactly whatever the host does; what the
+// host owes the reference is to STOP READING at the limit (a defect behind it is never met).  Looking
+// for the limit's line end costs a pass over every byte, so it is done only where the limit can be:
+// a piece of n bytes holds at most n line ends, and while (line ends so far, at most) + n stays below
+// the limit's line the piece goes through untouched.  When that bound is used up, the exact number of
+// lines is read back from the device (a few times per 20 GB at the default limit) -- and only when
+// the limit really lies within reach are pieces scanned (tdg::LineLimit).
+struct LimitState {
+    bool has = false;
+    uint64_t line = 0;           // the limit's line end: number 4 * maxreads - 2
+    uint64_t lines_ub = 0;       // line ends handed to the device so far, at most
+    bool careful = false;        // pieces are scanned
+    tdg::LineLimit ll;
+    uint8_t last_byte = 0;       // of the text so far (a '\r' there may still end a line)
+
+    void init(uint64_t reads_limit, size_t chunk_bytes)
+    {
+        has = reads_limit < ((uint64_t)1 << 60);
+        line = has ? (reads_limit ? 4 * reads_limit - 2 : 1) : 0;
+        if (has && line <= chunk_bytes) {                    // within reach of the first piece: scan from the start
+            careful = true;
+            ll.remaining = line;
+        }
+    }
+};
+
+// May `nbytes` more bytes of text go to the device without a look?  1 yes, 0 no (lim.careful is set and
+// lim.ll counts down to the limit's line from here), negative: error.
+int limit_admits(tdg_ctx *ctx, LimitState &lim, size_t nbytes)
+{
+    if (!lim.has) return 1;
+    if (lim.careful) return 0;
+    if (lim.lines_ub + nbytes < lim.line) {
+        lim.lines_ub += nbytes;
+        return 1;
+    }
+    uint64_t t[4];
+    int rc = tdg_file_totals(ctx, t);                        // (synchronises) t[3]: line ends counted so far, exactly
+    if (rc) return rc;
+    lim.lines_ub = t[3];
+    if (lim.lines_ub + nbytes < lim.line) {
+        lim.lines_ub += nbytes;
+        return 1;
+    }
+    lim.careful = true;
+    lim.ll.remaining = lim.line - t[3];
+    lim.ll.prev_cr = lim.last_byte == '\r';
+    return 0;
+}
 
 // what happens to a round's text: counted (tdg_count_file) or copied out (tdg_gz_inflate_host)
 struct GzSink {
@@ -653,6 +713,9 @@ struct GzSink {
     // Sets `carry` to the number of bytes it wants to see again, in front of the next round's text
     // (they must be at d_buf[0 ..) when it returns -- stream order).
     virtual int text(tdg_ctx *ctx, uint8_t *d_buf, size_t &carry, size_t len) = 0;
+    // Asked before a round's text is accepted: 1 go on, 0 the device feed must stop in front of this
+    // round (a read limit within reach: the host feeder takes over and stops at the limit), < 0 error.
+    virtual int may_take(tdg_ctx *, size_t) { return 1; }
 };
 
 int gz_io_threads()
@@ -851,6 +914,14 @@ int gz_device_feed_bgzf(tdg_ctx *ctx, const char *path, const GzMap &map, GzSink
             const bool good = c.flags == (gzl::F_FOUND | gzl::F_FINAL) && c.out_len == mem[k].isize && (c.end_bit + 7) / 8 * 8 == bits[n + k];
             if (!good) return fail(ctx, TDG_ERR_GZIP, std::string("gzip error in ") + path + ": corrupt BGZF member");
             ntok[k] = c.ntok;
+        }
+        if (text_len) {
+            const int go = sink.may_take(ctx, (size_t)text_len);
+            if (go < 0) return go;
+            if (go == 0) {                                   // a read limit within reach: the host feeder continues at this round's first member
+                foreign = true;
+                break;
+            }
         }
         if (text_len) {
             const uint32_t pieces = (uint32_t)((text_len + gzd::PIECE - 1) / gzd::PIECE);
@@ -1113,6 +1184,11 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
         // ---- which chunks continue the stream
         const gzc::Outcome o = st.chain(r, meta, symcap);
         uint64_t text_len = o.text_off.back();
+        if (o.accepted && text_len) {
+            const int go = sink.may_take(ctx, (size_t)text_len);
+            if (go < 0) return go;
+            if (go == 0) return TDG_STOP_ROUND;              // nothing of this round is used: the host feeder starts where it began
+        }
         uint32_t text_crc = 0;
         auto t4 = t3, t5 = t3;
         if (o.accepted && text_len) {
@@ -1258,9 +1334,9 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
     };
     while (!st.eof && !st.handover) {
         rc = one_round();
-        if (rc == TDG_ERR_NOMEM) {
+        if (rc == TDG_ERR_NOMEM || rc == TDG_STOP_ROUND) {
             st.handover = true;
-            st.why = "device memory";
+            st.why = rc == TDG_ERR_NOMEM ? "device memory" : "read limit within reach";
             pre_valid = false;
             break;
         }
@@ -1285,7 +1361,9 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
 // tdg_count_file's sink: whole lines go to the counting kernel, the rest is carried
 struct GzCountSink : GzSink {
     uint64_t reads_limit;
-    explicit GzCountSink(uint64_t limit) : reads_limit(limit) {}
+    LimitState *lim;
+    GzCountSink(uint64_t limit, LimitState *l) : reads_limit(limit), lim(l) {}
+    int may_take(tdg_ctx *ctx, size_t len) override { return lim ? limit_admits(ctx, *lim, len) : 1; }
     int text(tdg_ctx *ctx, uint8_t *d_buf, size_t &carry, size_t len) override
     {
         const size_t total = carry + len;
@@ -1337,7 +1415,7 @@ bool gz_device_wanted(const char *path, uint64_t reads_limit)
     if (const char *e = getenv("TDG_GZDEV")) {
         if (atoi(e) == 0) return false;
     }
-    if (reads_limit < ((uint64_t)1 << 61)) return false;           // with maxreads the reader stops early: small host pieces
+    if (reads_limit < ((uint64_t)1 << 60) && 4 * reads_limit <= ((uint64_t)64 << 20) + 2) return false;   // a small maxreads: the reader stops early, small host pieces
     uint64_t min_size = (uint64_t)8 << 20;
     if (const char *e = getenv("TDG_GZDEV_MIN")) min_size = strtoull(e, nullptr, 10);
     struct stat sb;
@@ -1893,8 +1971,8 @@ size_t file_chunk(const tdg_ctx *ctx, uint64_t reads_limit)
     // With a read limit the reference stops reading at the maxreads'th sequence line
     // (tagdigger_fun.py:272-273): feed smaller pieces, so that little is read, inflated and copied
     // beyond that point.
-    const bool limited = reads_limit < ((uint64_t)1 << 61);
-    return limited ? std::min<size_t>(ctx->chunk_bytes, (size_t)8 << 20) : ctx->chunk_bytes;
+    const bool small = reads_limit < ((uint64_t)1 << 60) && 4 * reads_limit <= ctx->chunk_bytes + 2;       // the limit's line can lie in the first piece
+    return small ? std::min<size_t>(ctx->chunk_bytes, (size_t)8 << 20) : ctx->chunk_bytes;
 }
 
 std::unique_ptr<FileReader> start_reader(tdg_ctx *ctx, const char *path, bool gz, size_t chunk, int set, const GzHandover *ho)
@@ -1921,8 +1999,9 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
     CK(cudaSetDevice(ctx->device));
     rc = ensure_slots(ctx);
     if (rc) return rc;
-    const bool limited = reads_limit < ((uint64_t)1 << 61);
     const size_t chunk = file_chunk(ctx, reads_limit);
+    LimitState lim;
+    lim.init(reads_limit, ctx->chunk_bytes);
 
     // a reader that was started for this file while the one before it was counted
     std::unique_ptr<FileReader> reader;
@@ -1950,7 +2029,7 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
     if (!reader && gz && gz_device_wanted(path, reads_limit)) {
         bool handled = false;
         size_t dcarry = 0;
-        GzCountSink sink(reads_limit);
+        GzCountSink sink(reads_limit, &lim);
         int drc = gz_device_feed(ctx, path, sink, handled, ho, dcarry, nullptr, &u8);
         if (drc == TDG_OK && handled && dcarry) {
             // the bytes behind the last line end become the host path's carry
@@ -1960,6 +2039,8 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
                 CK(cudaMemcpyAsync(cs.carry, ctx->gz_text.p, dcarry, cudaMemcpyDeviceToHost, ctx->stream));
                 CK(cudaStreamSynchronize(ctx->stream));
                 ctx->carry_len = dcarry;
+                lim.last_byte = cs.carry[dcarry - 1];
+                if (lim.careful) lim.ll.prev_cr = lim.last_byte == '\r';
             }
         }
         if (drc == TDG_OK && handled && !ho.active) {
@@ -1979,22 +2060,32 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
     if (!reader) reader = start_reader(ctx, path, gz != 0, chunk, set, ho.active ? &ho : nullptr);
 
     FileReader &fr = *reader;
+    const bool fdebug = getenv("TDG_FILE_DEBUG") != nullptr;
+    const auto ft0 = std::chrono::steady_clock::now();
+    double ms_wait = 0, ms_submit = 0;
     int bi = 0;
     int result = TDG_OK;
-    tdg::LineLimit ll;
     // the read with index maxreads-1 is line 4*maxreads-3: everything up to line end number
-    // 4*maxreads-2 is needed, nothing beyond it is looked at
-    if (limited) ll.remaining = reads_limit ? 4 * reads_limit - 2 : 1;
+    // 4*maxreads-2 is needed, nothing beyond it is looked at (LimitState)
     bool at_eof = false;
     for (;;) {
         FileReader::Buf &b = fr.bufs[bi];
+        const auto fw0 = std::chrono::steady_clock::now();
         {
             std::unique_lock<std::mutex> lk(fr.mu);
             fr.cv.wait(lk, [&] { return b.state == 1; });
         }
+        const auto fw1 = std::chrono::steady_clock::now();
+        ms_wait += std::chrono::duration<double, std::milli>(fw1 - fw0).count();
         if (b.err) { result = fail(ctx, b.err, b.msg); break; }
         if (b.n == 0) { at_eof = true; break; }
-        size_t use = limited ? ll.feed(b.p, b.n) : b.n;
+        size_t use = b.n;
+        {
+            const int go = limit_admits(ctx, lim, b.n);
+            if (go < 0) { result = go; break; }
+            if (go == 0) use = lim.ll.feed(b.p, b.n);
+            if (use) lim.last_byte = b.p[use - 1];
+        }
         // text mode: the bytes the loop reads must be valid UTF-8 (open(f, 'r'), errors='strict')
         if (b.high || u8.need) {
             long long bad = tdg::utf8_feed(u8, b.p, use);
@@ -2006,12 +2097,13 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
             u8.offset += use;
         }
         if (use) result = submit_impl(ctx, b.p, use, reads_limit, true);
+        ms_submit += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - fw1).count();
         {
             std::lock_guard<std::mutex> lk(fr.mu);
             b.state = 0;
         }
         fr.cv.notify_all();
-        if (result || ll.reached) break;
+        if (result || lim.ll.reached) break;
         bi = (bi + 1) % FileReader::NBUF;
     }
     reader.reset();                                          // stops and joins the reading thread
@@ -2022,6 +2114,10 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
     if (result == TDG_OK && totals) result = tdg_file_totals(ctx, totals);
+    if (fdebug)
+        fprintf(stderr, "tdg_count_file %s: %.2f ms (waiting for the reader %.2f, validate + submit %.2f, end of file + totals %.2f)\n", path,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ft0).count(), ms_wait, ms_submit,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ft0).count() - ms_wait - ms_submit);
     return result;
 }
 

@@ -393,3 +393,61 @@ def test_count_files_reads_the_next_file_ahead(tmp_path):
         counting.count_files(bckeys, tags)
     got = np.asarray(counting.find_tags_fastq(names[5], bcs[:4], tags))
     assert (got == want_rows[5]).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# the read limit (maxreads, default 5e9) on the host side of tdg_count_file
+
+def _with_engine(chunk_bytes):
+    """A process-wide engine with small pieces, so that megabytes behave like the tens of gigabytes the default
+    limit is about; returns a function that puts the old engine back."""
+    old = counting._engines.pop(0, None)
+    counting._engines[0] = _native.Engine(0, chunk_bytes=chunk_bytes)
+
+    def restore():
+        counting._engines.pop(0).close()
+        if old is not None:
+            counting._engines[0] = old
+    return restore
+
+
+@pytest.mark.parametrize("kind", ["plain", "gzip", "gzip on the device", "bgzf on the device", "crlf"])
+def test_read_limit_is_looked_for_only_where_it_can_be(tmp_path, monkeypatch, kind):
+    """Limits far beyond the file cost nothing (no pass over the bytes on the host, device gzip feed in use); limits
+    inside the file stop the reader exactly there -- a defect behind the limit is never met; counts equal the
+    oracle's for every limit."""
+    from feed_check import bgzf_compress
+    rng, bcs, tags = _tables(9)
+    fq, _ = synth.make_fastq(30000, bcs, tags, rng)
+    if kind == "crlf":
+        fq = fq.replace(b"\n", b"\r\n")
+    nreads = 30000
+    bad_tail = b"@x\nAC\xffGT\n+\nIIII\n"                      # invalid UTF-8: the reference would raise if it got there
+    p = str(tmp_path / ("r.fq" + ("" if kind in ("plain", "crlf") else ".gz")))
+    restore = _with_engine(1 << 16)
+    try:
+        if "device" in kind:
+            monkeypatch.setenv("TDG_GZDEV_MIN", "0")
+            monkeypatch.setenv("TDG_GZDEV_CHUNK", "32768")
+            monkeypatch.setenv("TDG_GZDEV_MAXCHUNKS", "40")
+        else:
+            monkeypatch.setenv("TDG_GZDEV", "0")
+        for limit in (5e9, 20000, 29999, 30000, 30001, 16500, 123):
+            damaged = limit <= nreads
+            data = fq + (bad_tail if damaged else b"")
+            with open(p, "wb") as fh:
+                if kind in ("plain", "crlf"):
+                    fh.write(data)
+                elif kind.startswith("bgzf"):
+                    fh.write(bgzf_compress(data, block=4000))
+                else:
+                    fh.write(gzip.compress(data, 1))
+            want, wtot = c_oracle.Counter(bcs, tags).count(fq, limit)[:2]
+            tot = []
+            got = np.asarray(counting.find_tags_fastq(p, bcs, tags, maxreads=limit, totals=tot))
+            assert tot[:3] == wtot and (got == want).all(), (kind, limit)
+        # ... and without a limit in the way the damaged tail IS met
+        with pytest.raises(UnicodeDecodeError):
+            counting.find_tags_fastq(p, bcs, tags, maxreads=nreads + 2)
+    finally:
+        restore()
