@@ -164,6 +164,11 @@ int         tdg_count_file(tdg_ctx *ctx, const char *path, int gz,
 int         tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit, uint64_t totals[4],
                             const char *next_path, int next_gz);
 
+/* How the last tdg_count_file fed its file: info[0] rounds of the device gzip feed, [1] chunks (or BGZF
+ * members) accepted, [2] 0 = the whole file went through the device, 1 = the host feeder took over
+ * somewhere, -1 = host feeder only. */
+int         tdg_last_file_info(tdg_ctx *ctx, int64_t info[3]);
+
 /* Frees the working buffers of the device-side gzip feed (tokens, symbols, windows, text: about ten
  * times the compressed bytes of a round, at most ~12 GB); they are kept between files otherwise. */
 int         tdg_release_scratch(tdg_ctx *ctx);

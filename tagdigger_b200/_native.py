@@ -34,7 +34,7 @@ NO_LIMIT = (1 << 63)
 
 EXPORTS = """tdg_abi_version tdg_create tdg_destroy tdg_last_error tdg_set_tags tdg_set_matrix
 tdg_bind_matrix tdg_zero_matrix tdg_begin_file tdg_reset_file tdg_submit tdg_end_file tdg_count_device
-tdg_count_lines_device tdg_count_file tdg_count_file2 tdg_gz_inflate_host tdg_release_scratch tdg_sync tdg_file_totals tdg_read_matrix tdg_matrix_min tdg_comm_unique_id tdg_comm_init tdg_allreduce_matrix tdg_finish
+tdg_count_lines_device tdg_count_file tdg_count_file2 tdg_last_file_info tdg_gz_inflate_host tdg_release_scratch tdg_sync tdg_file_totals tdg_read_matrix tdg_matrix_min tdg_comm_unique_id tdg_comm_init tdg_allreduce_matrix tdg_finish
 tdg_matrix_device_ptr tdg_stream tdg_stream_wait tdg_other_stream_wait tdg_host_alloc
 tdg_host_free tdg_device_alloc tdg_device_free tdg_memcpy_h2d tdg_memcpy_d2h tdg_launch_count
 tdg_timing_begin tdg_timing_end tdg_set_trim tdg_trim_batch tdg_split_batch tdg_split_begin tdg_split_block tdg_feed_open tdg_feed_read tdg_feed_close tdg_match_batch tdg_write_counts_csv tdg_write_geno_csv""".split()
@@ -113,6 +113,7 @@ def lib():
         "tdg_count_file": (i32, [vp, ctypes.c_char_p, i32, u64, vp]),
         "tdg_count_file2": (i32, [vp, ctypes.c_char_p, i32, u64, vp, ctypes.c_char_p, i32]),
         "tdg_gz_inflate_host": (i32, [vp, ctypes.c_char_p, vp, sz, vp, vp, vp]),
+        "tdg_last_file_info": (i32, [vp, vp]),
         "tdg_release_scratch": (i32, [vp]),
         "tdg_sync": (i32, [vp]),
         "tdg_file_totals": (i32, [vp, vp]),
@@ -339,6 +340,12 @@ class Engine(object):
         keys = ("upload", "scan", "decode", "resolve", "crc", "copy")
         return (out[:n.value].tobytes(), {"rounds": int(info[0]), "chunks": int(info[1]), "accepted": int(info[2]), "mode": int(info[3])},
                 dict(zip(keys, (round(float(x), 2) for x in ms))))
+
+    def last_file_info(self):
+        """How the last count_file fed its file: {rounds, accepted, mode} (mode 0 device, 1 host took over, -1 host only)."""
+        info = np.zeros(3, dtype=np.int64)
+        self._ck(self._L.tdg_last_file_info(self._h, info.ctypes.data))
+        return {"rounds": int(info[0]), "accepted": int(info[1]), "mode": int(info[2])}
 
     def release_scratch(self):
         """Free the working buffers of the device-side gzip feed (kept between files otherwise)."""

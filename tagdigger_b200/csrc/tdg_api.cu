@@ -213,6 +213,7 @@ struct tdg_ctx {
     Grow gz_hmeta, gz_hcrc, gz_htail;                                                                                       // pinned host
     cudaEvent_t gz_up[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t gz_pre = nullptr;
+    int64_t last_file[3] = {0, 0, 0};    // tdg_count_file: device gzip rounds, chunks accepted, 0 all on the device / 1 host feeder took over / -1 host feeder only
     bool gz_tables = false;
     uint32_t gz_op[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
@@ -2003,6 +2004,8 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
     LimitState lim;
     lim.init(reads_limit, ctx->chunk_bytes);
 
+    ctx->last_file[0] = ctx->last_file[1] = 0;
+    ctx->last_file[2] = -1;
     // a reader that was started for this file while the one before it was counted
     std::unique_ptr<FileReader> reader;
     if (ctx->ahead && ctx->ahead->path == path && ctx->ahead->gz == (gz != 0) && ctx->ahead->chunk == chunk) reader = std::move(ctx->ahead);
@@ -2030,7 +2033,11 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
         bool handled = false;
         size_t dcarry = 0;
         GzCountSink sink(reads_limit, &lim);
-        int drc = gz_device_feed(ctx, path, sink, handled, ho, dcarry, nullptr, &u8);
+        GzStats gst;
+        int drc = gz_device_feed(ctx, path, sink, handled, ho, dcarry, &gst, &u8);
+        ctx->last_file[0] = gst.rounds;
+        ctx->last_file[1] = gst.accepted;
+        ctx->last_file[2] = !handled ? -1 : (ho.active ? 1 : 0);
         if (drc == TDG_OK && handled && dcarry) {
             // the bytes behind the last line end become the host path's carry
             Slot &cs = ctx->slot[ctx->next_slot];
@@ -2124,6 +2131,16 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
 int tdg_count_file(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit, uint64_t totals[4])
 {
     return tdg_count_file2(ctx, path, gz, reads_limit, totals, nullptr, 0);
+}
+
+// How the last tdg_count_file fed its file: info[0] rounds of the device gzip feed, [1] chunks (or BGZF
+// members) they accepted, [2] 0 = the whole file went through the device, 1 = the host feeder took over
+// somewhere, -1 = host feeder only.
+int tdg_last_file_info(tdg_ctx *ctx, int64_t info[3])
+{
+    if (!ctx || !info) return fail(ctx, TDG_ERR_ARG, "null argument");
+    for (int i = 0; i < 3; i++) info[i] = ctx->last_file[i];
+    return TDG_OK;
 }
 
 // Gives the working buffers of the device-side gzip feed back (a 1.2 GB round holds about 12 GB:
