@@ -1197,8 +1197,8 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             if ((rc = grow(ctx, ctx->gz_windows, ((size_t)o.accepted + 1) * (gzl::WIN * 4 + 1), false))) return rc;
             if ((rc = grow(ctx, ctx->gz_lens, (size_t)o.accepted * 4, false))) return rc;
             if ((rc = grow(ctx, ctx->gz_offs, ((size_t)o.accepted + 1) * 8, false))) return rc;
-            if ((rc = grow(ctx, ctx->gz_crc, (size_t)pieces * 4 + 16, false))) return rc;
-            if ((rc = grow(ctx, ctx->gz_hcrc, (size_t)pieces * 4 + 16, true))) return rc;
+            if ((rc = grow(ctx, ctx->gz_crc, ((size_t)pieces + pieces / 256 + 2) * 4 + 16, false))) return rc;
+            if ((rc = grow(ctx, ctx->gz_hcrc, ((size_t)pieces / 256 + 4) * 4 + 16, true))) return rc;
             // the text buffer keeps the carried bytes in front
             const size_t need = round_up(carry + text_len, TDG_TILE_BYTES) + TDG_HALO_BYTES + 64;
             if (need > ctx->gz_text.cap) {
@@ -1283,20 +1283,40 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
             gzd::gz_ptr_take<<<8, gzd::WIN_THREADS, 0, ctx->stream>>>(w);
             CK(cudaGetLastError());
             ctx->launches += 2;
+            // the pieces' raw CRCs: 256 full pieces fold into one on the device, the host folds the rest
+            const uint32_t nfull = (uint32_t)(text_len / gzd::PIECE), groups = (nfull + 255) / 256;
+            uint32_t *d_group = d_flag + 1;
+            if (groups) {
+                gzd::CrcFoldArgs fa;
+                fa.piece = (const uint32_t *)ctx->gz_crc.p;
+                fa.nfull = nfull;
+                fa.group = d_group;
+                for (int j = 0; j < 8; j++) fa.op[j] = (uint32_t)crc32_combine_gen((z_off_t)((uint64_t)gzd::PIECE << j));
+                gzd::gz_crc_fold<<<groups, 256, 0, ctx->stream>>>(fa);
+                CK(cudaGetLastError());
+                ctx->launches++;
+            }
+            // host copy: [0] the high-bit flag, [1 .. groups] the group CRCs, [groups + 1] the last (partial) piece's
             uint32_t *hcrc = (uint32_t *)ctx->gz_hcrc.p;
-            CK(cudaMemcpyAsync(hcrc, ctx->gz_crc.p, (size_t)pieces * 4 + 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(hcrc, d_flag, ((size_t)groups + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            if (pieces > nfull)
+                CK(cudaMemcpyAsync(hcrc + groups + 1, (uint32_t *)ctx->gz_crc.p + nfull, 4, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             t4 = now();
-            // CRC-32 of the round's text from the pieces' raw CRCs
-            const uLong op_full = crc32_combine_gen((z_off_t)gzd::PIECE);
+            // CRC-32 of the round's text from the raw CRCs
             uLong raw = 0;
-            for (uint32_t p = 0; p + 1 < pieces; p++) raw = crc32_combine_op(raw, hcrc[p], op_full);
-            const uint64_t last_len = text_len - (uint64_t)(pieces - 1) * gzd::PIECE;
-            raw = crc32_combine_op(raw, hcrc[pieces - 1], crc32_combine_gen((z_off_t)last_len));
+            if (groups) {
+                const uLong op_group = crc32_combine_gen((z_off_t)((uint64_t)gzd::PIECE * 256));
+                for (uint32_t g = 0; g + 1 < groups; g++) raw = crc32_combine_op(raw, hcrc[1 + g], op_group);
+                const uint64_t last_group = (uint64_t)(nfull - (groups - 1) * 256u) * gzd::PIECE;
+                raw = crc32_combine_op(raw, hcrc[groups], crc32_combine_gen((z_off_t)last_group));
+            }
+            if (pieces > nfull) raw = crc32_combine_op(raw, hcrc[groups + 1], crc32_combine_gen((z_off_t)(text_len - (uint64_t)nfull * gzd::PIECE)));
             text_crc = (uint32_t)(raw ^ crc32_combine_op(0xFFFFFFFFul, 0, crc32_combine_gen((z_off_t)text_len)) ^ 0xFFFFFFFFul);
+            const uint32_t high_flag = hcrc[0];
             // text mode: bytes >= 0x80 must form valid UTF-8 (open(f, 'rt'))
             if (u8) {
-                if ((hcrc[pieces] & 0x80u) || u8->need) {
+                if ((high_flag & 0x80u) || u8->need) {
                     std::vector<uint8_t> host(text_len);
                     CK(cudaMemcpy(host.data(), (uint8_t *)ctx->gz_text.p + carry, text_len, cudaMemcpyDeviceToHost));
                     long long bad = tdg::utf8_feed(*u8, host.data(), host.size());

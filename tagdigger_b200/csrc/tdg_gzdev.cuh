@@ -364,6 +364,34 @@ __global__ void __launch_bounds__(RES_THREADS) gz_resolve(const ResArgs a)
     if ((tid & 31u) == 0 && (any & 0x80u)) atomicOr(a.flag, 0x80u);
 }
 
+// The raw CRCs of 256 consecutive FULL pieces become one (the host then folds one value per 4 MiB of
+// text instead of one per 16 KiB).  A group that has fewer pieces (the last one) sits against the end
+// of its frame: the empty slots in front are zero and stay zero under the shifts.
+struct CrcFoldArgs {
+    const uint32_t *piece;       // [nfull]
+    uint32_t nfull;
+    uint32_t *group;             // [ceil(nfull / 256)]
+    uint32_t op[8];              // x^(8 * PIECE * 2^j) modulo the polynomial
+};
+
+__global__ void __launch_bounds__(256) gz_crc_fold(const CrcFoldArgs a)
+{
+    __shared__ uint32_t s_part[256];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t first = blockIdx.x * 256u;
+    const uint32_t cnt = a.nfull - first < 256u ? a.nfull - first : 256u;
+    const uint32_t shift = 256u - cnt;
+    s_part[tid] = tid >= shift ? a.piece[first + (tid - shift)] : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t stride = 1u << j;
+        if ((tid & (2 * stride - 1)) == 0) s_part[tid] = gf_mul(a.op[j], s_part[tid]) ^ s_part[tid + stride];
+        __syncthreads();
+    }
+    if (tid == 0) a.group[blockIdx.x] = s_part[0];
+}
+
 // BGZF: the CRC-32 of every member's bytes (at most 64 KiB each), one warp per member.  Lane l takes
 // the l-th 2 KiB of the member laid against the END of a 64 KiB frame (the lanes in front of a short
 // member have nothing: a register that is still zero stays zero under the shifts); the lane that
