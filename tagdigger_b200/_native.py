@@ -17,7 +17,7 @@ _CSRC = os.path.join(_HERE, "csrc")
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_PATH = os.environ.get("TDG_LIB") or os.path.join(_HERE, "libtagdigger_b200.so")   # TDG_LIB: tuning builds (scripts/sweep.py)
 _SOURCES = ["tdg_api.cu", "tdg_text.h", "tdg_comm.h", "tdg_kernel.cuh", "tdg_match.h", "tdg_tables.h", "tdg_trim.cuh", "tdg_split.cuh", "tdg_feed.h", "tdg_pgz.h", "tdg_csv.h",
-            "tdg_gzlane.h", "tdg_gzchain.h", "tdg_gzdev.cuh", "tdg_pool.h"]
+            "tdg_gzlane.h", "tdg_gzchain.h", "tdg_gzdev.cuh", "tdg_gzfeed.cuh", "tdg_pool.h"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "20014,20011", "-shared"]
