@@ -1239,7 +1239,7 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
     rc = ensure_file_bufs(ctx, set);
     if (rc) return rc;
     // ... and the one for the file that comes next (files the device gzip feed takes are not read ahead)
-    if (next_path && *next_path && std::string(next_path) != path && !(next_gz && gz_device_wanted(next_path, reads_limit))) {
+    if (next_path && *next_path && std::string(next_path) != path && !(next_gz && gz_device_wanted(ctx, next_path, reads_limit))) {
         struct stat sb;
         if (stat(next_path, &sb) == 0 && S_ISREG(sb.st_mode)) {
             rc = ensure_file_bufs(ctx, set ^ 1);
@@ -1254,7 +1254,7 @@ int tdg_count_file2(tdg_ctx *ctx, const char *path, int gz, uint64_t reads_limit
     // feeder below, which resumes exactly where the device feed stopped.
     tdg::Utf8State u8;
     GzHandover ho;
-    if (!reader && gz && gz_device_wanted(path, reads_limit)) {
+    if (!reader && gz && gz_device_wanted(ctx, path, reads_limit)) {
         bool handled = false;
         size_t dcarry = 0;
         GzCountSink sink(reads_limit, &lim);

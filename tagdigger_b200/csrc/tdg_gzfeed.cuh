@@ -193,7 +193,7 @@ int gz_device_feed_bgzf(tdg_ctx *ctx, const char *path, const GzMap &map, GzSink
     carry = 0;
     size_t off = 0;
     uint64_t delivered = 0;
-    bool foreign = false;
+    bool foreign = false, oom = false;         // oom: a buffer could not be had -- the host feeder continues at this round's first member
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
         return std::chrono::duration<double, std::milli>(b - a).count();
@@ -225,15 +225,15 @@ int gz_device_feed_bgzf(tdg_ctx *ctx, const char *path, const GzMap &map, GzSink
         if (mem.empty()) break;
         const uint32_t n = (uint32_t)mem.size();
         const size_t nb = end - off, nwords = (nb + 3) / 4;
-        if ((rc = gz_upload(ctx, map, path, threads, up_i, 0, off, end, ctx->stream))) return rc;
-        if ((rc = grow(ctx, ctx->gz_syms, (size_t)n * tokcap * 2, false))) return rc;
-        if ((rc = grow(ctx, ctx->gz_sym2, (size_t)n * symcap * 2, false))) return rc;
-        if ((rc = grow(ctx, ctx->gz_meta, (size_t)n * sizeof(gzl::Meta), false))) return rc;
-        if ((rc = grow(ctx, ctx->gz_hmeta, (size_t)n * sizeof(gzl::Meta), true))) return rc;
-        if ((rc = grow(ctx, ctx->gz_cold, (size_t)(n + 8) * gzl::COLD_U16 * 2, false))) return rc;
-        if ((rc = grow(ctx, ctx->gz_offs, ((size_t)n * 3 + 1) * 8, false))) return rc;       // [n] start bits, [n] end bits, [n + 1] text offsets
-        if ((rc = grow(ctx, ctx->gz_lens, (size_t)n * 4, false))) return rc;
-        if ((rc = grow(ctx, ctx->gz_ntok, (size_t)n * 4, false))) return rc;
+        if ((rc = gz_upload(ctx, map, path, threads, up_i, 0, off, end, ctx->stream))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
+        if ((rc = grow(ctx, ctx->gz_syms, (size_t)n * tokcap * 2, false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
+        if ((rc = grow(ctx, ctx->gz_sym2, (size_t)n * symcap * 2, false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
+        if ((rc = grow(ctx, ctx->gz_meta, (size_t)n * sizeof(gzl::Meta), false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
+        if ((rc = grow(ctx, ctx->gz_hmeta, (size_t)n * sizeof(gzl::Meta), true))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
+        if ((rc = grow(ctx, ctx->gz_cold, (size_t)(n + 8) * gzl::COLD_U16 * 2, false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
+        if ((rc = grow(ctx, ctx->gz_offs, ((size_t)n * 3 + 1) * 8, false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }       // [n] start bits, [n] end bits, [n + 1] text offsets
+        if ((rc = grow(ctx, ctx->gz_lens, (size_t)n * 4, false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
+        if ((rc = grow(ctx, ctx->gz_ntok, (size_t)n * 4, false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
         std::vector<uint64_t> bits(2 * (size_t)n), text_off(n + 1, 0);
         std::vector<uint32_t> lens(n);
         for (uint32_t k = 0; k < n; k++) {
@@ -285,16 +285,16 @@ int gz_device_feed_bgzf(tdg_ctx *ctx, const char *path, const GzMap &map, GzSink
         }
         if (text_len) {
             const uint32_t pieces = (uint32_t)((text_len + gzd::PIECE - 1) / gzd::PIECE);
-            if ((rc = grow(ctx, ctx->gz_crc, ((size_t)pieces + n) * 4 + 16, false))) return rc;
-            if ((rc = grow(ctx, ctx->gz_hcrc, ((size_t)n + 1) * 4 + 16, true))) return rc;
-            if ((rc = grow(ctx, ctx->gz_windows, gzl::WIN * 4, false))) return rc;          // (never read: a member has no history before it)
+            if ((rc = grow(ctx, ctx->gz_crc, ((size_t)pieces + n) * 4 + 16, false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
+            if ((rc = grow(ctx, ctx->gz_hcrc, ((size_t)n + 1) * 4 + 16, true))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
+            if ((rc = grow(ctx, ctx->gz_windows, gzl::WIN * 4, false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }          // (never read: a member has no history before it)
             const size_t need = round_up(carry + text_len, TDG_TILE_BYTES) + TDG_HALO_BYTES + 64;
             if (need > ctx->gz_text.cap) {
                 if (carry) {
-                    if ((rc = grow(ctx, ctx->gz_carry, carry, false))) return rc;
+                    if ((rc = grow(ctx, ctx->gz_carry, carry, false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
                     CK(cudaMemcpyAsync(ctx->gz_carry.p, ctx->gz_text.p, carry, cudaMemcpyDeviceToDevice, ctx->stream));
                 }
-                if ((rc = grow(ctx, ctx->gz_text, need, false))) return rc;
+                if ((rc = grow(ctx, ctx->gz_text, need, false))) { if (rc == TDG_ERR_NOMEM) { oom = true; break; } return rc; }
                 if (carry) CK(cudaMemcpyAsync(ctx->gz_text.p, ctx->gz_carry.p, carry, cudaMemcpyDeviceToDevice, ctx->stream));
             }
             CK(cudaMemcpyAsync(ctx->gz_ntok.p, ntok.data(), ntok.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -370,13 +370,13 @@ int gz_device_feed_bgzf(tdg_ctx *ctx, const char *path, const GzMap &map, GzSink
             fprintf(stderr, "gzdev BGZF round: %u members, %zu compressed bytes, %llu bytes of text; upload + decode %.1f, rest %.1f ms\n", n, nb,
                     (unsigned long long)text_len, ms(t0, t1), ms(t1, now()));
     }
-    if (foreign || off < map.n) {
+    if (foreign || oom || off < map.n) {
         // something that is not a BGZF member follows (or the file stops inside one): the host feeder's to judge
         ho.active = true;
         ho.bgzf = true;
         ho.bgzf_off = off;
         ho.delivered = delivered;
-        ho.why = "not a BGZF member";
+        ho.why = oom ? "device memory" : "not a BGZF member";
     }
     return TDG_OK;
 }
@@ -402,16 +402,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
     map.p = (const uint8_t *)mp;
     if (tdg::Feeder::is_bgzf(map.p, std::min<size_t>(map.n, 1024))) {
         handled = true;
-        int brc = gz_device_feed_bgzf(ctx, path, map, sink, ho, carry, stats, u8);
-        if (brc == TDG_ERR_NOMEM) {
-            // (a buffer that cannot be had: nothing sensible to resume from in the middle of a round -- only
-            // when nothing has been delivered yet does the host feeder simply start over)
-            if (!ho.active && carry == 0 && (!stats || stats->rounds == 0)) {
-                handled = false;
-                return TDG_OK;
-            }
-        }
-        return brc;
+        return gz_device_feed_bgzf(ctx, path, map, sink, ho, carry, stats, u8);
     }
     gzc::Stream st;
     if (!st.open(map.p, map.n)) return TDG_OK;
@@ -710,7 +701,7 @@ int gz_device_feed(tdg_ctx *ctx, const char *path, GzSink &sink, bool &handled, 
                     r.nchunks, chunk >> 10, o.accepted, (unsigned long long)text_len, ms(t0, t1), prefetched ? " (prefetched)" : "", ms(t1, t2),
                     ms(t2, t3), ms_prefetch, ms(t3, t4), ms(t4, t5),
                     ms(t5, t6), st.handover ? "  -> host reader: " : "", st.handover ? st.why : "");
-            return TDG_OK;
+        return TDG_OK;
     };
     while (!st.eof && !st.handover) {
         rc = one_round();
@@ -790,12 +781,13 @@ struct GzCopySink : GzSink {
     }
 };
 
-bool gz_device_wanted(const char *path, uint64_t reads_limit)
+bool gz_device_wanted(const tdg_ctx *ctx, const char *path, uint64_t reads_limit)
 {
     if (const char *e = getenv("TDG_GZDEV")) {
         if (atoi(e) == 0) return false;
     }
-    if (reads_limit < ((uint64_t)1 << 60) && 4 * reads_limit <= ((uint64_t)64 << 20) + 2) return false;   // a small maxreads: the reader stops early, small host pieces
+    // a maxreads whose line can lie in the first piece (LimitState::init): the reader stops early, small host pieces
+    if (reads_limit < ((uint64_t)1 << 60) && 4 * reads_limit <= (uint64_t)ctx->chunk_bytes + 2) return false;
     uint64_t min_size = (uint64_t)8 << 20;
     if (const char *e = getenv("TDG_GZDEV_MIN")) min_size = strtoull(e, nullptr, 10);
     struct stat sb;

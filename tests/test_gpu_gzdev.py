@@ -411,7 +411,7 @@ def _with_engine(chunk_bytes):
     return restore
 
 
-@pytest.mark.parametrize("kind", ["plain", "gzip", "gzip on the device", "bgzf on the device", "crlf"])
+@pytest.mark.parametrize("kind", ["plain", "gzip", "gzip on the device", "gzip on the device, tiny rounds", "bgzf on the device", "crlf"])
 def test_read_limit_is_looked_for_only_where_it_can_be(tmp_path, monkeypatch, kind):
     """Limits far beyond the file cost nothing (no pass over the bytes on the host, device gzip feed in use); limits
     inside the file stop the reader exactly there -- a defect behind the limit is never met; counts equal the
@@ -428,8 +428,8 @@ def test_read_limit_is_looked_for_only_where_it_can_be(tmp_path, monkeypatch, ki
     try:
         if "device" in kind:
             monkeypatch.setenv("TDG_GZDEV_MIN", "0")
-            monkeypatch.setenv("TDG_GZDEV_CHUNK", "32768")
-            monkeypatch.setenv("TDG_GZDEV_MAXCHUNKS", "40")
+            monkeypatch.setenv("TDG_GZDEV_CHUNK", "16384" if "tiny" in kind else "32768")
+            monkeypatch.setenv("TDG_GZDEV_MAXCHUNKS", "2" if "tiny" in kind else "40")
         else:
             monkeypatch.setenv("TDG_GZDEV", "0")
         for limit in (5e9, 20000, 29999, 30000, 30001, 16500, 123):
@@ -446,6 +446,13 @@ def test_read_limit_is_looked_for_only_where_it_can_be(tmp_path, monkeypatch, ki
             tot = []
             got = np.asarray(counting.find_tags_fastq(p, bcs, tags, maxreads=limit, totals=tot))
             assert tot[:3] == wtot and (got == want).all(), (kind, limit)
+            info = counting.get_engine(0).last_file_info()
+            if "device" in kind and limit == 5e9:
+                assert info["mode"] == 0 and info["rounds"] >= 1, (kind, info)         # the default limit keeps nothing from the device
+            if "tiny" in kind and limit == 20000:
+                # rounds of 65 KB of text fit under the limit's line for a while: the device feeds them, then the host
+                # feeder takes over and stops at the limit
+                assert info["mode"] == 1 and info["rounds"] >= 10, info
         # ... and without a limit in the way the damaged tail IS met
         with pytest.raises(UnicodeDecodeError):
             counting.find_tags_fastq(p, bcs, tags, maxreads=nreads + 2)
